@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: long-running CPU test")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_oracle():
+    """The oracle's C++ part (test infrastructure) is built on demand."""
+    so = os.path.join(REPO, "oracle", "_build", "librvo2_ref.so")
+    src = os.path.join(REPO, "oracle", "rvo2_ref.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(REPO, "oracle")])

@@ -1,0 +1,74 @@
+"""Pins oracle/crowd_env.py (+ oracle/rvo2_ref.cpp) against golden vectors recorded from the
+UNMODIFIED reference environment (tools/make_golden.py).
+
+Integer outputs (done, info code, detected_human_num, visibility) must match bit-exactly;
+float outputs within 1e-6 (fp32 observations) / 1e-9 (fp64 state) — slack only covers
+libm/BLAS last-bit differences between machines, the oracle uses the reference's own call forms.
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from oracle.crowd_env import CrowdEnvOracle, EnvConfig
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5"]
+
+
+def load_case(name):
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture %s missing" % name)
+    g = np.load(path, allow_pickle=False)
+    case = ast.literal_eval(str(g["meta"][0]))
+    cfg = EnvConfig(human_num=case["human_num"], predict_method=case["predict_method"],
+                    randomize_attributes=case["randomize"], random_goal_changing=case["goal_changing"])
+    return g, case, cfg
+
+
+def check_state(st, g, t, k, tol=1e-9):
+    np.testing.assert_allclose(st["robot"], g["st_robot"][t, k], rtol=0, atol=tol)
+    for key in ("hpx", "hpy", "hvx", "hvy", "hgx", "hgy", "hrad", "hvpref", "belief"):
+        np.testing.assert_allclose(st[key], g["st_" + key][t, k], rtol=0, atol=tol, err_msg=key)
+    assert np.array_equal(st["vis"], g["st_vis"][t, k])
+    assert st["global_time"] == g["st_global_time"][t, k]
+    np.testing.assert_allclose(st["potential"], g["st_potential"][t, k], rtol=0, atol=tol)
+    np.testing.assert_allclose(st["nd_global"], g["st_nd_global"][t, k], rtol=0, atol=tol)
+    assert np.array_equal(st["sim_exists"], g["st_sim_exists"][t, k])
+    if g["st_traj"][t, k].size:
+        np.testing.assert_allclose(st["traj"], g["st_traj"][t, k], rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    g, case, cfg = load_case(name)
+    T, N = g["actions"].shape[:2]
+    obs_keys = [k[3:] for k in g.files if k.startswith("ob_")]
+    for k in range(N):
+        env = CrowdEnvOracle(cfg, case["seed"] + k, case["nenv"], "train")
+        ob = env.reset()
+        for key in obs_keys:
+            np.testing.assert_allclose(ob[key], g["ob_" + key][0, k], rtol=0, atol=1e-6, err_msg=key)
+        check_state(env.get_state(), g, 0, k)
+        for t in range(T):
+            a = g["actions"][t, k].copy()
+            ob, rew, done, info = env.worker_step(a)
+            assert bool(done) == bool(g["done"][t, k]), (name, k, t)
+            assert info["info"] == g["info"][t, k], (name, k, t)
+            np.testing.assert_allclose(rew, g["reward"][t, k], rtol=0, atol=1e-9)
+            ha = np.asarray(env.last_human_actions, dtype=np.float32)
+            ref_ha = g["human_actions"][t, k]
+            ok = ~np.isnan(ref_ha[:, 0])
+            assert np.array_equal(ha[ok], ref_ha[ok]), (name, k, t)        # bit-exact fp32 ORCA output
+            diag = np.asarray(env.last_orca_diag)
+            assert np.array_equal(diag[ok, 0], g["orca_nlines"][t, k][ok])
+            assert np.array_equal(diag[ok, 1], g["orca_fail"][t, k][ok])
+            for key in obs_keys:
+                if g["ob_" + key].dtype == bool:
+                    assert np.array_equal(ob[key], g["ob_" + key][t + 1, k])
+                else:
+                    np.testing.assert_allclose(ob[key], g["ob_" + key][t + 1, k], rtol=0, atol=1e-6,
+                                               err_msg="%s t=%d" % (key, t))
+            check_state(env.get_state(), g, t + 1, k)
