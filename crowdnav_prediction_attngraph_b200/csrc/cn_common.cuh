@@ -1,0 +1,94 @@
+// Shared definitions for the crowd-navigation rollout engine (sm_100a).
+//
+// Everything that is pure per-environment arithmetic is written as CN_HD (host+device)
+// functions so the SAME source can be compiled by g++ into a unit-test harness
+// (tests/cpu_harness) and checked against the oracle without a GPU.  The harness is
+// test infrastructure only: the product entry points (cn_api.cu) launch CUDA kernels and
+// fail loudly if no device is present.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CN_HD __host__ __device__ __forceinline__
+#define CN_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CN_HD inline
+#define CN_HD_NOINLINE inline
+#endif
+
+// info codes (crowd_sim/envs/utils/info.py): Nothing, Timeout, Collision, ReachGoal, Danger
+enum { CN_INFO_NOTHING = 0, CN_INFO_TIMEOUT = 1, CN_INFO_COLLISION = 2, CN_INFO_REACHGOAL = 3, CN_INFO_DANGER = 4 };
+
+// Device-side mirror of cn_config (include/crowdnav_b200.h) with derived constants.
+struct CnParams {
+  int N;            // environments in this shard
+  int H;            // humans per environment (sim.human_num, human_num_range == 0)
+  int P;            // sim.predict_steps
+  int W;            // spatial_edges row width: 2*(P+1) (CrowdSimPred) or 2 (CrowdSimVarNum)
+  int const_vel;    // 1: CrowdSimPred-v0 'const_vel'; 0: CrowdSimVarNum-v0 'none'
+  int randomize;    // env.randomize_attributes
+  int goal_changing;      // humans.random_goal_changing
+  int end_goal_changing;  // humans.end_goal_changing
+  int sort_humans;        // args.sort_humans
+  int nenv_total;         // env.nenv (global, across shards)
+  uint32_t seed_base;     // thisSeed of env 0 of this shard = seed + rank_offset
+  uint32_t phase_offset;  // 2000 for 'train' (crowd_sim_var_num.py:329-334)
+  double time_step, time_limit, pred_dt;   // pred_dt = time_step * pred_interval
+  double circle_radius, arena_size;
+  double discomfort_dist, discomfort_penalty_factor, success_reward, collision_penalty;
+  double human_radius, human_vpref, robot_radius, robot_vpref, sensor_range;
+  double human_fov, robot_fov;             // radians (config value * pi)
+  double goal_change_chance;
+  double orca_safety_space, orca_neighbor_dist;   // neighbor_dist: initial value of the global
+  float orca_time_horizon;
+};
+
+// Struct-of-arrays environment state in HBM.  Per-human arrays are [N][H] (human index
+// fastest) so that the (env, human) thread mapping of the step kernel is coalesced.
+struct CnState {
+  // robot
+  double *rpx, *rpy, *rgx, *rgy;     // fp64 like the reference's Python floats
+  float *rvx, *rvy;                  // fp32-valued (clipped action)
+  double *potential;                 // -|goal - pos| bookkeeping (crowd_sim_var_num.py:351-352)
+  double *fut_pen;                   // future-intrusion penalty of the STORED prediction (crowd_sim_pred.py:222-231)
+  double *nd_global;                 // process-global config.orca.neighbor_dist (agent.py:21-22)
+  double *ep_ret;                    // bench.Monitor episode return
+  int *ep_len;
+  int *step_count;                   // global_time = step_count * time_step
+  uint32_t *case_counter;            // case_counter['train']
+  // humans [N][H]
+  double *hpx, *hpy, *hgx, *hgy, *hrad, *hvpref;
+  float *hvx, *hvy;
+  // robot belief (last_human_states) [N][H]
+  double *bpx, *bpy, *bvx, *bvy, *brad;
+  uint8_t *vis;                      // human_visibility (to the robot)
+  // per-human cached rvo2 simulator parameters (crowd_nav/policy/orca.py:79-95): frozen at creation
+  uint8_t *sim_exists;               // [N][H]
+  float *sim_nd, *sim_rself, *sim_vmax;   // [N][H]
+  float *sim_rother;                 // [N][H][H] (only when randomize)
+  // legacy numpy MT19937 per environment
+  uint32_t *mt;                      // [N][624]
+  int *mt_pos;                       // [N]
+  // diagnostics of the last step (parity tests)
+  float *last_hvx, *last_hvy;        // ORCA output velocities [N][H]
+  int *orca_nlines, *orca_fail;      // [N][H]
+};
+
+// Caller-owned observation/result buffers (PyTorch tensors in the host mirror).
+struct CnObs {
+  float *robot_node;          // [N,1,7]
+  float *temporal_edges;      // [N,1,2]
+  float *spatial_edges;       // [N,H,W]
+  float *detected_human_num;  // [N,1]
+  uint8_t *visible_masks;     // [N,H] or nullptr
+};
+
+struct CnStepOut {
+  float *reward;       // [N]
+  uint8_t *done;       // [N]
+  int32_t *info;       // [N] CN_INFO_*
+  float *info_aux;     // [N] Danger.min_dist (0 in train phase)
+  double *ep_ret;      // [N] episode return at done (bench.Monitor 'r')
+  int32_t *ep_len;     // [N] episode length at done
+};

@@ -1,0 +1,463 @@
+// Per-environment step / reset / observation logic of the crowd simulator, written as
+// "phase" functions for the (environment, human) thread mapping of the step kernel.
+//
+// Follows the reference's order of operations exactly:
+//   crowd_sim/envs/crowd_sim_pred.py:100-213       CrowdSimPred.step
+//   crowd_sim/envs/crowd_sim_var_num.py:303-363    reset / generate_robot_humans
+//   crowd_sim/envs/crowd_sim_var_num.py:465-561    calc_reward (train phase) + crowd_sim_pred.py:216-233
+//   crowd_sim/envs/crowd_sim_pred.py:62-97         generate_ob  (VarNum: crowd_sim_var_num.py:233-279)
+//   crowd_sim/envs/crowd_sim.py:243-273,513-572    belief update / visibility
+//   crowd_sim/envs/crowd_sim.py:415-450            update_human_goals_randomly
+//   crowd_sim/envs/crowd_sim_var_num.py:116-146    generate_circle_crossing_human
+//   crowd_nav/policy/orca.py:64-117                per-human cached rvo2 simulator
+//   crowd_nav/policy/srnn.py:17-33                 clip_action (fp32)
+//
+// Numeric conventions (what makes done/collision masks bit-exact against the oracle):
+//   * positions, goals, radii, potential, reward: fp64, same expression trees as the Python;
+//   * numpy's 1-D `norm((a, b))` is sqrt(dot) with dot = fma(b, b, a*a)  -> cn_norm_dot();
+//     numpy's axis-norm and fp32 dot are plain a*a + b*b               -> cn_norm_plain();
+//   * ORCA in fp32 without contraction (cn_orca.cuh); this TU is built with --fmad=false.
+//
+// Between phases the caller synchronises the threads of one environment (block barrier
+// on the GPU; a plain loop over humans in the CPU test harness).
+#pragma once
+#include "cn_common.cuh"
+#include "cn_rng.cuh"
+#include "cn_orca.cuh"
+
+#define CN_PI 3.141592653589793
+
+CN_HD double cn_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+CN_HD double cn_norm_dot(double x, double y) { return sqrt(cn_fma(y, y, x * x)); }
+CN_HD double cn_norm_plain(double x, double y) { return sqrt(x * x + y * y); }
+CN_HD double cn_dot2(double a0, double a1, double b0, double b1) { return cn_fma(a1, b1, a0 * b0); }
+
+// Working set of ONE environment while a step is in flight (shared memory on the GPU).
+struct CnEnvSh {
+  // human arrays, length H
+  double *px, *py, *gx, *gy, *rad, *vpref;
+  float *vx, *vy;        // current velocities (fp32-valued)
+  float *fx, *fy;        // positions narrowed to fp32 (what the Cython boundary hands to rvo2)
+  float *nvx, *nvy;      // ORCA output
+  double *t0;            // scratch: closest distance / sort key
+  double *t1;            // scratch: per-human future penalty
+  uint8_t *visr;         // visible to the robot
+  // robot + scalars
+  double rpx, rpy, rgx, rgy;
+  float rvx, rvy;
+  float ax, ay;          // clipped action
+  double reward;
+  int done, info, reset_flag;
+  int nvis;
+};
+
+CN_HD size_t cn_idx(const CnParams& p, int e, int h) { return (size_t)e * p.H + h; }
+
+// ------------------------------------------------------------------------------------------
+// visibility helpers (crowd_sim.py:513-552)
+CN_HD bool cn_in_fov(double x1, double y1, double vx1, double vy1, double x2, double y2, double fov) {
+  if (fov >= 2.0 * CN_PI) {
+    // offset = arccos(.) in [0, pi] <= fov/2 unless NaN (coincident centres -> 0/0)
+    return !(x1 == x2 && y1 == y2);
+  }
+  const double th = atan2(vy1, vx1);
+  double f0 = cos(th), f1 = sin(th);
+  double d0 = x2 - x1, d1 = y2 - y1;
+  const double nf = cn_norm_dot(f0, f1), nd = cn_norm_dot(d0, d1);
+  f0 = f0 / nf; f1 = f1 / nf; d0 = d0 / nd; d1 = d1 / nd;
+  double c = cn_dot2(f0, f1, d0, d1);
+  if (c != c) return false;
+  c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+  return fabs(acos(c)) <= fov / 2;
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase LOAD: every (env, human) thread loads its human; the leader (h == 0) loads the robot
+// and clips the action (srnn.py:17-33, fp32).
+CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h,
+                         const float* action /* [N,2] or null (reset) */) {
+  const size_t i = cn_idx(p, e, h);
+  s.px[h] = g.hpx[i]; s.py[h] = g.hpy[i]; s.gx[h] = g.hgx[i]; s.gy[h] = g.hgy[i];
+  s.rad[h] = g.hrad[i]; s.vpref[h] = g.hvpref[i];
+  s.vx[h] = g.hvx[i]; s.vy[h] = g.hvy[i];
+  s.fx[h] = (float)s.px[h]; s.fy[h] = (float)s.py[h];
+  if (h == 0) {
+    s.rpx = g.rpx[e]; s.rpy = g.rpy[e]; s.rgx = g.rgx[e]; s.rgy = g.rgy[e];
+    s.rvx = g.rvx[e]; s.rvy = g.rvy[e];
+    s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0;
+    if (action) {
+      float ax = action[2 * e], ay = action[2 * e + 1];
+      const float nrm = sqrtf(ax * ax + ay * ay);          // np.linalg.norm(float32[2])
+      const float vp = (float)p.robot_vpref;
+      if (nrm > vp) { ax = ax / nrm * vp; ay = ay / nrm * vp; }
+      s.ax = ax; s.ay = ay;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase ORCA: one thread = one human's rvo2 simulator (crowd_sim.py:680-703, orca.py:64-117).
+template <int MAXH>
+CN_HD void cn_phase_orca(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnLineStore lines) {
+  const int H = p.H;
+  const size_t i = cn_idx(p, e, h);
+  const double fov = p.human_fov;
+  float nd, rself, vmax;
+  const double pad = 0.01;
+  // --- cached simulator parameters (frozen at creation; orca.py:80-95 only updates pos/vel)
+  if (p.randomize) {
+    if (!g.sim_exists[i]) {
+      g.sim_nd[i] = (float)g.nd_global[e];
+      g.sim_rself[i] = (float)(s.rad[h] + pad + p.orca_safety_space);
+      g.sim_vmax[i] = (float)s.vpref[h];
+      for (int j = 0; j < H; ++j) {
+        if (j == h) continue;
+        const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
+        g.sim_rother[i * H + j] = (float)((v ? s.rad[j] : 0.3) + pad + p.orca_safety_space);
+      }
+      g.sim_exists[i] = 1;
+    }
+    nd = g.sim_nd[i]; rself = g.sim_rself[i]; vmax = g.sim_vmax[i];
+  } else {
+    // non-randomised attributes never change, so the frozen-at-creation values equal these
+    nd = (float)p.orca_neighbor_dist;
+    rself = (float)(s.rad[h] + pad + p.orca_safety_space);
+    vmax = (float)s.vpref[h];
+    g.sim_exists[i] = 1;
+  }
+  // --- preferred velocity (orca.py:98-100), fp64 then narrowed
+  const double dvx = s.gx[h] - s.px[h], dvy = s.gy[h] - s.py[h];
+  const double speed = cn_norm_dot(dvx, dvy);
+  const CnF2 pref = speed > 1 ? f2((float)(dvx / speed), (float)(dvy / speed)) : f2((float)dvx, (float)dvy);
+
+  const CnF2 pos = f2(s.fx[h], s.fy[h]);
+  const CnF2 vel = f2(s.vx[h], s.vy[h]);
+  const float rangeSq = nd * nd;
+  const float invTimeHorizon = 1.0f / p.orca_time_horizon;
+  const float timeStep = (float)p.time_step;
+
+  // --- neighbour selection: dist^2 < neighborDist^2, ascending, ties in insertion (index) order
+  float dist[MAXH];
+  uint32_t dummy_mask[(MAXH + 31) / 32];
+  for (int w = 0; w < (MAXH + 31) / 32; ++w) dummy_mask[w] = 0u;
+  for (int j = 0; j < H; ++j) {
+    if (j == h) { dist[j] = -1.0f; continue; }
+    const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
+    if (!v) dummy_mask[j >> 5] |= (1u << (j & 31));
+    const CnF2 op = v ? f2(s.fx[j], s.fy[j]) : f2(7.0f, 7.0f);     // dummy_human (crowd_sim.py:130-133)
+    const float d = f2abssq(f2sub(pos, op));
+    dist[j] = (d < rangeSq) ? d : -1.0f;
+  }
+  int nl = 0;
+  for (int j = 0; j < H; ++j) {
+    const float dj = dist[j];
+    if (dj < 0.0f) continue;
+    int rank = 0;
+    for (int k = 0; k < H; ++k) {
+      const float dk = dist[k];
+      if (dk < 0.0f) continue;
+      rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
+    }
+    const bool dummy = (dummy_mask[j >> 5] >> (j & 31)) & 1u;
+    const CnF2 op = dummy ? f2(7.0f, 7.0f) : f2(s.fx[j], s.fy[j]);
+    const CnF2 ov = dummy ? f2(0.0f, 0.0f) : f2(s.vx[j], s.vy[j]);
+    const float orad = p.randomize ? g.sim_rother[i * H + j]
+                                   : (float)((dummy ? 0.3 : s.rad[j]) + pad + p.orca_safety_space);
+    lines.set(rank, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
+    ++nl;
+  }
+  CnF2 result;
+  const int lineFail = cn_lp2(lines, nl, vmax, pref, false, result);
+  if (lineFail < nl) cn_lp3<MAXH>(lines, nl, lineFail, vmax, result);
+  s.nvx[h] = result.x; s.nvy[h] = result.y;
+  g.last_hvx[i] = result.x; g.last_hvy[i] = result.y;
+  g.orca_nlines[i] = nl; g.orca_fail[i] = (lineFail < nl) ? lineFail : -1;
+
+  // --- collision distance to the robot for calc_reward (state BEFORE the action is applied)
+  const double dx = s.px[h] - s.rpx, dy = s.py[h] - s.rpy;
+  s.t0[h] = sqrt(dx * dx + dy * dy) - s.rad[h] - p.robot_radius;
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase REWARD (leader): calc_reward + robot integration + time.
+CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int e, const CnStepOut& out) {
+  const int H = p.H;
+  double dmin = INFINITY;
+  bool collision = false;
+  for (int i = 0; i < H; ++i) {
+    const double c = s.t0[i];
+    if (c < 0) { collision = true; break; }
+    else if (c < dmin) dmin = c;
+  }
+  const bool reaching_goal = cn_norm_dot(s.rpx - s.rgx, s.rpy - s.rgy) < p.robot_radius;
+  const bool danger = dmin < p.discomfort_dist;              // phase == 'train' (crowd_sim_var_num.py:495-497)
+  const int step = g.step_count[e];
+  const double global_time = step * p.time_step;
+  double reward; int done, info;
+  if (global_time >= p.time_limit - 1) { reward = 0; done = 1; info = CN_INFO_TIMEOUT; }
+  else if (collision) { reward = p.collision_penalty; done = 1; info = CN_INFO_COLLISION; }
+  else if (reaching_goal) { reward = p.success_reward; done = 1; info = CN_INFO_REACHGOAL; }
+  else if (danger) {
+    reward = (dmin - p.discomfort_dist) * p.discomfort_penalty_factor * p.time_step;
+    done = 0; info = CN_INFO_DANGER;
+  } else {
+    const double pot = cn_norm_dot(s.rpx - s.rgx, s.rpy - s.rgy);
+    reward = 2 * (-fabs(pot) - g.potential[e]);
+    g.potential[e] = -fabs(pot);
+    done = 0; info = CN_INFO_NOTHING;
+  }
+  if (p.const_vel) reward = reward + g.fut_pen[e];            // crowd_sim_pred.py:216-233
+  s.reward = reward; s.done = done; s.info = info;
+  // Monitor bookkeeping + outputs
+  const double ret = g.ep_ret[e] + reward;
+  const int len = g.ep_len[e] + 1;
+  g.ep_ret[e] = ret; g.ep_len[e] = len;
+  out.reward[e] = (float)reward;
+  out.done[e] = (uint8_t)done;
+  out.info[e] = info;
+  out.info_aux[e] = 0.0f;
+  if (done) { out.ep_ret[e] = ret; out.ep_len[e] = len; }
+  // robot.step(action) (agent.py:170-183); time
+  s.rpx = s.rpx + (double)s.ax * p.time_step;
+  s.rpy = s.rpy + (double)s.ay * p.time_step;
+  s.rvx = s.ax; s.rvy = s.ay;
+  g.step_count[e] = step + 1;
+}
+
+// Phase INTEGRATE (per human): humans[i].step(human_action).
+CN_HD void cn_phase_integrate(const CnParams& p, CnEnvSh& s, int h) {
+  s.px[h] = s.px[h] + (double)s.nvx[h] * p.time_step;
+  s.py[h] = s.py[h] + (double)s.nvy[h] * p.time_step;
+  s.vx[h] = s.nvx[h]; s.vy[h] = s.nvy[h];
+}
+
+// ------------------------------------------------------------------------------------------
+// RNG-consuming pieces (leader thread only, serial — they share one MT19937 stream).
+struct CnSpawn { double px, py, vpref, rad; };
+
+CN_HD void cn_new_human_attrs(const CnParams& p, const CnState& g, int e, CnRng& rng, double& vpref, double& rad) {
+  vpref = p.human_vpref; rad = p.human_radius;
+  if (p.randomize) {                      // agent.py:20-23 then agent.py:44-50
+    g.nd_global[e] = cn_rng_uniform(rng, 5, 10);
+    vpref = cn_rng_uniform(rng, 0.5, 1.5);
+    rad = cn_rng_uniform(rng, 0.3, 0.5);
+  }
+}
+
+// generate_circle_crossing_human (crowd_sim_var_num.py:116-146) against robot + humans[0..n_present)
+CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, const CnEnvSh& s, int e,
+                                       CnRng& rng, int n_present) {
+  CnSpawn sp;
+  cn_new_human_attrs(p, g, e, rng, sp.vpref, sp.rad);
+  for (;;) {
+    const double angle = cn_rng_double(rng) * CN_PI * 2;
+    const double px_noise = cn_rng_uniform(rng, 0, 1) * 2;
+    const double py_noise = cn_rng_uniform(rng, 0, 1) * 2;
+    const double px = p.circle_radius * cos(angle) + px_noise;
+    const double py = p.circle_radius * sin(angle) + py_noise;
+    bool collide = false;
+    for (int k = -1; k < n_present; ++k) {
+      double ax, ay, agx, agy, ar;
+      if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
+      else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
+      const double min_dist = sp.rad + ar + p.discomfort_dist;
+      if (cn_norm_dot(px - ax, py - ay) < min_dist || cn_norm_dot(px - agx, py - agy) < min_dist) {
+        collide = true; break;
+      }
+    }
+    if (!collide) { sp.px = px; sp.py = py; break; }
+  }
+  return sp;
+}
+
+// reset (crowd_sim_var_num.py:303-363), leader only.  Rewrites the shared working set.
+CN_HD void cn_reset_leader(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
+  const int H = p.H;
+  CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = 624;
+  const uint32_t cc = g.case_counter[e];
+  const uint32_t this_seed = p.seed_base + (uint32_t)e;
+  cn_rng_seed(rng, p.phase_offset + cc + this_seed);
+  for (;;) {
+    const double px = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
+    const double py = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
+    const double gx = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
+    const double gy = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
+    if (cn_norm_dot(px - gx, py - gy) >= 8) { s.rpx = px; s.rpy = py; s.rgx = gx; s.rgy = gy; break; }
+  }
+  s.rvx = 0.0f; s.rvy = 0.0f;
+  for (int i = 0; i < H; ++i) {
+    const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, i);
+    s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
+    s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
+    s.fx[i] = (float)sp.px; s.fy[i] = (float)sp.py;
+    const size_t gi = cn_idx(p, e, i);
+    g.sim_exists[gi] = 0;
+    g.bpx[gi] = 0; g.bpy[gi] = 0; g.bvx[gi] = 0; g.bvy[gi] = 0; g.brad[gi] = 0;   // last_human_states = zeros
+  }
+  // case_counter = (case_counter + nenv) % case_size['train'] with case_size = UINT32_MAX - 2000
+  const uint64_t case_size = 4294967295ull - 2000ull;
+  g.case_counter[e] = (uint32_t)(((uint64_t)cc + (uint64_t)p.nenv_total) % case_size);
+  g.potential[e] = -fabs(cn_norm_dot(s.rgx - s.rpx, s.rgy - s.rpy));
+  g.step_count[e] = 0;
+  g.ep_ret[e] = 0.0; g.ep_len[e] = 0;
+  g.mt_pos[e] = rng.pos;
+  s.reset_flag = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase OBS-A (per human): robot visibility, belief update, prediction, sort key, future penalty.
+// Writes the fp32 observation row into `row` (W floats, caller-provided per-thread scratch).
+template <int MAXW>
+CN_HD void cn_phase_obs_a(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, float* row) {
+  const size_t i = cn_idx(p, e, h);
+  const double dist = cn_norm_dot(s.rpx - s.px[h], s.rpy - s.py[h]) - p.robot_radius - s.rad[h];
+  const bool in_fov = cn_in_fov(s.rpx, s.rpy, s.rvx, s.rvy, s.px[h], s.py[h], p.robot_fov);
+  const bool vis = in_fov && (dist <= p.sensor_range);
+  s.visr[h] = vis ? 1 : 0;
+  g.vis[i] = vis ? 1 : 0;
+  // prev_human_pos[:, 2:4] = belief velocity BEFORE this update (crowd_sim_pred.py:71)
+  const double pvx = g.bvx[i], pvy = g.bvy[i];
+  double bx, by;
+  if (vis) {
+    g.bpx[i] = s.px[h]; g.bpy[i] = s.py[h]; g.bvx[i] = (double)s.vx[h]; g.bvy[i] = (double)s.vy[h];
+    g.brad[i] = s.rad[h];
+    bx = s.px[h]; by = s.py[h];
+  } else if (s.reset_flag) {
+    g.bpx[i] = 15.; g.bpy[i] = 15.; g.bvx[i] = 0.; g.bvy[i] = 0.; g.brad[i] = 0.3;
+    bx = 15.; by = 15.;
+  } else {
+    bx = g.bpx[i] + pvx * p.time_step; by = g.bpy[i] + pvy * p.time_step;
+    g.bpx[i] = bx; g.bpy[i] = by;
+  }
+  if (p.const_vel) {
+    // calc_human_future_traj('const_vel') (crowd_sim_var_num.py:152-228)
+    double pen = 0.0;   // min over k of [dist < r_robot + humans.radius] * penalty / 2^(k+1)
+    const double thresh = p.robot_radius + p.human_radius;
+    double coef = 2.0;
+    for (int k = 0; k <= p.P; ++k) {
+      double tx, ty;
+      if (vis) { const double t = (double)k * p.pred_dt; tx = s.px[h] + t * pvx; ty = s.py[h] + t * pvy; }
+      else { tx = 15.; ty = 15.; }
+      const double rx = tx - s.rpx, ry = ty - s.rpy;
+      row[2 * k] = (float)rx; row[2 * k + 1] = (float)ry;
+      if (k == 0) s.t0[h] = vis ? cn_norm_dot(rx, ry) : INFINITY;
+      else {
+        coef = coef * 2.0;                                   // 2^(k+1)
+        const double c = (cn_norm_plain(rx, ry) < thresh) ? (p.collision_penalty / coef) : 0.0;
+        pen = c < pen ? c : pen;
+      }
+    }
+    s.t1[h] = pen;
+  } else {
+    const double rx = bx - s.rpx, ry = by - s.rpy;
+    row[0] = (float)rx; row[1] = (float)ry;
+    s.t0[h] = vis ? cn_norm_dot(rx, ry) : INFINITY;
+    s.t1[h] = 0.0;
+  }
+}
+
+// Phase OBS-B (per human): stable rank by key, write the row; leader writes the per-env parts.
+CN_HD void cn_phase_obs_b(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, const float* row,
+                          const CnObs& ob) {
+  const int H = p.H, W = p.W;
+  int rank = h;
+  if (p.sort_humans) {
+    rank = 0;
+    const double kh = s.t0[h];
+    for (int k = 0; k < H; ++k) {
+      const double kk = s.t0[k];
+      rank += (kk < kh || (kk == kh && k < h)) ? 1 : 0;
+    }
+  }
+  float* dst = ob.spatial_edges + ((size_t)e * H + rank) * W;
+  const bool vis = s.visr[h] != 0;
+  for (int c = 0; c < W; ++c) dst[c] = vis ? row[c] : 15.0f;
+  if (h == 0) {
+    int nvis = 0; double pen = 0.0;
+    for (int k = 0; k < H; ++k) { nvis += s.visr[k]; pen = s.t1[k] < pen ? s.t1[k] : pen; }
+    s.nvis = nvis;
+    g.fut_pen[e] = pen;
+    float* rn = ob.robot_node + (size_t)e * 7;
+    rn[0] = (float)s.rpx; rn[1] = (float)s.rpy; rn[2] = (float)p.robot_radius; rn[3] = (float)s.rgx;
+    rn[4] = (float)s.rgy; rn[5] = (float)p.robot_vpref; rn[6] = (float)(CN_PI / 2);
+    ob.temporal_edges[2 * e] = s.rvx; ob.temporal_edges[2 * e + 1] = s.rvy;
+    ob.detected_human_num[e] = (float)(nvis > 0 ? nvis : 1);
+  }
+  if (ob.visible_masks) {
+    // sorted: first num_visibles entries True (crowd_sim_var_num.py:262-266); unsorted: by id
+    // (written in cn_phase_obs_c once nvis is known when sorted)
+    if (!p.sort_humans) ob.visible_masks[(size_t)e * H + h] = vis ? 1 : 0;
+  }
+}
+CN_HD void cn_phase_obs_c(const CnParams& p, CnEnvSh& s, int e, int h, const CnObs& ob) {
+  if (ob.visible_masks && p.sort_humans) ob.visible_masks[(size_t)e * p.H + h] = (h < s.nvis) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase GOALS (leader, only when the episode continues): random goal changes every 5 s and
+// end-goal respawns (crowd_sim_pred.py:202-211).
+CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
+  const int H = p.H;
+  CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = g.mt_pos[e];
+  const int step = g.step_count[e];
+  // global_time % 5 == 0 with global_time = step * 0.25 accumulated exactly
+  const double gt = step * p.time_step;
+  if (p.goal_changing && fmod(gt, 5.0) == 0.0) {
+    for (int i = 0; i < H; ++i) {
+      if (s.vpref[i] == 0) continue;
+      if (cn_rng_double(rng) <= p.goal_change_chance) {
+        double gx, gy;
+        for (;;) {
+          const double angle = cn_rng_double(rng) * CN_PI * 2;
+          const double vp = (s.vpref[i] == 0) ? 1.0 : s.vpref[i];
+          const double gx_noise = (cn_rng_double(rng) - 0.5) * vp;
+          const double gy_noise = (cn_rng_double(rng) - 0.5) * vp;
+          gx = p.circle_radius * cos(angle) + gx_noise;
+          gy = p.circle_radius * sin(angle) + gy_noise;
+          bool collide = false;
+          for (int k = -1; k < H; ++k) {
+            if (k == i) continue;
+            double ax, ay, agx, agy, ar;
+            if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
+            else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
+            const double min_dist = s.rad[i] + ar + p.discomfort_dist;
+            if (cn_norm_dot(gx - ax, gy - ay) < min_dist || cn_norm_dot(gx - agx, gy - agy) < min_dist) {
+              collide = true; break;
+            }
+          }
+          if (!collide) break;
+        }
+        s.gx[i] = gx; s.gy[i] = gy;
+      }
+    }
+  }
+  if (p.end_goal_changing) {
+    for (int i = 0; i < H; ++i) {
+      if (cn_norm_dot(s.gx[i] - s.px[i], s.gy[i] - s.py[i]) < s.rad[i]) {
+        const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, H);
+        s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
+        s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
+        g.sim_exists[cn_idx(p, e, i)] = 0;       // new Human => new ORCA policy => new rvo2 sim
+      }
+    }
+  }
+  g.mt_pos[e] = rng.pos;
+}
+
+// Phase STORE: write the working set back to HBM.
+CN_HD void cn_phase_store(const CnParams& p, const CnState& g, const CnEnvSh& s, int e, int h) {
+  const size_t i = cn_idx(p, e, h);
+  g.hpx[i] = s.px[h]; g.hpy[i] = s.py[h]; g.hgx[i] = s.gx[h]; g.hgy[i] = s.gy[h];
+  g.hrad[i] = s.rad[h]; g.hvpref[i] = s.vpref[h];
+  g.hvx[i] = s.vx[h]; g.hvy[i] = s.vy[h];
+  if (h == 0) {
+    g.rpx[e] = s.rpx; g.rpy[e] = s.rpy; g.rgx[e] = s.rgx; g.rgy[e] = s.rgy;
+    g.rvx[e] = s.rvx; g.rvy[e] = s.rvy;
+  }
+}

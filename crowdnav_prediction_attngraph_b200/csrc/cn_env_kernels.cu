@@ -1,0 +1,359 @@
+// crowd_sim step()/reset() for thousands of environments: one fused sm_100a kernel per
+// rollout step over the SoA state in HBM.  Thread mapping: one thread per (environment,
+// human); a CTA owns EPB whole environments; neighbour tiles (positions, velocities, radii)
+// and the ORCA half-plane lines live in shared memory.  See cn_env_core.cuh for the per-phase
+// arithmetic and the reference lines each phase follows.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false  (no FMA contraction: the
+// fp32 ORCA sequence and the fp64 reward/visibility tests must round exactly like the oracle).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/crowdnav_b200.h"
+#include "cn_env_core.cuh"
+#include "cn_host_util.h"
+
+namespace {
+
+// shared-memory carve-up of one environment's working set
+struct EnvSmemLayout {
+  size_t per_env;      // bytes per environment (without lines)
+  size_t off_dbl;      // 8 double arrays
+  size_t off_flt;      // 6 float arrays
+  size_t off_u8;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline EnvSmemLayout env_layout(int H) {
+  EnvSmemLayout L;
+  size_t o = align16(sizeof(CnEnvSh));
+  L.off_dbl = o; o += (size_t)8 * H * sizeof(double);
+  L.off_flt = o; o += (size_t)6 * H * sizeof(float);
+  L.off_u8 = o; o += (size_t)H;
+  L.per_env = align16(o);
+  return L;
+}
+
+__device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L, int H) {
+  CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
+  double* d = reinterpret_cast<double*>(base + L.off_dbl);
+  float* f = reinterpret_cast<float*>(base + L.off_flt);
+  s->px = d; s->py = d + H; s->gx = d + 2 * H; s->gy = d + 3 * H; s->rad = d + 4 * H; s->vpref = d + 5 * H;
+  s->t0 = d + 6 * H; s->t1 = d + 7 * H;
+  s->vx = f; s->vy = f + H; s->fx = f + 2 * H; s->fy = f + 3 * H; s->nvx = f + 4 * H; s->nvy = f + 5 * H;
+  s->visr = base + L.off_u8;
+  return s;
+}
+
+// mode 0: step (+ auto-reset where done); mode 1: reset every environment.
+template <int MAXH, int MAXW>
+__global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
+                                                          CnObs ob, CnStepOut out, int epb, int mode) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int H = p.H;
+  const int le = threadIdx.x / H;
+  const int h = threadIdx.x - le * H;
+  const int e = blockIdx.x * epb + le;
+  const bool active = (le < epb) && (e < p.N);
+  const EnvSmemLayout L = env_layout(H);
+  CnEnvSh* s = nullptr;
+  if (le < epb) {
+    s = reinterpret_cast<CnEnvSh*>(smem + (size_t)le * L.per_env);
+    if (h == 0) env_view(smem + (size_t)le * L.per_env, L, H);
+  }
+  __syncthreads();
+  CnLineStore lines;
+  lines.base = reinterpret_cast<float4*>(smem + align16((size_t)epb * L.per_env)) + threadIdx.x;
+  lines.stride = blockDim.x;
+
+  if (active) cn_phase_load(p, g, *s, e, h, mode == 0 ? action : nullptr);
+  __syncthreads();
+  if (mode == 0) {
+    if (active) cn_phase_orca<MAXH>(p, g, *s, e, h, lines);
+    __syncthreads();
+    if (active) {
+      if (h == 0) cn_phase_reward(p, g, *s, e, out);
+      cn_phase_integrate(p, *s, h);
+    }
+    __syncthreads();
+  }
+  if (active && h == 0 && (mode == 1 || s->done)) cn_reset_leader(p, g, *s, e);
+  __syncthreads();
+  float row[MAXW];
+  if (active) cn_phase_obs_a<MAXW>(p, g, *s, e, h, row);
+  __syncthreads();
+  if (active) cn_phase_obs_b(p, g, *s, e, h, row, ob);
+  __syncthreads();
+  if (active) {
+    cn_phase_obs_c(p, *s, e, h, ob);
+    if (h == 0 && mode == 0 && !s->done) cn_phase_goals_leader(p, g, *s, e);
+  }
+  __syncthreads();
+  if (active) cn_phase_store(p, g, *s, e, h);
+}
+
+struct Field {
+  void* ptr;
+  size_t bytes;
+};
+
+}  // namespace
+
+struct cn_env {
+  cn_config cfg;
+  CnParams p;
+  CnState g;
+  int device;
+  int epb;
+  int threads;
+  size_t smem_bytes;
+  int maxh;
+  int64_t launches;
+  std::map<std::string, Field> fields;
+  std::vector<void*> allocs;
+  // staging for the host-buffer entry point
+  float* d_action;
+  cn_obs_ptrs d_obs;
+  cn_step_ptrs d_out;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(cn_env* env, const char* name, T** ptr, size_t count) {
+  void* q = nullptr;
+  const size_t bytes = count * sizeof(T);
+  cudaError_t err = cudaMalloc(&q, bytes ? bytes : 16);
+  if (err != cudaSuccess) return cn_set_error("cudaMalloc(%s, %zu bytes): %s", name, bytes, cudaGetErrorString(err));
+  err = cudaMemset(q, 0, bytes ? bytes : 16);
+  if (err != cudaSuccess) return cn_set_error("cudaMemset(%s): %s", name, cudaGetErrorString(err));
+  *ptr = static_cast<T*>(q);
+  env->allocs.push_back(q);
+  if (name) env->fields[name] = Field{q, bytes};
+  return 0;
+}
+
+typedef void (*KernelFn)(CnParams, CnState, const float*, CnObs, CnStepOut, int, int);
+
+KernelFn pick_kernel(int maxh) {
+  if (maxh <= 32) return cn_env_step_kernel<32, 16>;
+  if (maxh <= 64) return cn_env_step_kernel<64, 16>;
+  return cn_env_step_kernel<128, 16>;
+}
+
+int launch(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const cn_step_ptrs* r, int mode,
+           cudaStream_t stream) {
+  CnObs ob;
+  ob.robot_node = o->robot_node; ob.temporal_edges = o->temporal_edges; ob.spatial_edges = o->spatial_edges;
+  ob.detected_human_num = o->detected_human_num; ob.visible_masks = o->visible_masks;
+  CnStepOut out;
+  memset(&out, 0, sizeof(out));
+  if (r) {
+    out.reward = r->reward; out.done = r->done; out.info = r->info; out.info_aux = r->info_aux;
+    out.ep_ret = r->ep_ret; out.ep_len = r->ep_len;
+  }
+  const int grid = (env->p.N + env->epb - 1) / env->epb;
+  KernelFn fn = pick_kernel(env->maxh);
+  fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, ob, out, env->epb, mode);
+  env->launches += 1;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cn_abi_version(void) { return CN_ABI_VERSION; }
+
+int cn_env_create(const cn_config* cfg, cn_env** out) {
+  if (!cfg || !out) return cn_set_error("cn_env_create: null argument");
+  *out = nullptr;
+  if (cfg->num_envs <= 0 || cfg->human_num <= 0 || cfg->human_num > 128)
+    return cn_set_error("cn_env_create: need num_envs > 0 and 1 <= human_num <= 128 (got %d, %d)", cfg->num_envs,
+                        cfg->human_num);
+  if (cfg->const_vel && (cfg->predict_steps < 0 || 2 * (cfg->predict_steps + 1) > 16))
+    return cn_set_error("cn_env_create: predict_steps %d unsupported (row width > 16)", cfg->predict_steps);
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return cn_set_error("cn_env_create: no CUDA device (%s); this engine has no CPU fallback",
+                        err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+  if (cfg->device < 0 || cfg->device >= ndev) return cn_set_error("cn_env_create: bad device %d", cfg->device);
+  err = cudaSetDevice(cfg->device);
+  if (err != cudaSuccess) return cn_set_error("cudaSetDevice: %s", cudaGetErrorString(err));
+
+  cn_env* env = new cn_env();
+  env->cfg = *cfg;
+  env->device = cfg->device;
+  env->launches = 0;
+  CnParams& p = env->p;
+  memset(&p, 0, sizeof(p));
+  p.N = cfg->num_envs; p.H = cfg->human_num; p.P = cfg->predict_steps;
+  p.const_vel = cfg->const_vel ? 1 : 0;
+  p.W = p.const_vel ? 2 * (p.P + 1) : 2;
+  p.randomize = cfg->randomize_attributes; p.goal_changing = cfg->random_goal_changing;
+  p.end_goal_changing = cfg->end_goal_changing; p.sort_humans = cfg->sort_humans;
+  p.nenv_total = cfg->nenv_total; p.seed_base = (uint32_t)(cfg->seed + cfg->rank_offset);
+  p.phase_offset = 2000u;
+  p.time_step = cfg->time_step; p.time_limit = cfg->time_limit;
+  {
+    // pred_interval = int(pred_timestep // time_step) (crowd_sim.py:187)
+    const double q = floor(cfg->pred_timestep / cfg->time_step);
+    p.pred_dt = cfg->time_step * (double)(int)q;
+  }
+  p.circle_radius = cfg->circle_radius; p.arena_size = cfg->arena_size;
+  p.discomfort_dist = cfg->discomfort_dist; p.discomfort_penalty_factor = cfg->discomfort_penalty_factor;
+  p.success_reward = cfg->success_reward; p.collision_penalty = cfg->collision_penalty;
+  p.human_radius = cfg->human_radius; p.human_vpref = cfg->human_v_pref;
+  p.robot_radius = cfg->robot_radius; p.robot_vpref = cfg->robot_v_pref; p.sensor_range = cfg->sensor_range;
+  p.human_fov = CN_PI * cfg->human_fov; p.robot_fov = CN_PI * cfg->robot_fov;
+  p.goal_change_chance = cfg->goal_change_chance;
+  p.orca_safety_space = cfg->orca_safety_space; p.orca_neighbor_dist = cfg->orca_neighbor_dist;
+  p.orca_time_horizon = (float)cfg->orca_time_horizon;
+
+  const size_t N = (size_t)p.N, NH = N * p.H;
+  CnState& g = env->g;
+  memset(&g, 0, sizeof(g));
+  int rc = 0;
+#define A(field, count) if (!rc) rc = dev_alloc(env, #field, &g.field, (count))
+  A(rpx, N); A(rpy, N); A(rgx, N); A(rgy, N); A(rvx, N); A(rvy, N); A(potential, N); A(fut_pen, N);
+  A(nd_global, N); A(ep_ret, N); A(ep_len, N); A(step_count, N); A(case_counter, N);
+  A(hpx, NH); A(hpy, NH); A(hgx, NH); A(hgy, NH); A(hrad, NH); A(hvpref, NH); A(hvx, NH); A(hvy, NH);
+  A(bpx, NH); A(bpy, NH); A(bvx, NH); A(bvy, NH); A(brad, NH); A(vis, NH);
+  A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH);
+  A(sim_rother, p.randomize ? NH * p.H : (size_t)4);
+  A(mt, N * 624); A(mt_pos, N);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH);
+#undef A
+  if (!rc) {
+    // nd_global starts at the configured value (config.orca.neighbor_dist)
+    std::vector<double> nd(N, cfg->orca_neighbor_dist);
+    err = cudaMemcpy(g.nd_global, nd.data(), N * sizeof(double), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) rc = cn_set_error("init nd_global: %s", cudaGetErrorString(err));
+  }
+  // staging buffers for cn_env_step_host
+  memset(&env->d_obs, 0, sizeof(env->d_obs)); memset(&env->d_out, 0, sizeof(env->d_out));
+  env->d_action = nullptr;
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_action, N * 2);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_obs.robot_node, N * 7);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_obs.temporal_edges, N * 2);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_obs.spatial_edges, NH * p.W);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_obs.detected_human_num, N);
+  if (!rc && !p.const_vel) rc = dev_alloc(env, nullptr, &env->d_obs.visible_masks, NH);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.reward, N);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.done, N);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.info, N);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.info_aux, N);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.ep_ret, N);
+  if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.ep_len, N);
+  if (rc) { cn_env_destroy(env); return rc; }
+
+  // launch geometry: EPB whole environments per CTA, <= 256 threads, lines in shared memory
+  env->maxh = p.H <= 32 ? 32 : (p.H <= 64 ? 64 : 128);
+  const EnvSmemLayout L = env_layout(p.H);
+  const size_t smem_cap = 200 * 1024;
+  int epb = 256 / p.H;
+  if (epb < 1) epb = 1;
+  for (;;) {
+    const size_t need = align16((size_t)epb * L.per_env) + (size_t)(p.H - 1 > 0 ? p.H - 1 : 1) * epb * p.H * sizeof(float4);
+    if (need <= smem_cap || epb == 1) { env->smem_bytes = need; break; }
+    --epb;
+  }
+  env->epb = epb;
+  env->threads = ((epb * p.H + 31) / 32) * 32;
+  if (env->threads > 256) return cn_env_destroy(env), cn_set_error("internal: %d threads", env->threads);
+  // lines are indexed [line][thread] with stride blockDim.x
+  env->smem_bytes = align16((size_t)epb * L.per_env) + (size_t)(p.H > 1 ? p.H - 1 : 1) * env->threads * sizeof(float4);
+  if (env->smem_bytes > 227 * 1024) {
+    cn_env_destroy(env);
+    return cn_set_error("cn_env_create: human_num %d needs %zu B shared memory per CTA", p.H, env->smem_bytes);
+  }
+  err = cudaFuncSetAttribute(pick_kernel(env->maxh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+  if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+  *out = env;
+  return 0;
+}
+
+int cn_env_destroy(cn_env* env) {
+  if (!env) return 0;
+  cudaSetDevice(env->device);
+  for (void* q : env->allocs) cudaFree(q);
+  delete env;
+  return 0;
+}
+
+int cn_env_reset(cn_env* env, const cn_obs_ptrs* d_obs, void* stream) {
+  if (!env || !d_obs) return cn_set_error("cn_env_reset: null argument");
+  cudaSetDevice(env->device);
+  // a reset of the whole vec env restarts Monitor bookkeeping but NOT case_counter (it keeps advancing)
+  return launch(env, nullptr, d_obs, nullptr, 1, (cudaStream_t)stream);
+}
+
+int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, const cn_step_ptrs* d_out,
+                void* stream) {
+  if (!env || !d_action || !d_obs || !d_out) return cn_set_error("cn_env_step: null argument");
+  if (!d_out->reward || !d_out->done || !d_out->info || !d_out->info_aux || !d_out->ep_ret || !d_out->ep_len)
+    return cn_set_error("cn_env_step: every cn_step_ptrs field must be set");
+  cudaSetDevice(env->device);
+  return launch(env, d_action, d_obs, d_out, 0, (cudaStream_t)stream);
+}
+
+int cn_env_step_host(cn_env* env, const float* h_action, const cn_obs_ptrs* h_obs, const cn_step_ptrs* h_out) {
+  if (!env || !h_action || !h_obs || !h_out) return cn_set_error("cn_env_step_host: null argument");
+  cudaSetDevice(env->device);
+  const size_t N = (size_t)env->p.N, NH = N * env->p.H;
+  cudaStream_t st = 0;
+  cudaError_t err = cudaMemcpyAsync(env->d_action, h_action, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (err != cudaSuccess) return cn_set_error("H2D action: %s", cudaGetErrorString(err));
+  int rc = launch(env, env->d_action, &env->d_obs, &env->d_out, 0, st);
+  if (rc) return rc;
+#define D2H(dst, src, bytes) if (dst) { err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); \
+    if (err != cudaSuccess) return cn_set_error("D2H " #dst ": %s", cudaGetErrorString(err)); }
+  D2H(h_obs->robot_node, env->d_obs.robot_node, N * 7 * sizeof(float));
+  D2H(h_obs->temporal_edges, env->d_obs.temporal_edges, N * 2 * sizeof(float));
+  D2H(h_obs->spatial_edges, env->d_obs.spatial_edges, NH * env->p.W * sizeof(float));
+  D2H(h_obs->detected_human_num, env->d_obs.detected_human_num, N * sizeof(float));
+  if (env->d_obs.visible_masks) D2H(h_obs->visible_masks, env->d_obs.visible_masks, NH);
+  D2H(h_out->reward, env->d_out.reward, N * sizeof(float));
+  D2H(h_out->done, env->d_out.done, N);
+  D2H(h_out->info, env->d_out.info, N * sizeof(int32_t));
+  D2H(h_out->info_aux, env->d_out.info_aux, N * sizeof(float));
+  D2H(h_out->ep_ret, env->d_out.ep_ret, N * sizeof(double));
+  D2H(h_out->ep_len, env->d_out.ep_len, N * sizeof(int32_t));
+#undef D2H
+  err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) return cn_set_error("cn_env_step_host: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+size_t cn_env_state_bytes(cn_env* env, const char* name) {
+  if (!env || !name) return 0;
+  auto it = env->fields.find(name);
+  return it == env->fields.end() ? 0 : it->second.bytes;
+}
+
+int cn_env_state_copy(cn_env* env, const char* name, void* h_buf, size_t bytes, int dir) {
+  if (!env || !name || !h_buf) return cn_set_error("cn_env_state_copy: null argument");
+  auto it = env->fields.find(name);
+  if (it == env->fields.end()) return cn_set_error("cn_env_state_copy: unknown field '%s'", name);
+  if (bytes != it->second.bytes)
+    return cn_set_error("cn_env_state_copy: field '%s' is %zu bytes, got %zu", name, it->second.bytes, bytes);
+  cudaSetDevice(env->device);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err == cudaSuccess)
+    err = dir ? cudaMemcpy(it->second.ptr, h_buf, bytes, cudaMemcpyHostToDevice)
+              : cudaMemcpy(h_buf, it->second.ptr, bytes, cudaMemcpyDeviceToHost);
+  if (err != cudaSuccess) return cn_set_error("cn_env_state_copy(%s): %s", name, cudaGetErrorString(err));
+  return 0;
+}
+
+int64_t cn_env_launch_count(cn_env* env) { return env ? env->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// ORCA (RVO2) velocity solve for ONE agent against its neighbours — the arithmetic the
+// reference obtains from the external rvo2 library through crowd_nav/policy/orca.py:64-117
+// (Agent::computeNeighbors / computeNewVelocity / linearProgram1-3 of RVO2 v2.0.x).
+//
+// One thread per human.  All arithmetic is IEEE fp32 in the RVO2 operation order; this
+// translation unit MUST be compiled with --fmad=false (nvcc) / -ffp-contract=off (g++ test
+// harness) so no multiply-add is contracted: that is what makes the result bit-identical to
+// the CPU oracle (oracle/rvo2_ref.cpp).  Division and sqrt are the IEEE-rounded ones.
+//
+// ORCA lines live in a caller-provided store (shared memory on the GPU, [line][thread]
+// layout => conflict-free 16-byte accesses); the rarely used LP3 projection lines live in a
+// per-thread local array.
+#pragma once
+#include "cn_common.cuh"
+
+#define CN_RVO_EPS 0.00001f
+
+struct CnF2 {
+  float x, y;
+};
+CN_HD CnF2 f2(float x, float y) { CnF2 r; r.x = x; r.y = y; return r; }
+CN_HD CnF2 f2add(CnF2 a, CnF2 b) { return f2(a.x + b.x, a.y + b.y); }
+CN_HD CnF2 f2sub(CnF2 a, CnF2 b) { return f2(a.x - b.x, a.y - b.y); }
+CN_HD CnF2 f2neg(CnF2 a) { return f2(-a.x, -a.y); }
+CN_HD float f2dot(CnF2 a, CnF2 b) { return a.x * b.x + a.y * b.y; }
+CN_HD CnF2 f2scale(float s, CnF2 a) { return f2(s * a.x, s * a.y); }
+// RVO2 Vector2::operator/(float): multiply by the reciprocal
+CN_HD CnF2 f2div(CnF2 a, float s) { const float inv = 1.0f / s; return f2(a.x * inv, a.y * inv); }
+CN_HD float f2abssq(CnF2 a) { return f2dot(a, a); }
+CN_HD float f2abs(CnF2 a) { return sqrtf(f2dot(a, a)); }
+CN_HD float f2det(CnF2 a, CnF2 b) { return a.x * b.y - a.y * b.x; }
+CN_HD CnF2 f2normalize(CnF2 a) { return f2div(a, f2abs(a)); }
+// std::min / std::max semantics (matter only for NaN, kept for faithfulness)
+CN_HD float cn_minf(float a, float b) { return (b < a) ? b : a; }
+CN_HD float cn_maxf(float a, float b) { return (a < b) ? b : a; }
+
+struct CnLine {
+  CnF2 point, dir;
+};
+
+// Strided line store: element k at base[k * stride] as 4 floats (point.x, point.y, dir.x, dir.y).
+struct CnLineStore {
+  float4* base;
+  int stride;
+  CN_HD CnLine get(int k) const {
+    const float4 v = base[(size_t)k * stride];
+    CnLine l; l.point = f2(v.x, v.y); l.dir = f2(v.z, v.w); return l;
+  }
+  CN_HD void set(int k, const CnLine& l) {
+    float4 v; v.x = l.point.x; v.y = l.point.y; v.z = l.dir.x; v.w = l.dir.y;
+    base[(size_t)k * stride] = v;
+  }
+};
+
+template <class Lines>
+CN_HD bool cn_lp1(const Lines& lines, int lineNo, float radius, CnF2 optVelocity, bool directionOpt,
+                  CnF2& result) {
+  const CnLine ln = lines.get(lineNo);
+  const float dotProduct = f2dot(ln.point, ln.dir);
+  const float discriminant = dotProduct * dotProduct + radius * radius - f2abssq(ln.point);
+  if (discriminant < 0.0f) return false;
+  const float sqrtDiscriminant = sqrtf(discriminant);
+  float tLeft = -dotProduct - sqrtDiscriminant;
+  float tRight = -dotProduct + sqrtDiscriminant;
+  for (int i = 0; i < lineNo; ++i) {
+    const CnLine li = lines.get(i);
+    const float denominator = f2det(ln.dir, li.dir);
+    const float numerator = f2det(li.dir, f2sub(ln.point, li.point));
+    if (fabsf(denominator) <= CN_RVO_EPS) {
+      if (numerator < 0.0f) return false;
+      continue;
+    }
+    const float t = numerator / denominator;
+    if (denominator >= 0.0f) {
+      tRight = cn_minf(tRight, t);
+    } else {
+      tLeft = cn_maxf(tLeft, t);
+    }
+    if (tLeft > tRight) return false;
+  }
+  if (directionOpt) {
+    if (f2dot(optVelocity, ln.dir) > 0.0f) {
+      result = f2add(ln.point, f2scale(tRight, ln.dir));
+    } else {
+      result = f2add(ln.point, f2scale(tLeft, ln.dir));
+    }
+  } else {
+    const float t = f2dot(ln.dir, f2sub(optVelocity, ln.point));
+    if (t < tLeft) {
+      result = f2add(ln.point, f2scale(tLeft, ln.dir));
+    } else if (t > tRight) {
+      result = f2add(ln.point, f2scale(tRight, ln.dir));
+    } else {
+      result = f2add(ln.point, f2scale(t, ln.dir));
+    }
+  }
+  return true;
+}
+
+template <class Lines>
+CN_HD int cn_lp2(const Lines& lines, int numLines, float radius, CnF2 optVelocity, bool directionOpt,
+                 CnF2& result) {
+  if (directionOpt) {
+    result = f2scale(radius, optVelocity);   // optVelocity * radius (commutative)
+  } else if (f2abssq(optVelocity) > radius * radius) {
+    result = f2scale(radius, f2normalize(optVelocity));
+  } else {
+    result = optVelocity;
+  }
+  for (int i = 0; i < numLines; ++i) {
+    const CnLine li = lines.get(i);
+    if (f2det(li.dir, f2sub(li.point, result)) > 0.0f) {
+      const CnF2 tempResult = result;
+      if (!cn_lp1(lines, i, radius, optVelocity, directionOpt, result)) {
+        result = tempResult;
+        return i;
+      }
+    }
+  }
+  return numLines;
+}
+
+template <int MAXH>
+struct CnLocalLines {
+  float4 v[MAXH];
+  CN_HD CnLine get(int k) const {
+    CnLine l; l.point = f2(v[k].x, v[k].y); l.dir = f2(v[k].z, v[k].w); return l;
+  }
+  CN_HD void set(int k, const CnLine& l) {
+    v[k].x = l.point.x; v[k].y = l.point.y; v[k].z = l.dir.x; v[k].w = l.dir.y;
+  }
+};
+
+template <int MAXH, class Lines>
+CN_HD_NOINLINE void cn_lp3(const Lines& lines, int numLines, int beginLine, float radius, CnF2& result) {
+  CnLocalLines<MAXH> proj;
+  float distance = 0.0f;
+  for (int i = beginLine; i < numLines; ++i) {
+    const CnLine li = lines.get(i);
+    if (f2det(li.dir, f2sub(li.point, result)) > distance) {
+      int np = 0;
+      for (int j = 0; j < i; ++j) {
+        const CnLine lj = lines.get(j);
+        CnLine line;
+        const float determinant = f2det(li.dir, lj.dir);
+        if (fabsf(determinant) <= CN_RVO_EPS) {
+          if (f2dot(li.dir, lj.dir) > 0.0f) continue;
+          line.point = f2scale(0.5f, f2add(li.point, lj.point));
+        } else {
+          line.point = f2add(li.point,
+                             f2scale(f2det(lj.dir, f2sub(li.point, lj.point)) / determinant, li.dir));
+        }
+        line.dir = f2normalize(f2sub(lj.dir, li.dir));
+        proj.set(np++, line);
+      }
+      const CnF2 tempResult = result;
+      if (cn_lp2(proj, np, radius, f2(-li.dir.y, li.dir.x), true, result) < np) {
+        result = tempResult;
+      }
+      distance = f2det(li.dir, f2sub(li.point, result));
+    }
+  }
+}
+
+// One ORCA half-plane (Agent::computeNewVelocity body for one neighbour).
+CN_HD CnLine cn_orca_line(CnF2 pos, CnF2 vel, float radius, CnF2 opos, CnF2 ovel, float oradius,
+                          float invTimeHorizon, float timeStep) {
+  const CnF2 relativePosition = f2sub(opos, pos);
+  const CnF2 relativeVelocity = f2sub(vel, ovel);
+  const float distSq = f2abssq(relativePosition);
+  const float combinedRadius = radius + oradius;
+  const float combinedRadiusSq = combinedRadius * combinedRadius;
+  CnLine line;
+  CnF2 u;
+  if (distSq > combinedRadiusSq) {
+    const CnF2 w = f2sub(relativeVelocity, f2scale(invTimeHorizon, relativePosition));
+    const float wLengthSq = f2abssq(w);
+    const float dotProduct1 = f2dot(w, relativePosition);
+    if (dotProduct1 < 0.0f && dotProduct1 * dotProduct1 > combinedRadiusSq * wLengthSq) {
+      const float wLength = sqrtf(wLengthSq);
+      const CnF2 unitW = f2div(w, wLength);
+      line.dir = f2(unitW.y, -unitW.x);
+      u = f2scale(combinedRadius * invTimeHorizon - wLength, unitW);
+    } else {
+      const float leg = sqrtf(distSq - combinedRadiusSq);
+      if (f2det(relativePosition, w) > 0.0f) {
+        line.dir = f2div(f2(relativePosition.x * leg - relativePosition.y * combinedRadius,
+                            relativePosition.x * combinedRadius + relativePosition.y * leg),
+                         distSq);
+      } else {
+        line.dir = f2div(f2neg(f2(relativePosition.x * leg + relativePosition.y * combinedRadius,
+                                  -relativePosition.x * combinedRadius + relativePosition.y * leg)),
+                         distSq);
+      }
+      const float dotProduct2 = f2dot(relativeVelocity, line.dir);
+      u = f2sub(f2scale(dotProduct2, line.dir), relativeVelocity);
+    }
+  } else {
+    const float invTimeStep = 1.0f / timeStep;
+    const CnF2 w = f2sub(relativeVelocity, f2scale(invTimeStep, relativePosition));
+    const float wLength = f2abs(w);
+    const CnF2 unitW = f2div(w, wLength);
+    line.dir = f2(unitW.y, -unitW.x);
+    u = f2scale(combinedRadius * invTimeStep - wLength, unitW);
+  }
+  line.point = f2add(vel, f2scale(0.5f, u));
+  return line;
+}

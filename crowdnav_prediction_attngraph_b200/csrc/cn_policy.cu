@@ -1,0 +1,335 @@
+// Host side of the attention-graph policy forward: parameter upload / folding and the
+// per-rollout-step launch sequence behind cn_policy_act (replaces Policy.act,
+// rl/networks/model.py:56-74, for base = selfAttn_merge_SRNN with sort_humans = True).
+//
+// Algebraic folds done once per parameter upload (fp64 accumulate, exact same function):
+//   q/k/v_linear  o  MultiheadAttention.in_proj   ->  one 512 -> 1536 projection
+//   MultiheadAttention.out_proj  o  spatial_linear -> one 512 -> 256 projection (ReLU after)
+//   spatial_edge_layer folded into the robot side of the dot-product attention (u = W_s^T te)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/crowdnav_b200.h"
+#include "cn_host_util.h"
+#include "cn_policy_kernels.cuh"
+
+struct cn_policy {
+  cn_policy_config cfg;
+  int N, H, Win, M;
+  int64_t launches;
+  bool finalized;
+  std::map<std::string, std::vector<float>> host;
+  std::vector<void*> allocs;
+  size_t ws_allocs;   // allocs[0..ws_allocs) = workspace (kept); the rest = parameters of the last finalize
+  // device parameters (kernel layouts)
+  float *W1, *b1, *W2, *b2, *Wqkv, *bqkv, *Wos, *bos;
+  float *Wr, *br, *Wet, *bet, *WsT, *bs, *Wa, *ba, *Wih, *bih, *Whh, *bhh, *Wo, *bo;
+  float *Wac1, *bac1, *Wa2, *ba2, *Wc2, *bc2, *wv_, *bv, *Wm, *bm, *logstd;
+  // optional per-stage profiling
+  bool profile;
+  std::vector<cudaEvent_t> ev;
+  // workspace
+  float *x16, *e1, *e2, *qkv, *ao, *sout, *xr, *rs, *t1, *u, *wv, *h0, *gi, *gh, *outb, *ac1, *a2, *c2;
+};
+
+namespace {
+
+int palloc(cn_policy* p, float** ptr, size_t count) {
+  void* q = nullptr;
+  cudaError_t err = cudaMalloc(&q, (count ? count : 4) * sizeof(float));
+  if (err != cudaSuccess) return cn_set_error("cudaMalloc(%zu floats): %s", count, cudaGetErrorString(err));
+  cudaMemset(q, 0, (count ? count : 4) * sizeof(float));
+  p->allocs.push_back(q);
+  *ptr = static_cast<float*>(q);
+  return 0;
+}
+
+int upload(cn_policy* p, float** dst, const std::vector<float>& src) {
+  int rc = palloc(p, dst, src.size());
+  if (rc) return rc;
+  cudaError_t err = cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return cn_set_error("H2D param: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+const std::vector<float>* get(cn_policy* p, const char* key, size_t count) {
+  auto it = p->host.find(key);
+  if (it == p->host.end()) { cn_set_error("cn_policy_finalize: parameter '%s' was not set", key); return nullptr; }
+  if (it->second.size() != count) {
+    cn_set_error("cn_policy_finalize: parameter '%s' has %zu elements, expected %zu", key, it->second.size(), count);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+void gemm(cn_policy* p, cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias,
+          float* C, int ldc, int M, int N, int K, int act, int act_lo = 0, int act_hi = 1 << 30) {
+  dim3 grid((N + CN_GEMM_BN - 1) / CN_GEMM_BN, (M + CN_GEMM_BM - 1) / CN_GEMM_BM);
+  cn_gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, act_lo, act_hi);
+  p->launches += 1;
+}
+
+const char* kStageNames[] = {"pack_inputs", "embed1_gemm", "embed2_gemm", "qkv_gemm", "hh_attention",
+                             "outproj_spatial_gemm", "robot_branch", "hr_attention", "gru", "actor_critic_heads"};
+const int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+
+inline void mark(cn_policy* p, cudaStream_t st, int i) {
+  if (p->profile) cudaEventRecord(p->ev[i], st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cn_policy_profile(cn_policy* p, int enable) {
+  if (!p) return cn_set_error("cn_policy_profile: null argument");
+  cudaSetDevice(p->cfg.device);
+  if (enable && p->ev.empty()) {
+    p->ev.resize(kNumStages + 1);
+    for (auto& e : p->ev) cudaEventCreate(&e);
+  }
+  p->profile = enable != 0;
+  return 0;
+}
+int cn_policy_stage_count(void) { return kNumStages; }
+const char* cn_policy_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+int cn_policy_stage_ms(cn_policy* p, float* out, int n) {
+  if (!p || !out) return cn_set_error("cn_policy_stage_ms: null argument");
+  if (p->ev.empty()) return cn_set_error("cn_policy_stage_ms: profiling was never enabled");
+  cudaSetDevice(p->cfg.device);
+  cudaError_t err = cudaEventSynchronize(p->ev[kNumStages]);
+  if (err != cudaSuccess) return cn_set_error("cn_policy_stage_ms: %s", cudaGetErrorString(err));
+  for (int i = 0; i < n && i < kNumStages; ++i) cudaEventElapsedTime(&out[i], p->ev[i], p->ev[i + 1]);
+  return 0;
+}
+
+int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
+  if (!cfg || !out) return cn_set_error("cn_policy_create: null argument");
+  *out = nullptr;
+  if (cfg->num_envs <= 0 || cfg->human_num <= 0 || cfg->human_num > 128 || cfg->input_size <= 0 || cfg->input_size > 16)
+    return cn_set_error("cn_policy_create: unsupported dims N=%d H=%d input=%d", cfg->num_envs, cfg->human_num,
+                        cfg->input_size);
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0)
+    return cn_set_error("cn_policy_create: no CUDA device (%s); this engine has no CPU fallback",
+                        err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+  if (cfg->device < 0 || cfg->device >= ndev) return cn_set_error("cn_policy_create: bad device %d", cfg->device);
+  cudaSetDevice(cfg->device);
+  cn_policy* p = new cn_policy();
+  memset(static_cast<void*>(&p->cfg), 0, sizeof(p->cfg));
+  p->cfg = *cfg;
+  p->N = cfg->num_envs; p->H = cfg->human_num; p->Win = cfg->input_size; p->M = p->N * p->H;
+  p->launches = 0; p->finalized = false; p->profile = false;
+  const size_t M = (size_t)p->M, N = (size_t)p->N;
+  int rc = 0;
+#define WS(name, count) if (!rc) rc = palloc(p, &p->name, (count))
+  WS(x16, M * 16); WS(e1, M * 128); WS(e2, M * 512); WS(qkv, M * 1536); WS(ao, M * 512); WS(sout, M * 256);
+  WS(xr, N * 16); WS(rs, N * 256); WS(t1, N * 128); WS(u, N * 256); WS(wv, N * 256); WS(h0, N * 128);
+  WS(gi, N * 384); WS(gh, N * 384); WS(outb, N * 256); WS(ac1, N * 512); WS(a2, N * 256); WS(c2, N * 256);
+#undef WS
+  if (rc) { cn_policy_destroy(p); return rc; }
+  p->ws_allocs = p->allocs.size();
+  const size_t attn_smem = ((size_t)p->H * 65 + (size_t)p->H * 64 + 256) * sizeof(float);
+  err = cudaFuncSetAttribute(cn_hh_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem);
+  if (err != cudaSuccess) { cn_policy_destroy(p); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+  *out = p;
+  return 0;
+}
+
+int cn_policy_destroy(cn_policy* p) {
+  if (!p) return 0;
+  cudaSetDevice(p->cfg.device);
+  for (void* q : p->allocs) cudaFree(q);
+  for (auto& e : p->ev) cudaEventDestroy(e);
+  delete p;
+  return 0;
+}
+
+int cn_policy_set_param(cn_policy* p, const char* key, const float* h_data, size_t count) {
+  if (!p || !key || !h_data) return cn_set_error("cn_policy_set_param: null argument");
+  p->host[key] = std::vector<float>(h_data, h_data + count);
+  p->finalized = false;
+  return 0;
+}
+
+int cn_policy_finalize(cn_policy* p, void* stream) {
+  if (!p) return cn_set_error("cn_policy_finalize: null argument");
+  cudaSetDevice(p->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Win = p->Win;
+#define GET(var, key, count) const std::vector<float>* var = get(p, key, (count)); if (!var) return 1
+  GET(w1, "base.spatial_attn.embedding_layer.0.weight", (size_t)128 * Win);
+  GET(b1, "base.spatial_attn.embedding_layer.0.bias", 128);
+  GET(w2, "base.spatial_attn.embedding_layer.2.weight", (size_t)512 * 128);
+  GET(b2, "base.spatial_attn.embedding_layer.2.bias", 512);
+  GET(wq, "base.spatial_attn.q_linear.weight", (size_t)512 * 512);
+  GET(bq, "base.spatial_attn.q_linear.bias", 512);
+  GET(wk, "base.spatial_attn.k_linear.weight", (size_t)512 * 512);
+  GET(bk, "base.spatial_attn.k_linear.bias", 512);
+  GET(wvv, "base.spatial_attn.v_linear.weight", (size_t)512 * 512);
+  GET(bvv, "base.spatial_attn.v_linear.bias", 512);
+  GET(win, "base.spatial_attn.multihead_attn.in_proj_weight", (size_t)1536 * 512);
+  GET(bin, "base.spatial_attn.multihead_attn.in_proj_bias", 1536);
+  GET(wout, "base.spatial_attn.multihead_attn.out_proj.weight", (size_t)512 * 512);
+  GET(bout, "base.spatial_attn.multihead_attn.out_proj.bias", 512);
+  GET(wsl, "base.spatial_linear.0.weight", (size_t)256 * 512);
+  GET(bsl, "base.spatial_linear.0.bias", 256);
+  GET(wr, "base.robot_linear.0.weight", (size_t)256 * 9);
+  GET(br, "base.robot_linear.0.bias", 256);
+  GET(wt, "base.attn.temporal_edge_layer.0.weight", (size_t)64 * 256);
+  GET(bt, "base.attn.temporal_edge_layer.0.bias", 64);
+  GET(ws, "base.attn.spatial_edge_layer.0.weight", (size_t)64 * 256);
+  GET(bs, "base.attn.spatial_edge_layer.0.bias", 64);
+  GET(we, "base.humanNodeRNN.encoder_linear.weight", (size_t)64 * 256);
+  GET(be, "base.humanNodeRNN.encoder_linear.bias", 64);
+  GET(wa, "base.humanNodeRNN.edge_attention_embed.weight", (size_t)64 * 256);
+  GET(ba, "base.humanNodeRNN.edge_attention_embed.bias", 64);
+  GET(wih, "base.humanNodeRNN.gru.weight_ih_l0", (size_t)384 * 128);
+  GET(whh, "base.humanNodeRNN.gru.weight_hh_l0", (size_t)384 * 128);
+  GET(bih, "base.humanNodeRNN.gru.bias_ih_l0", 384);
+  GET(bhh, "base.humanNodeRNN.gru.bias_hh_l0", 384);
+  GET(wo, "base.humanNodeRNN.output_linear.weight", (size_t)256 * 128);
+  GET(bo, "base.humanNodeRNN.output_linear.bias", 256);
+  GET(wa0, "base.actor.0.weight", (size_t)256 * 256);
+  GET(ba0, "base.actor.0.bias", 256);
+  GET(wa2, "base.actor.2.weight", (size_t)256 * 256);
+  GET(ba2, "base.actor.2.bias", 256);
+  GET(wc0, "base.critic.0.weight", (size_t)256 * 256);
+  GET(bc0, "base.critic.0.bias", 256);
+  GET(wc2, "base.critic.2.weight", (size_t)256 * 256);
+  GET(bc2, "base.critic.2.bias", 256);
+  GET(wcl, "base.critic_linear.weight", 256);
+  GET(bcl, "base.critic_linear.bias", 1);
+  GET(wm, "dist.fc_mean.weight", (size_t)2 * 256);
+  GET(bm, "dist.fc_mean.bias", 2);
+  GET(ls, "dist.logstd._bias", 2);
+#undef GET
+  // release device parameters of a previous finalize (workspace allocations come first and stay)
+  cudaStreamSynchronize(st);
+  for (size_t i = p->ws_allocs; i < p->allocs.size(); ++i) cudaFree(p->allocs[i]);
+  p->allocs.resize(p->ws_allocs);
+  int rc = 0;
+  auto pad_k = [](const std::vector<float>& w, int rows, int k, int kp) {
+    std::vector<float> o((size_t)rows * kp, 0.0f);
+    for (int r = 0; r < rows; ++r) for (int c = 0; c < k; ++c) o[(size_t)r * kp + c] = w[(size_t)r * k + c];
+    return o;
+  };
+  auto cat = [](const std::vector<float>& a, const std::vector<float>& b) {
+    std::vector<float> o(a); o.insert(o.end(), b.begin(), b.end()); return o;
+  };
+#define UP(dst, vec) if (!rc) rc = upload(p, &p->dst, (vec))
+  UP(W1, pad_k(*w1, 128, Win, 16)); UP(b1, *b1); UP(W2, *w2); UP(b2, *b2);
+  UP(Wr, pad_k(*wr, 256, 9, 16)); UP(br, *br);
+  UP(Wet, cat(*we, *wt)); UP(bet, cat(*be, *bt));           // rows 0..63 encoder_linear, 64..127 temporal_edge_layer
+  {
+    std::vector<float> wst((size_t)256 * 64);                // W_s^T: [256][64]
+    for (int r = 0; r < 64; ++r) for (int c = 0; c < 256; ++c) wst[(size_t)c * 64 + r] = (*ws)[(size_t)r * 256 + c];
+    UP(WsT, wst);
+  }
+  UP(bs, *bs); UP(Wa, *wa); UP(ba, *ba); UP(Wih, *wih); UP(bih, *bih); UP(Whh, *whh); UP(bhh, *bhh);
+  UP(Wo, *wo); UP(bo, *bo);
+  UP(Wac1, cat(*wa0, *wc0)); UP(bac1, cat(*ba0, *bc0));      // rows 0..255 actor.0, 256..511 critic.0
+  UP(Wa2, *wa2); UP(ba2, *ba2); UP(Wc2, *wc2); UP(bc2, *bc2);
+  UP(wv_, *wcl); UP(bv, *bcl); UP(Wm, *wm); UP(bm, *bm); UP(logstd, *ls);
+  // folded projections
+  float *d_win = nullptr, *d_bin = nullptr, *d_wl[3] = {nullptr, nullptr, nullptr}, *d_bl[3] = {nullptr, nullptr, nullptr};
+  float *d_wout = nullptr, *d_bout = nullptr, *d_wsl = nullptr, *d_bsl = nullptr;
+  if (!rc) rc = upload(p, &d_win, *win);
+  if (!rc) rc = upload(p, &d_bin, *bin);
+  const std::vector<float>* wl[3] = {wq, wk, wvv};
+  const std::vector<float>* bl[3] = {bq, bk, bvv};
+  for (int i = 0; i < 3 && !rc; ++i) { rc = upload(p, &d_wl[i], *wl[i]); if (!rc) rc = upload(p, &d_bl[i], *bl[i]); }
+  if (!rc) rc = upload(p, &d_wout, *wout);
+  if (!rc) rc = upload(p, &d_bout, *bout);
+  if (!rc) rc = upload(p, &d_wsl, *wsl);
+  if (!rc) rc = upload(p, &d_bsl, *bsl);
+  if (!rc) rc = palloc(p, &p->Wqkv, (size_t)1536 * 512);
+  if (!rc) rc = palloc(p, &p->bqkv, 1536);
+  if (!rc) rc = palloc(p, &p->Wos, (size_t)256 * 512);
+  if (!rc) rc = palloc(p, &p->bos, 256);
+  if (rc) return rc;
+  for (int i = 0; i < 3; ++i) {
+    // Wf_i = Win_i (512x512) @ Wl_i (512x512);  bf_i = Win_i @ bl_i + bin_i
+    cn_fold_mm_kernel<<<dim3(4, 512), 128, 0, st>>>(d_win + (size_t)i * 512 * 512, d_wl[i],
+                                                     p->Wqkv + (size_t)i * 512 * 512, 512, 512, 512);
+    cn_fold_mv_kernel<<<4, 128, 0, st>>>(d_win + (size_t)i * 512 * 512, d_bl[i], d_bin + i * 512, p->bqkv + i * 512, 512, 512);
+  }
+  // Wos = Wsl (256x512) @ Wout (512x512);  bos = Wsl @ bout + bsl
+  cn_fold_mm_kernel<<<dim3(4, 256), 128, 0, st>>>(d_wsl, d_wout, p->Wos, 256, 512, 512);
+  cn_fold_mv_kernel<<<2, 128, 0, st>>>(d_wsl, d_bout, d_bsl, p->bos, 256, 512);
+  cudaError_t err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) return cn_set_error("cn_policy_finalize: %s", cudaGetErrorString(err));
+  p->finalized = true;
+  return 0;
+}
+
+int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
+  if (!p || !d) return cn_set_error("cn_policy_act: null argument");
+  if (!p->finalized) return cn_set_error("cn_policy_act: call cn_policy_finalize after setting parameters");
+  if (!d->robot_node || !d->temporal_edges || !d->spatial_edges || !d->detected_human_num || !d->h_in || !d->masks ||
+      !d->value || !d->action || !d->log_prob || !d->h_out)
+    return cn_set_error("cn_policy_act: missing input/output pointer");
+  cudaSetDevice(p->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = p->N, H = p->H, M = p->M;
+  mark(p, st, 0);
+  // 0. pack / pad inputs, h0 = h * mask
+  {
+    const int total = M * 16 > N * 128 ? M * 16 : N * 128;
+    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, M, p->x16, d->temporal_edges,
+                                                               d->robot_node, d->h_in, d->masks, N, p->xr, p->h0);
+    p->launches += 1;
+  }
+  // 1. human-human branch over all N*H rows
+  mark(p, st, 1);
+  gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU);
+  mark(p, st, 2);
+  gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU);
+  mark(p, st, 3);
+  gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE);
+  mark(p, st, 4);
+  {
+    const size_t smem = ((size_t)H * 65 + (size_t)H * 64 + 256) * sizeof(float);
+    cn_hh_attention_kernel<<<dim3(N, 8), 128, smem, st>>>(p->qkv, d->detected_human_num, H, p->ao);
+    p->launches += 1;
+  }
+  mark(p, st, 5);
+  gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU);
+  // 2. robot branch
+  mark(p, st, 6);
+  gemm(p, st, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
+  gemm(p, st, p->rs, 256, p->Wet, 256, p->bet, p->t1, 128, N, 128, 256, CN_ACT_RELU, 0, 64);   // [enc | te]
+  gemm(p, st, p->t1 + 64, 128, p->WsT, 64, nullptr, p->u, 256, N, 256, 64, CN_ACT_NONE);        // u = W_s^T te
+  mark(p, st, 7);
+  cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, d->detected_human_num, N, H,
+                                                      p->wv);
+  p->launches += 1;
+  mark(p, st, 8);
+  // emb overwrites the te half of t1 -> t1 = [enc | emb] = GRU input
+  gemm(p, st, p->wv, 256, p->Wa, 256, p->ba, p->t1 + 64, 128, N, 64, 256, CN_ACT_RELU);
+  gemm(p, st, p->t1, 128, p->Wih, 128, p->bih, p->gi, 384, N, 384, 128, CN_ACT_NONE);
+  gemm(p, st, p->h0, 128, p->Whh, 128, p->bhh, p->gh, 384, N, 384, 128, CN_ACT_NONE);
+  cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out);
+  p->launches += 1;
+  mark(p, st, 9);
+  gemm(p, st, d->h_out, 128, p->Wo, 128, p->bo, p->outb, 256, N, 256, 128, CN_ACT_NONE);
+  gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);      // [actor.0 | critic.0]
+  gemm(p, st, p->ac1, 512, p->Wa2, 256, p->ba2, p->a2, 256, N, 256, 256, CN_ACT_TANH);
+  gemm(p, st, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
+  cn_heads_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->a2, 256, p->c2, 256, p->wv_, p->bv, p->Wm, p->bm, p->logstd, d->noise, N,
+                                               d->value, d->action, d->log_prob, d->action_mean);
+  p->launches += 1;
+  mark(p, st, kNumStages);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return cn_set_error("cn_policy_act launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+int64_t cn_policy_launch_count(cn_policy* p) { return p ? p->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// Device kernels of the attention-graph policy forward (rollout / infer=True path):
+//   rl/networks/selfAttn_srnn_temp_node.py:360-449 (selfAttn_merge_SRNN.forward)
+//   rl/networks/selfAttn_srnn_temp_node.py:63-91   (SpatialEdgeSelfAttn, nn.MultiheadAttention 8 heads)
+//   rl/networks/selfAttn_srnn_temp_node.py:145-223 (EdgeAttention_M)
+//   rl/networks/selfAttn_srnn_temp_node.py:262-285 + srnn_model.py:35-47 (EndRNN / GRU step)
+//   rl/networks/distributions.py:76-95,36-44       (DiagGaussian / FixedNormal)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum { CN_ACT_NONE = 0, CN_ACT_RELU = 1, CN_ACT_TANH = 2 };
+
+// ------------------------------------------------------------------------------------------
+// fp32 CUDA-core GEMM:  C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]),  act on columns [act_lo, act_hi).
+// 128x128x16 tiles, 256 threads, 8x8 register tile per thread, register-prefetched double
+// buffering through shared memory.  K % 16 == 0 (buffers are zero padded), M and N ragged.
+#define CN_GEMM_BM 128
+#define CN_GEMM_BN 128
+#define CN_GEMM_BK 16
+#define CN_GEMM_PAD 4
+
+__device__ __forceinline__ float cn_apply_act(float v, int act) {
+  if (act == CN_ACT_RELU) return v > 0.0f ? v : 0.0f;
+  if (act == CN_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) cn_gemm_f32_kernel(const float* __restrict__ A, int lda,
+                                                          const float* __restrict__ W, int ldw,
+                                                          const float* __restrict__ bias, float* __restrict__ Cout,
+                                                          int ldc, int M, int N, int K, int act, int act_lo,
+                                                          int act_hi) {
+  __shared__ __align__(16) float As[2][CN_GEMM_BK][CN_GEMM_BM + CN_GEMM_PAD];
+  __shared__ __align__(16) float Bs[2][CN_GEMM_BK][CN_GEMM_BN + CN_GEMM_PAD];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * CN_GEMM_BM, n0 = blockIdx.x * CN_GEMM_BN;
+  const int tx = tid & 15, ty = tid >> 4;
+  // global -> register staging: each thread moves two float4 of A and two of W per k-tile
+  const int lrow = tid >> 2;          // 0..63
+  const int lk = (tid & 3) * 4;       // 0,4,8,12
+  float4 ra[2], rb[2];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = m0 + lrow + i * 64;
+      ra[i] = (m < M) ? *reinterpret_cast<const float4*>(A + (size_t)m * lda + k0 + lk) : make_float4(0, 0, 0, 0);
+      const int n = n0 + lrow + i * 64;
+      rb[i] = (n < N) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k0 + lk) : make_float4(0, 0, 0, 0);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = lrow + i * 64;
+      As[buf][lk + 0][r] = ra[i].x; As[buf][lk + 1][r] = ra[i].y; As[buf][lk + 2][r] = ra[i].z; As[buf][lk + 3][r] = ra[i].w;
+      Bs[buf][lk + 0][r] = rb[i].x; Bs[buf][lk + 1][r] = rb[i].y; Bs[buf][lk + 2][r] = rb[i].z; Bs[buf][lk + 3][r] = rb[i].w;
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  const int nk = K / CN_GEMM_BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * CN_GEMM_BK);
+#pragma unroll
+    for (int k = 0; k < CN_GEMM_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int nb = n0 + (jj == 0 ? tx * 4 : 64 + tx * 4);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = nb + j;
+        float x = acc[i][jj * 4 + j];
+        if (n < N) {
+          if (bias) x += bias[n];
+          if (n >= act_lo && n < act_hi) x = cn_apply_act(x, act);
+        }
+        v[j] = x;
+      }
+      float* dst = Cout + (size_t)m * ldc + nb;
+      if (nb + 3 < N && ((ldc & 3) == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nb + j < N) dst[j] = v[j];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight folding at parameter-load time (fp64 accumulate):  C[m,n] = sum_k A[m,k] * B[k,n]
+// and  c[m] = sum_k A[m,k] * b[k] + d[m].   Not on the rollout path.
+__global__ void cn_fold_mm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Cm,
+                                  int M, int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  double acc = 0.0;
+  for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * K + k] * (double)B[(size_t)k * N + n];
+  Cm[(size_t)m * N + n] = (float)acc;
+}
+__global__ void cn_fold_mv_kernel(const float* __restrict__ A, const float* __restrict__ b, const float* __restrict__ d,
+                                  float* __restrict__ c, int M, int K) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double acc = d ? (double)d[m] : 0.0;
+  for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * K + k] * (double)b[k];
+  c[m] = (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Input packing: x16[M,16] = spatial_edges rows zero-padded to K=16;
+// xr[N,16] = cat(temporal_edges(2), robot_node(7)) zero padded; h0 = h_in * mask.
+__global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win, int M, float* __restrict__ x16,
+                                      const float* __restrict__ temporal, const float* __restrict__ robot,
+                                      const float* __restrict__ h_in, const float* __restrict__ masks, int N,
+                                      float* __restrict__ xr, float* __restrict__ h0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < M * 16) {
+    const int r = idx >> 4, c = idx & 15;
+    x16[idx] = c < Win ? spatial[(size_t)r * Win + c] : 0.0f;
+  }
+  if (idx < N * 16) {
+    const int e = idx >> 4, c = idx & 15;
+    float v = 0.0f;
+    if (c < 2) v = temporal[2 * e + c];
+    else if (c < 9) v = robot[7 * e + (c - 2)];
+    xr[idx] = v;
+  }
+  if (idx < N * 128) h0[idx] = h_in[idx] * masks[idx >> 7];
+}
+
+// ------------------------------------------------------------------------------------------
+// Human-human multi-head self attention for one (environment, head) per CTA.
+// qkv: [N*H, 1536] rows = (q | k | v), head hd uses columns hd*64..hd*64+63 of each third.
+// Keys j >= n_e are padding (key_padding_mask); query rows >= n_e are never consumed
+// downstream (their robot-human attention weight is exactly 0), they are written as zeros.
+__global__ void __launch_bounds__(128) cn_hh_attention_kernel(const float* __restrict__ qkv,
+                                                              const float* __restrict__ detected, int H,
+                                                              float* __restrict__ out /* [N*H,512] */) {
+  extern __shared__ float sm[];
+  const int e = blockIdx.x, hd = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n = (int)detected[e];
+  n = n < 1 ? 1 : (n > H ? H : n);
+  float* Ks = sm;                    // [H][65]
+  float* Vs = sm + (size_t)H * 65;   // [H][64]
+  float* Qs = Vs + (size_t)H * 64;   // [4 warps][64]
+  const size_t row0 = (size_t)e * H;
+  for (int idx = threadIdx.x; idx < n * 64; idx += blockDim.x) {
+    const int j = idx >> 6, d = idx & 63;
+    const float* src = qkv + (row0 + j) * 1536 + hd * 64 + d;
+    Ks[j * 65 + d] = src[512];
+    Vs[j * 64 + d] = src[1024];
+  }
+  __syncthreads();
+  const float scale = 0.125f;   // 1/sqrt(head_dim = 64)
+  for (int i = warp; i < H; i += 4) {
+    float* orow = out + (row0 + i) * 512 + hd * 64;
+    if (i >= n) {
+      orow[lane] = 0.0f; orow[lane + 32] = 0.0f;
+      continue;
+    }
+    const float* qsrc = qkv + (row0 + i) * 1536 + hd * 64;
+    float* q = Qs + warp * 64;
+    q[lane] = qsrc[lane] * scale; q[lane + 32] = qsrc[lane + 32] * scale;   // torch scales q before q k^T
+    __syncwarp();
+    // scores: lanes over keys
+    float sc[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane + 32 * t;
+      float s = -INFINITY;
+      if (j < n) {
+        s = 0.0f;
+        const float* kr = Ks + j * 65;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) s = fmaf(q[d], kr[d], s);
+      }
+      sc[t] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane + 32 * t;
+      sc[t] = (j < n) ? expf(sc[t] - mx) : 0.0f;
+      sum += sc[t];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    // O = P V: lanes over the 64 output dims (2 per lane)
+    float o0 = 0.0f, o1 = 0.0f;
+    for (int j = 0; j < n; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31) * inv;
+      o0 = fmaf(pj, Vs[j * 64 + lane], o0);
+      o1 = fmaf(pj, Vs[j * 64 + lane + 32], o1);
+    }
+    orow[lane] = o0; orow[lane + 32] = o1;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Robot-human attention (EdgeAttention_M.att_func) for one environment per warp:
+//   score_j = <W_t robot + b_t, W_s s_j + b_s> * (H / sqrt(64))  ==  (u . s_j + cst) * H/8
+// with u = W_s^T te (precomputed by a GEMM), cst = <b_s, te>;  masked_fill(-1e9) for j >= n_e;
+// softmax over all H; weighted sum of the 256-d human features.
+__global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __restrict__ s_out /* [N*H,256] */,
+                                                              const float* __restrict__ u /* [N,256] */,
+                                                              const float* __restrict__ te /* [N, ldte] cols te_off.. */,
+                                                              int ldte, int te_off, const float* __restrict__ b_s,
+                                                              const float* __restrict__ detected, int N, int H,
+                                                              float* __restrict__ wv /* [N,256] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 4 + warp;
+  if (e >= N) return;
+  int n = (int)detected[e];
+  n = n < 1 ? 1 : (n > H ? H : n);
+  float ur[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) ur[t] = u[(size_t)e * 256 + lane + 32 * t];
+  float cst = b_s[lane] * te[(size_t)e * ldte + te_off + lane] + b_s[lane + 32] * te[(size_t)e * ldte + te_off + lane + 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cst += __shfl_xor_sync(0xffffffffu, cst, o);
+  const float temperature = (float)H / 8.0f;
+  // scores for valid humans; lanes cooperate on each 256-d dot product
+  float sc[4] = {-1e9f, -1e9f, -1e9f, -1e9f};   // lane holds score of human lane + 32 t
+  for (int j = 0; j < n; ++j) {
+    const float* sr = s_out + ((size_t)e * H + j) * 256;
+    float d = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) d = fmaf(ur[t], sr[lane + 32 * t], d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    const float s = (d + cst) * temperature;
+    if ((j & 31) == lane) sc[j >> 5] = s;
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) if (lane + 32 * t < H) mx = fmaxf(mx, sc[t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.0f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    sc[t] = (lane + 32 * t < H) ? expf(sc[t] - mx) : 0.0f;   // masked entries: exp(-1e9 - mx) == 0
+    sum += sc[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < n; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31) * inv;
+    const float* sr = s_out + ((size_t)e * H + j) * 256;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = fmaf(pj, sr[lane + 32 * t], acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) wv[(size_t)e * 256 + lane + 32 * t] = acc[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// GRU cell gates (PyTorch order r, z, n; h' = (1 - z) * n + z * h), one thread per (env, unit).
+__device__ __forceinline__ float cn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void cn_gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                   const float* __restrict__ h0, int N, float* __restrict__ h1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * 128) return;
+  const int e = idx >> 7, c = idx & 127;
+  const float* a = gi + (size_t)e * 384;
+  const float* b = gh + (size_t)e * 384;
+  const float r = cn_sigmoid(a[c] + b[c]);
+  const float z = cn_sigmoid(a[128 + c] + b[128 + c]);
+  const float n = tanhf(a[256 + c] + r * b[256 + c]);
+  h1[idx] = (1.0f - z) * n + z * h0[idx];
+}
+
+// ------------------------------------------------------------------------------------------
+// Output heads, one warp per environment: value = critic_linear(hc); mean = fc_mean(ha);
+// action = mean + exp(logstd) * noise (torch.normal = randn * std + mean); log-prob summed.
+__global__ void __launch_bounds__(128) cn_heads_kernel(const float* __restrict__ ha, int ldha,
+                                                       const float* __restrict__ hc, int ldhc,
+                                                       const float* __restrict__ w_v, const float* __restrict__ b_v,
+                                                       const float* __restrict__ w_m, const float* __restrict__ b_m,
+                                                       const float* __restrict__ logstd,
+                                                       const float* __restrict__ noise, int N,
+                                                       float* __restrict__ value, float* __restrict__ action,
+                                                       float* __restrict__ logp, float* __restrict__ mean_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 4 + warp;
+  if (e >= N) return;
+  float v = 0.0f, m0 = 0.0f, m1 = 0.0f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int c = lane + 32 * t;
+    const float a = ha[(size_t)e * ldha + c], cc = hc[(size_t)e * ldhc + c];
+    v = fmaf(cc, w_v[c], v);
+    m0 = fmaf(a, w_m[c], m0);
+    m1 = fmaf(a, w_m[256 + c], m1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+  }
+  if (lane == 0) {
+    v += b_v[0]; m0 += b_m[0]; m1 += b_m[1];
+    value[e] = v;
+    if (mean_out) { mean_out[2 * e] = m0; mean_out[2 * e + 1] = m1; }
+    const float ls0 = logstd[0], ls1 = logstd[1];
+    const float s0 = expf(ls0), s1 = expf(ls1);
+    float a0 = m0, a1 = m1;
+    if (noise) {
+      a0 = __fadd_rn(__fmul_rn(noise[2 * e], s0), m0);
+      a1 = __fadd_rn(__fmul_rn(noise[2 * e + 1], s1), m1);
+    }
+    action[2 * e] = a0; action[2 * e + 1] = a1;
+    // Normal.log_prob: -((x - mu)^2) / (2 var) - log(std) - log(sqrt(2 pi))
+    const float c = 0.91893853320467274178f;
+    const float d0 = a0 - m0, d1 = a1 - m1;
+    const float l0 = -(d0 * d0) / (2.0f * (s0 * s0)) - logf(s0) - c;   // log_scale = scale.log()
+    const float l1 = -(d1 * d1) / (2.0f * (s1 * s1)) - logf(s1) - c;
+    logp[e] = l0 + l1;
+  }
+}

@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference policy surface over the CUDA kernels.
+
+`Policy` keeps the entry points train.py / test.py call on rl.networks.model.Policy
+(rl/networks/model.py:14-90): `act`, `get_value`, `evaluate_actions`, `state_dict` with the
+reference's keys and shapes so checkpoints interchange both ways.
+
+  * act / get_value (rollout, infer=True)  -> ONE call into the C ABI (cn_policy_act): the fused
+    sm_100a forward; no torch ops on the hot path except drawing the Gaussian noise.
+  * evaluate_actions (PPO update)          -> PyTorch on device (north_star: the clipped-loss
+    minibatch update stays in PyTorch), written here for [T, N] batches with done-mask GRU resets.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi
+
+HIDDEN = 128
+
+
+class _AddBias(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self._bias = nn.Parameter(torch.zeros(n, 1))
+
+
+def _ortho(m, gain=1.0):
+    nn.init.orthogonal_(m.weight.data, gain=gain)
+    nn.init.constant_(m.bias.data, 0)
+    return m
+
+
+class _Params(nn.Module):
+    """Parameter container with the reference's module tree (names drive the state_dict keys)."""
+
+    def __init__(self, input_size):
+        super().__init__()
+        g = math.sqrt(2)
+        base = nn.Module()
+        rnn = nn.Module()
+        rnn.gru = nn.GRU(128, HIDDEN)
+        for name, prm in rnn.gru.named_parameters():          # srnn_model.py:27-31
+            if 'bias' in name:
+                nn.init.constant_(prm, 0)
+            else:
+                nn.init.orthogonal_(prm)
+        rnn.encoder_linear = nn.Linear(256, 64)
+        rnn.edge_attention_embed = nn.Linear(256, 64)
+        rnn.output_linear = nn.Linear(HIDDEN, 256)
+        base.humanNodeRNN = rnn
+        att = nn.Module()
+        att.temporal_edge_layer = nn.ModuleList([nn.Linear(256, 64)])
+        att.spatial_edge_layer = nn.ModuleList([nn.Linear(256, 64)])
+        base.attn = att
+        base.actor = nn.Sequential(_ortho(nn.Linear(256, 256), g), nn.Tanh(), _ortho(nn.Linear(256, 256), g), nn.Tanh())
+        base.critic = nn.Sequential(_ortho(nn.Linear(256, 256), g), nn.Tanh(), _ortho(nn.Linear(256, 256), g), nn.Tanh())
+        base.critic_linear = _ortho(nn.Linear(256, 1), g)
+        base.robot_linear = nn.Sequential(_ortho(nn.Linear(9, 256), g), nn.ReLU())
+        base.human_node_final_linear = _ortho(nn.Linear(256, 2), g)   # unused by forward (reference :338)
+        sa = nn.Module()
+        sa.embedding_layer = nn.Sequential(nn.Linear(input_size, 128), nn.ReLU(), nn.Linear(128, 512), nn.ReLU())
+        sa.q_linear = nn.Linear(512, 512)
+        sa.v_linear = nn.Linear(512, 512)
+        sa.k_linear = nn.Linear(512, 512)
+        sa.multihead_attn = nn.MultiheadAttention(512, 8)
+        base.spatial_attn = sa
+        base.spatial_linear = nn.Sequential(_ortho(nn.Linear(512, 256), g), nn.ReLU())
+        self.base = base
+        dist = nn.Module()
+        dist.fc_mean = _ortho(nn.Linear(256, 2))
+        dist.logstd = _AddBias(2)
+        self.dist = dist
+
+
+def make_reference_like_state_dict(input_size=12, seed=0):
+    """Random-init parameters with the reference's initialisers (orthogonal where it uses them)."""
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    sd = {k: v.detach().clone() for k, v in _Params(input_size).state_dict().items()}
+    torch.random.set_rng_state(gen_state)
+    return sd
+
+
+class CudaPolicy(object):
+    """Thin handle on cn_policy: upload a reference state_dict, run the rollout forward."""
+
+    def __init__(self, num_envs, human_num, input_size=12, device="cuda:0", gemm_mode=0):
+        self.lib = _capi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("CudaPolicy needs a CUDA device (no CPU fallback)")
+        self.N, self.H, self.Win = num_envs, human_num, input_size
+        cfg = _capi.CnPolicyConfig(num_envs, human_num, input_size,
+                                   self.device.index if self.device.index is not None else 0, gemm_mode)
+        self._h = C.c_void_p()
+        _capi.check(self.lib, self.lib.cn_policy_create(C.byref(cfg), C.byref(self._h)), "cn_policy_create")
+        dev = self.device
+        N = num_envs
+        self._bufs = [dict(value=torch.zeros(N, 1, device=dev), action=torch.zeros(N, 2, device=dev),
+                           log_prob=torch.zeros(N, 1, device=dev), h_out=torch.zeros(N, 1, HIDDEN, device=dev),
+                           mean=torch.zeros(N, 2, device=dev)) for _ in range(2)]
+        self._flip = 0
+        self._gen = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            if k.startswith("base.human_node_final_linear"):
+                continue      # unused by the forward (reference selfAttn_srnn_temp_node.py:338)
+            arr = v.detach().to("cpu", torch.float32).contiguous().numpy()
+            _capi.check(self.lib, self.lib.cn_policy_set_param(self._h, k.encode(), arr.ctypes.data, arr.size),
+                        "cn_policy_set_param(%s)" % k)
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib, self.lib.cn_policy_finalize(self._h, self._stream()), "cn_policy_finalize")
+
+    def act(self, obs, h, masks, deterministic=False, return_mean=False, noise=None):
+        """obs: dict of device tensors; h: [N,1,128]; masks: [N,1].  Returns value, action, log_prob, h_new
+        (views of internal double buffers: valid until the call after next)."""
+        N = self.N
+        self._flip ^= 1
+        b = self._bufs[self._flip]
+        if not deterministic and noise is None:
+            noise = torch.randn(N, 2, device=self.device)      # torch.normal(mean, std) == randn * std + mean
+        sp = obs["spatial_edges"]
+        args = dict(robot_node=obs["robot_node"], temporal_edges=obs["temporal_edges"], spatial_edges=sp,
+                    detected_human_num=obs["detected_human_num"], h_in=h, masks=masks)
+        for k, t in args.items():
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                args[k] = t.to(self.device, torch.float32).contiguous()
+        ptrs = _capi.CnActPtrs(
+            args["robot_node"].data_ptr(), args["temporal_edges"].data_ptr(), args["spatial_edges"].data_ptr(),
+            args["detected_human_num"].data_ptr(), args["h_in"].data_ptr(), args["masks"].data_ptr(),
+            None if deterministic else noise.data_ptr(), b["value"].data_ptr(), b["action"].data_ptr(),
+            b["log_prob"].data_ptr(), b["h_out"].data_ptr(), b["mean"].data_ptr())
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib, self.lib.cn_policy_act(self._h, C.byref(ptrs), self._stream()), "cn_policy_act")
+        self._keep = (args, noise)      # keep inputs alive until the kernels are enqueued behind the next call
+        if return_mean:
+            return b["value"], b["action"], b["log_prob"], b["h_out"], b["mean"]
+        return b["value"], b["action"], b["log_prob"], b["h_out"]
+
+    def launch_count(self):
+        return int(self.lib.cn_policy_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            self.lib.cn_policy_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Policy(nn.Module):
+    """Drop-in for rl.networks.model.Policy(obs_space.spaces, action_space, base_kwargs=args, base=...)."""
+
+    def __init__(self, obs_shape, action_space, base=None, base_kwargs=None):
+        super().__init__()
+        if base not in (None, 'selfAttn_merge_srnn'):
+            raise NotImplementedError("only base='selfAttn_merge_srnn' is on the hot path (SURVEY.md §2.1 row 9)")
+        sp = obs_shape['spatial_edges'].shape
+        self.human_num, self.input_size = int(sp[0]), int(sp[1])
+        args = base_kwargs
+        self.nenv = int(getattr(args, 'num_processes', 1)) if args is not None else 1
+        self.seq_length = int(getattr(args, 'seq_length', 30)) if args is not None else 30
+        self.nminibatch = int(getattr(args, 'num_mini_batch', 2)) if args is not None else 2
+        p = _Params(self.input_size)
+        self.base = p.base
+        self.base.nenv = self.nenv
+        self.dist = p.dist
+        self.srnn = True
+        self._cuda = None
+        self._cuda_version = -1
+
+    is_recurrent = True
+
+    # ------------------------------------------------------------------ CUDA rollout path
+    def _engine(self, N, device):
+        if self._cuda is None or self._cuda.N != N or self._cuda.device != device:
+            self._cuda = CudaPolicy(N, self.human_num, self.input_size, device=device,
+                                    gemm_mode=int(os.environ.get("CN_GEMM_MODE", "0")))
+            self._cuda_version = -1
+        ver = sum(int(p._version) for p in self.parameters())
+        if ver != self._cuda_version:                       # parameters changed (optimizer step / load_state_dict)
+            self._cuda.load_state_dict(self.state_dict())
+            self._cuda_version = ver
+        return self._cuda
+
+    def act(self, inputs, rnn_hxs, masks, deterministic=False):
+        sp = inputs['spatial_edges']
+        eng = self._engine(sp.shape[0], sp.device)
+        value, action, logp, h_new = eng.act(inputs, rnn_hxs['human_node_rnn'], masks, deterministic=deterministic)
+        out_hxs = {'human_node_rnn': h_new,
+                   # all-zeros in the reference (selfAttn_srnn_temp_node.py:390-395): stride-0 view, no 2.7 GB buffer
+                   'human_human_edge_rnn': torch.zeros(1, 1, 1, device=sp.device).expand(sp.shape[0], self.human_num + 1, 256)}
+        return value, action, logp, out_hxs
+
+    def get_value(self, inputs, rnn_hxs, masks):
+        sp = inputs['spatial_edges']
+        eng = self._engine(sp.shape[0], sp.device)
+        value, _, _, _ = eng.act(inputs, rnn_hxs['human_node_rnn'], masks, deterministic=True)
+        return value
+
+    # ------------------------------------------------------------------ PyTorch update path
+    def _features(self, inputs, h0, masks, T, N):
+        b = self.base
+        H = self.human_num
+        sp = inputs['spatial_edges'].reshape(T * N, H, -1).float()
+        n = inputs['detected_human_num'].reshape(T * N).long().clamp(1, H)
+        valid = torch.arange(H, device=sp.device)[None, :] < n[:, None]
+        rs = b.robot_linear(torch.cat([inputs['temporal_edges'].reshape(T * N, 2),
+                                       inputs['robot_node'].reshape(T * N, 7)], -1).float())
+        sa = b.spatial_attn
+        e = sa.embedding_layer(sp)
+        mha = sa.multihead_attn
+        wq, wk, wv = mha.in_proj_weight.chunk(3, 0)
+        bq, bk, bv = mha.in_proj_bias.chunk(3, 0)
+        def heads(x):
+            return x.reshape(T * N, H, 8, 64).transpose(1, 2)
+        q = heads(F.linear(sa.q_linear(e), wq, bq))
+        k = heads(F.linear(sa.k_linear(e), wk, bk))
+        v = heads(F.linear(sa.v_linear(e), wv, bv))
+        amask = valid[:, None, None, :]
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=amask)
+        o = mha.out_proj(o.transpose(1, 2).reshape(T * N, H, 512))
+        hs = b.spatial_linear(o)
+        te = b.attn.temporal_edge_layer[0](rs)
+        se = b.attn.spatial_edge_layer[0](hs)
+        att = (te[:, None, :] * se).sum(-1) * (H / 8.0)
+        att = torch.softmax(att.masked_fill(~valid, -1e9), dim=-1)
+        wvv = torch.bmm(hs.transpose(1, 2), att.unsqueeze(-1)).squeeze(-1)
+        r = b.humanNodeRNN
+        x = torch.cat([torch.relu(r.encoder_linear(rs)), torch.relu(r.edge_attention_embed(wvv))], -1).reshape(T, N, 128)
+        g = r.gru
+        h = h0.reshape(N, HIDDEN)
+        m = masks.reshape(T, N, 1)
+        gi_all = F.linear(x, g.weight_ih_l0, g.bias_ih_l0)
+        outs = []
+        for t in range(T):
+            h = h * m[t]
+            gh = F.linear(h, g.weight_hh_l0, g.bias_hh_l0)
+            ir, iz, inn = gi_all[t].chunk(3, -1)
+            hr, hz, hn = gh.chunk(3, -1)
+            rg = torch.sigmoid(ir + hr)
+            zg = torch.sigmoid(iz + hz)
+            ng = torch.tanh(inn + rg * hn)
+            h = (1 - zg) * ng + zg * h
+            outs.append(h)
+        y = r.output_linear(torch.stack(outs, 0)).reshape(T * N, 256)
+        return b.critic_linear(b.critic(y)), b.actor(y), h.reshape(N, 1, HIDDEN)
+
+    def evaluate_actions(self, inputs, rnn_hxs, masks, action):
+        """inputs flattened [T*N, ...] (storage.py recurrent_generator), rnn_hxs['human_node_rnn'] [N,1,128]."""
+        h0 = rnn_hxs['human_node_rnn']
+        N = h0.shape[0]
+        T = inputs['spatial_edges'].shape[0] // N
+        value, feat, h = self._features(inputs, h0, masks, T, N)
+        mean = self.dist.fc_mean(feat)
+        logstd = self.dist.logstd._bias.t().view(1, -1).expand_as(mean)
+        dist = torch.distributions.Normal(mean, logstd.exp())
+        logp = dist.log_prob(action).sum(-1, keepdim=True)
+        entropy = dist.entropy().sum(-1).mean()
+        return value, logp, entropy, {'human_node_rnn': h}

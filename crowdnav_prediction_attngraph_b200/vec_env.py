@@ -1,0 +1,285 @@
+"""Host-side mirror of the reference's vec-env surface over the CUDA engine.
+
+`CudaCrowdVecEnv` keeps the contract of the wrapped `VecPyTorch(ShmemVecEnv(...))` object that
+`make_vec_envs` returns in the reference (rl/networks/envs.py:97-140, 193-224;
+rl/networks/shmem_vec_env.py:62-80): `reset()` -> dict of device tensors with leading dim N;
+`step(action_tensor)` -> (obs dict on device, reward CPU float32 [N,1], done np.bool_[N],
+infos sequence of dicts {'info': obj[, 'episode': {'r','l'}]}).  All N environments live in
+HBM and one kernel launch advances them; there are no worker processes, pipes or pickles.
+
+A zero-host-round-trip variant (`step_device`) returns reward/done/info as device tensors for the
+device-resident rollout loop.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _capi
+
+# crowd_sim/envs/utils/info.py equivalents (same __str__), index = CN_INFO_* code
+class Nothing(object):
+    def __str__(self):
+        return ''
+
+
+class Timeout(object):
+    def __str__(self):
+        return 'Timeout'
+
+
+class Collision(object):
+    def __str__(self):
+        return 'Collision'
+
+
+class ReachGoal(object):
+    def __str__(self):
+        return 'Reaching goal'
+
+
+class Danger(object):
+    def __init__(self, min_dist=0.0):
+        self.min_dist = min_dist
+
+    def __str__(self):
+        return 'Too close'
+
+
+_INFO_CLASSES = (Nothing, Timeout, Collision, ReachGoal, Danger)
+
+
+class _Space(object):
+    """Minimal Box-like descriptor (shape, dtype) — gym is not a dependency of the engine."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.low = -np.inf
+        self.high = np.inf
+
+
+class _DictSpace(object):
+    def __init__(self, spaces):
+        self.spaces = OrderedDict(sorted(spaces.items()))
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+
+class Box(_Space):
+    pass
+
+
+def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None, rank_offset=0, device_index=0):
+    """Snapshot a reference `Config` object (crowd_nav/configs/config.py) into the flat cn_config."""
+    if config.sim.human_num_range != 0:
+        raise NotImplementedError("sim.human_num_range > 0 is outside the engine's scope (SURVEY.md §8f row 4)")
+    if config.action_space.kinematics != "holonomic" or config.humans.policy != "orca" or config.robot.visible:
+        raise NotImplementedError("engine covers holonomic robot, ORCA humans, robot.visible=False")
+    if env_name == "CrowdSimPred-v0":
+        if config.sim.predict_method != "const_vel":
+            raise NotImplementedError("CrowdSimPred-v0 is covered for predict_method='const_vel'")
+        const_vel = 1
+    elif env_name == "CrowdSimVarNum-v0":
+        const_vel = 0
+    else:
+        raise NotImplementedError("env id %r is not covered by the CUDA engine" % env_name)
+    sort_humans = getattr(getattr(config, "args", None), "sort_humans", True)
+    return _capi.default_config_dict(
+        num_envs=num_envs, nenv_total=nenv_total or num_envs, rank_offset=rank_offset, seed=seed,
+        human_num=config.sim.human_num, predict_steps=config.sim.predict_steps, const_vel=const_vel,
+        randomize_attributes=int(bool(config.env.randomize_attributes)),
+        random_goal_changing=int(bool(config.humans.random_goal_changing)),
+        end_goal_changing=int(bool(config.humans.end_goal_changing)), sort_humans=int(bool(sort_humans)),
+        device=device_index, time_step=float(config.env.time_step), time_limit=float(config.env.time_limit),
+        pred_timestep=float(config.data.pred_timestep), circle_radius=float(config.sim.circle_radius),
+        arena_size=float(config.sim.arena_size), discomfort_dist=float(config.reward.discomfort_dist),
+        discomfort_penalty_factor=float(config.reward.discomfort_penalty_factor),
+        success_reward=float(config.reward.success_reward), collision_penalty=float(config.reward.collision_penalty),
+        human_radius=float(config.humans.radius), human_v_pref=float(config.humans.v_pref),
+        human_fov=float(config.humans.FOV), robot_radius=float(config.robot.radius),
+        robot_v_pref=float(config.robot.v_pref), robot_fov=float(config.robot.FOV),
+        sensor_range=float(config.robot.sensor_range), goal_change_chance=float(config.humans.goal_change_chance),
+        orca_neighbor_dist=float(config.orca.neighbor_dist), orca_safety_space=float(config.orca.safety_space),
+        orca_time_horizon=float(config.orca.time_horizon))
+
+
+class LazyInfos(object):
+    """Sequence of per-env info dicts, materialised on access (train.py:180-189 iterates it)."""
+
+    def __init__(self, info_codes, aux, done, ep_ret, ep_len):
+        self._codes, self._aux, self._done, self._ret, self._len = info_codes, aux, done, ep_ret, ep_len
+
+    def __len__(self):
+        return len(self._codes)
+
+    def __getitem__(self, i):
+        code = int(self._codes[i])
+        obj = Danger(float(self._aux[i])) if code == 4 else _INFO_CLASSES[code]()
+        d = {'info': obj}
+        if self._done[i]:
+            d['episode'] = {'r': round(float(self._ret[i]), 6), 'l': int(self._len[i])}
+        return d
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+class CudaCrowdVecEnv(object):
+    """N crowd-navigation environments resident on one GPU (one shard of the job)."""
+
+    def __init__(self, num_envs=None, device=None, cfg=None, **cfg_over):
+        self.lib = _capi.load_library()
+        self.device = torch.device(device if device is not None else "cuda:0")
+        if self.device.type != "cuda":
+            raise RuntimeError("CudaCrowdVecEnv needs a CUDA device (no CPU fallback)")
+        d = dict(cfg) if cfg is not None else _capi.default_config_dict()
+        if num_envs is not None:
+            d["num_envs"] = num_envs
+            if cfg is None and "nenv_total" not in cfg_over:
+                d["nenv_total"] = num_envs
+        d.update(cfg_over)
+        d["device"] = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.cfgd = d
+        self._cfg = _capi.config_from_dict(d)
+        self._h = C.c_void_p()
+        _capi.check(self.lib, self.lib.cn_env_create(C.byref(self._cfg), C.byref(self._h)), "cn_env_create")
+        N, H = d["num_envs"], d["human_num"]
+        W = 2 * (d["predict_steps"] + 1) if d["const_vel"] else 2
+        self.num_envs, self.human_num, self.row_width = N, H, W
+        spaces = {
+            'robot_node': Box((1, 7)), 'temporal_edges': Box((1, 2)), 'spatial_edges': Box((H, W)),
+            'detected_human_num': Box((1,)),
+        }
+        if not d["const_vel"]:
+            spaces['visible_masks'] = Box((H,), np.bool_)
+        self.observation_space = _DictSpace(spaces)
+        self.action_space = Box((2,))
+        dev = self.device
+        # double-buffered observation tensors so a returned dict stays valid for one more step
+        self._obs_bufs = [self._alloc_obs(dev) for _ in range(2)]
+        self._flip = 0
+        self._out = dict(reward=torch.zeros(N, dtype=torch.float32, device=dev),
+                         done=torch.zeros(N, dtype=torch.uint8, device=dev),
+                         info=torch.zeros(N, dtype=torch.int32, device=dev),
+                         info_aux=torch.zeros(N, dtype=torch.float32, device=dev),
+                         ep_ret=torch.zeros(N, dtype=torch.float64, device=dev),
+                         ep_len=torch.zeros(N, dtype=torch.int32, device=dev))
+        self._outp = _capi.CnStepPtrs(*[self._out[k].data_ptr() for k, _ in _capi.CnStepPtrs._fields_])
+        # one packed pinned host buffer for the per-step D2H of (reward, done, info, aux, ep_ret, ep_len)
+        self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self._out.items()}
+        self.closed = False
+
+    def _alloc_obs(self, dev):
+        N, H, W = self.num_envs, self.human_num, self.row_width
+        t = OrderedDict(robot_node=torch.zeros(N, 1, 7, device=dev), temporal_edges=torch.zeros(N, 1, 2, device=dev),
+                        spatial_edges=torch.zeros(N, H, W, device=dev), detected_human_num=torch.zeros(N, 1, device=dev))
+        if not self.cfgd["const_vel"]:
+            t['visible_masks'] = torch.zeros(N, H, dtype=torch.bool, device=dev)
+        ptrs = _capi.CnObsPtrs(*[t[k].data_ptr() if k in t else None for k, _ in _capi.CnObsPtrs._fields_])
+        return t, ptrs
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ VecEnv surface
+    def reset(self):
+        self._flip ^= 1
+        obs, ptrs = self._obs_bufs[self._flip]
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib, self.lib.cn_env_reset(self._h, C.byref(ptrs), self._stream()), "cn_env_reset")
+        return dict(obs)
+
+    def step_device(self, actions):
+        """Device-resident step: returns (obs, reward[N] f32, done[N] u8, info[N] i32) as device tensors
+        (views of internal buffers, valid until the next step)."""
+        if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
+            actions = actions.to(self.device, torch.float32).contiguous()
+        assert actions.shape == (self.num_envs, 2)
+        self._flip ^= 1
+        obs, ptrs = self._obs_bufs[self._flip]
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib, self.lib.cn_env_step(self._h, C.c_void_p(actions.data_ptr()), C.byref(ptrs),
+                                                       C.byref(self._outp), self._stream()), "cn_env_step")
+        return dict(obs), self._out["reward"], self._out["done"], self._out["info"]
+
+    def step_async(self, actions):
+        self._pending = self.step_device(actions)
+
+    def step_wait(self):
+        obs, _, _, _ = self._pending
+        for k, v in self._out.items():
+            self._host[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        h = self._host
+        reward = h["reward"].clone().unsqueeze(1)
+        done = h["done"].numpy().astype(np.bool_)
+        infos = LazyInfos(h["info"].numpy().copy(), h["info_aux"].numpy().copy(), done, h["ep_ret"].numpy().copy(),
+                          h["ep_len"].numpy().copy())
+        return obs, reward, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def talk2Env(self, data):
+        return np.ones(self.num_envs, dtype=bool)
+
+    def render(self, mode='human'):
+        raise NotImplementedError("rendering is out of scope (SURVEY.md §2.1 row 1)")
+
+    def close(self):
+        if not self.closed and self._h:
+            self.lib.cn_env_destroy(self._h)
+            self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    # ------------------------------------------------------------------ parity-test access
+    _DT = dict(rpx="f8", rpy="f8", rgx="f8", rgy="f8", rvx="f4", rvy="f4", potential="f8", fut_pen="f8",
+               nd_global="f8", ep_ret="f8", ep_len="i4", step_count="i4", case_counter="u4",
+               hpx="f8", hpy="f8", hgx="f8", hgy="f8", hrad="f8", hvpref="f8", hvx="f4", hvy="f4",
+               bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
+               sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",
+               last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4")
+
+    def get_state(self, name):
+        nbytes = self.lib.cn_env_state_bytes(self._h, name.encode())
+        if not nbytes:
+            raise KeyError(name)
+        arr = np.zeros(nbytes // np.dtype(self._DT[name]).itemsize, self._DT[name])
+        _capi.check(self.lib, self.lib.cn_env_state_copy(self._h, name.encode(), arr.ctypes.data, nbytes, 0),
+                    "cn_env_state_copy")
+        return arr
+
+    def set_state(self, name, arr):
+        arr = np.ascontiguousarray(arr, dtype=self._DT[name])
+        _capi.check(self.lib, self.lib.cn_env_state_copy(self._h, name.encode(), arr.ctypes.data, arr.nbytes, 1),
+                    "cn_env_state_copy")
+
+    def launch_count(self):
+        return int(self.lib.cn_env_launch_count(self._h))
+
+
+def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, device, allow_early_resets,
+                  num_frame_stack=None, config=None, ax=None, test_case=-1, wrap_pytorch=True,
+                  pretext_wrapper=False, nenv_total=None, rank_offset=0):
+    """Same signature as rl/networks/envs.py:97-140.  Returns the CUDA vec env (already 'VecPyTorch')."""
+    if pretext_wrapper:
+        raise NotImplementedError("VecPretextNormalize / GST predictor is the 'next' row (SURVEY.md §8f row 2)")
+    device = torch.device(device)
+    d = config_dict_from_reference(config, num_processes, seed, env_name, nenv_total=nenv_total,
+                                   rank_offset=rank_offset,
+                                   device_index=device.index if device.index is not None else 0)
+    return CudaCrowdVecEnv(device=device, cfg=d)

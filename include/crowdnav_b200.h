@@ -1,0 +1,164 @@
+/*
+ * crowdnav_b200 — C ABI of the B200-native crowd-navigation rollout engine.
+ *
+ * Drop-in boundary for the reference's PPO-rollout hot path.  The reference
+ * has no FFI today (it is duck-typed Python); each entry point below names the reference
+ * interface it replaces.  The Python host mirror (crowdnav_prediction_attngraph_b200/) binds these
+ * with ctypes and re-exposes the reference's own VecEnv / Policy surface; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is CALLER-OWNED DEVICE memory (e.g. a PyTorch CUDA tensor);
+ *     h_* is caller-owned host memory.  Step calls never allocate.
+ *   - calls enqueue work on `stream` (a cudaStream_t passed as void*) and do not synchronise,
+ *     except the *_host variants, which copy through host buffers and return when done.
+ *   - return value: 0 = ok, non-zero = error; cn_last_error() gives the message of the last
+ *     failure on the calling thread.  A missing CUDA device is an error, never a CPU fallback.
+ *   - one host thread per handle; handles on different GPUs are independent.
+ */
+#ifndef CROWDNAV_B200_H
+#define CROWDNAV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CN_ABI_VERSION 1
+
+/* info codes — crowd_sim/envs/utils/info.py (Nothing, Timeout, Collision, ReachGoal, Danger) */
+#define CN_INFO_NOTHING_C 0
+#define CN_INFO_TIMEOUT_C 1
+#define CN_INFO_COLLISION_C 2
+#define CN_INFO_REACHGOAL_C 3
+#define CN_INFO_DANGER_C 4
+
+/* Flat snapshot of the reference Config the hot path reads
+ * (crowd_nav/configs/config.py:16-120, arguments.py:47,206; make_env: rl/networks/envs.py:51-58). */
+typedef struct cn_config {
+  int32_t num_envs;          /* environments owned by this handle (this GPU's shard)            */
+  int32_t nenv_total;        /* env.nenv: total environments of the job (case_counter stride)   */
+  int32_t rank_offset;       /* global index of this shard's env 0 (thisSeed = seed + rank)     */
+  int32_t seed;              /* --seed (arguments.py:47)                                        */
+  int32_t human_num;         /* sim.human_num (sim.human_num_range must be 0)                   */
+  int32_t predict_steps;     /* sim.predict_steps                                               */
+  int32_t const_vel;         /* 1: CrowdSimPred-v0 / 'const_vel'; 0: CrowdSimVarNum-v0 / 'none' */
+  int32_t randomize_attributes;   /* env.randomize_attributes                                   */
+  int32_t random_goal_changing;   /* humans.random_goal_changing                                */
+  int32_t end_goal_changing;      /* humans.end_goal_changing                                   */
+  int32_t sort_humans;            /* args.sort_humans                                           */
+  int32_t device;                 /* CUDA device ordinal                                        */
+  double time_step, time_limit, pred_timestep;
+  double circle_radius, arena_size;
+  double discomfort_dist, discomfort_penalty_factor, success_reward, collision_penalty;
+  double human_radius, human_v_pref, human_fov;     /* FOV as multiples of pi, like the Config  */
+  double robot_radius, robot_v_pref, robot_fov, sensor_range;
+  double goal_change_chance;
+  double orca_neighbor_dist, orca_safety_space, orca_time_horizon;
+} cn_config;
+
+/* Observation buffers: the dict rl/networks/shmem_vec_env.py:109-116 returns, float32.       */
+typedef struct cn_obs_ptrs {
+  float *robot_node;          /* [N,1,7]                                                       */
+  float *temporal_edges;      /* [N,1,2]                                                       */
+  float *spatial_edges;       /* [N,H,W]  W = 2*(predict_steps+1) or 2                         */
+  float *detected_human_num;  /* [N,1]                                                         */
+  uint8_t *visible_masks;     /* [N,H] or NULL (CrowdSimVarNum-v0 only)                        */
+} cn_obs_ptrs;
+
+/* Per-step results: (rews, dones, infos) of ShmemVecEnv.step_wait + bench.Monitor's episode. */
+typedef struct cn_step_ptrs {
+  float *reward;       /* [N]                                                                  */
+  uint8_t *done;       /* [N]                                                                  */
+  int32_t *info;       /* [N] CN_INFO_*                                                        */
+  float *info_aux;     /* [N] Danger.min_dist                                                  */
+  double *ep_ret;      /* [N] info['episode']['r'] (valid where done)                          */
+  int32_t *ep_len;     /* [N] info['episode']['l'] (valid where done)                          */
+} cn_step_ptrs;
+
+typedef struct cn_env cn_env;
+
+const char *cn_last_error(void);
+int cn_abi_version(void);
+
+/* replaces: make_vec_envs / ShmemVecEnv.__init__ + env.configure (rl/networks/envs.py:97-140,
+ * rl/networks/shmem_vec_env.py:26-58): N environments resident in HBM on cfg->device.          */
+int cn_env_create(const cn_config *cfg, cn_env **out);
+int cn_env_destroy(cn_env *env);
+
+/* replaces: ShmemVecEnv.reset (shmem_vec_env.py:62-68) -> CrowdSimVarNum.reset for every env.  */
+int cn_env_reset(cn_env *env, const cn_obs_ptrs *d_obs, void *stream);
+
+/* replaces: ShmemVecEnv.step_async/step_wait + _subproc_worker 'step' (shmem_vec_env.py:70-80,
+ * 138-142): CrowdSimPred.step for every env, auto-reset where done.  d_action: float32 [N,2].   */
+int cn_env_step(cn_env *env, const float *d_action, const cn_obs_ptrs *d_obs,
+                const cn_step_ptrs *d_out, void *stream);
+
+/* Same as cn_env_step with HOST buffers (the numpy arrays of the reference's VecEnv contract):
+ * H2D of the actions, the step, D2H of observations and results; synchronous.                  */
+int cn_env_step_host(cn_env *env, const float *h_action, const cn_obs_ptrs *h_obs,
+                     const cn_step_ptrs *h_out);
+
+/* Parity-test access to the persistent state (SURVEY.md §8a'): copies the named field
+ * ("hpx", "rpx", "bvx", "mt", ...) device->host (dir 0) or host->device (dir 1).
+ * cn_env_state_bytes returns the field size in bytes (0 if unknown).                            */
+size_t cn_env_state_bytes(cn_env *env, const char *name);
+int cn_env_state_copy(cn_env *env, const char *name, void *h_buf, size_t bytes, int dir);
+
+/* Number of kernels this library launched since the handle was created (bench gpu_launches).  */
+int64_t cn_env_launch_count(cn_env *env);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Attention-graph policy (rl/networks/model.py:56-80, selfAttn_srnn_temp_node.py:360-449).    */
+
+typedef struct cn_policy cn_policy;
+
+typedef struct cn_policy_config {
+  int32_t num_envs;     /* N                                                                   */
+  int32_t human_num;    /* H                                                                   */
+  int32_t input_size;   /* spatial_edges row width (12 for Pred envs, 2 for VarNum)            */
+  int32_t device;
+  int32_t gemm_mode;    /* 0: fp32 CUDA-core GEMM; 1: tcgen05 3xFP16 error-compensated GEMM    */
+} cn_policy_config;
+
+int cn_policy_create(const cn_policy_config *cfg, cn_policy **out);
+int cn_policy_destroy(cn_policy *pol);
+
+/* Upload one state_dict tensor by its reference key, float32 host data.       */
+int cn_policy_set_param(cn_policy *pol, const char *key, const float *h_data, size_t count);
+/* Fold/convert the uploaded parameters into the kernels' layouts; call after all set_param.    */
+int cn_policy_finalize(cn_policy *pol, void *stream);
+
+typedef struct cn_act_ptrs {
+  /* inputs */
+  const float *robot_node, *temporal_edges, *spatial_edges, *detected_human_num;
+  const float *h_in;    /* rnn_hxs['human_node_rnn'] [N,1,128]                                  */
+  const float *masks;   /* [N,1]                                                                */
+  const float *noise;   /* [N,2] standard normal draws, or NULL for deterministic (mode)        */
+  /* outputs */
+  float *value;         /* [N,1]                                                                */
+  float *action;        /* [N,2]                                                                */
+  float *log_prob;      /* [N,1]                                                                */
+  float *h_out;         /* [N,1,128]                                                            */
+  float *action_mean;   /* [N,2] (dist.fc_mean output; parity tests)                            */
+} cn_act_ptrs;
+
+/* replaces: Policy.act (rl/networks/model.py:56-74) with infer=True.                           */
+int cn_policy_act(cn_policy *pol, const cn_act_ptrs *d, void *stream);
+int64_t cn_policy_launch_count(cn_policy *pol);
+
+/* Per-stage device timing of cn_policy_act (CUDA events on the launching stream), for bench.py's
+ * roofline line.  enable != 0 records events around every stage of subsequent calls;
+ * cn_policy_stage_ms synchronises and writes the last call's stage durations (ms) into out[0..n).
+ * Stage names: cn_policy_stage_name(i), i < cn_policy_stage_count().                            */
+int cn_policy_profile(cn_policy *pol, int enable);
+int cn_policy_stage_count(void);
+const char *cn_policy_stage_name(int i);
+int cn_policy_stage_ms(cn_policy *pol, float *out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWDNAV_B200_H */

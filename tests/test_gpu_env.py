@@ -1,0 +1,123 @@
+"""GPU parity tests of the environment step kernel, called through the C ABI.
+
+  * golden replay: the CUDA engine vs vectors recorded from the unmodified reference
+    (bit-exact done / info / visibility / ORCA line counts and fp32 velocities; fp64 positions
+    1e-9 — CUDA's sin/cos/pow are not bit-identical to glibc's, so spawn positions may move by ulps);
+  * lock-step vs the oracle at a larger N with policy-like random actions;
+  * full-size (N = 4096) size-independent properties: determinism, shard invariance
+    (one 4096-env handle == two 2048-env shards with rank offsets), structural invariants.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import ENV_CASES, load_env_case, replay
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(**over):
+    from crowdnav_prediction_attngraph_b200.vec_env import CudaCrowdVecEnv
+    return CudaCrowdVecEnv(device="cuda:0", **over)
+
+
+def _np_obs(obs):
+    return {k: v.cpu().numpy() for k, v in obs.items()}
+
+
+@pytest.mark.parametrize("name", ENV_CASES)
+def test_cuda_env_matches_reference_golden(name):
+    g, case, over = load_env_case(name)
+    env = _engine(**over)
+
+    def step(a):
+        obs, rew, done, info = env.step_device(torch.from_numpy(a).cuda())
+        out = dict(reward=rew.cpu().numpy(), done=done.cpu().numpy(), info=info.cpu().numpy())
+        return _np_obs(obs), out
+
+    bad = replay(g, case, lambda: _np_obs(env.reset()), step, env.get_state, pos_tol=1e-9)
+    assert not bad, bad[:5]
+
+
+def test_cuda_env_matches_oracle_lockstep():
+    from oracle.crowd_env import EnvConfig, OracleVecEnv
+    import rvo2
+    rvo2.ONLY_AGENT0 = True
+    N, H, T = 48, 20, 60
+    env = _engine(num_envs=N, human_num=H, seed=31)
+    orc = OracleVecEnv(EnvConfig(human_num=H), N, seed=31)
+    obs, oobs = _np_obs(env.reset()), orc.reset()
+    rng = np.random.RandomState(5)
+    for t in range(T):
+        for k in oobs:
+            np.testing.assert_allclose(obs[k], oobs[k], atol=1e-5, err_msg="%s t=%d" % (k, t))
+        a = rng.uniform(-1.3, 1.3, (N, 2)).astype(np.float32)
+        o, rew, done, infos = env.step(torch.from_numpy(a).cuda())
+        obs = _np_obs(o)
+        oobs, orew, odone, oinfos = orc.step(a)
+        assert np.array_equal(done, odone), t
+        assert [int(i["info"]) for i in oinfos] == [int(c) for c in env._host["info"].numpy()], t
+        np.testing.assert_allclose(rew.numpy()[:, 0], orew, atol=1e-5)
+        for k, (i, oi) in enumerate(zip(infos, oinfos)):
+            if odone[k]:
+                assert i["episode"]["l"] == oi["episode"]["l"]
+                assert abs(i["episode"]["r"] - oi["episode"]["r"]) < 1e-4
+
+
+def test_full_size_properties():
+    N, H, T = 4096, 20, 40
+    a_env = _engine(num_envs=N, human_num=H, seed=425)
+    b_env = _engine(num_envs=N, human_num=H, seed=425)
+    s0 = _engine(num_envs=N // 2, nenv_total=N, rank_offset=0, human_num=H, seed=425)
+    s1 = _engine(num_envs=N // 2, nenv_total=N, rank_offset=N // 2, human_num=H, seed=425)
+    oa, ob_, o0, o1 = a_env.reset(), b_env.reset(), s0.reset(), s1.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    dones = 0
+    for t in range(T):
+        for k in oa:
+            assert torch.equal(oa[k], ob_[k]), "nondeterministic %s" % k
+            assert torch.equal(oa[k], torch.cat([o0[k], o1[k]])), "shard variance %s" % k
+        sp, n = oa["spatial_edges"], oa["detected_human_num"][:, 0]
+        # rows beyond detected_human_num are the padding value 15; rows sorted by distance
+        pad = torch.arange(H, device="cuda")[None, :] >= n[:, None]
+        nvis_true = (sp[:, :, 0] != 15).sum(1)
+        assert torch.all((nvis_true == n) | ((nvis_true == 0) & (n == 1)))
+        assert torch.all(sp[pad & (nvis_true > 0)[:, None]] == 15)
+        d = torch.where(pad, torch.full_like(sp[:, :, 0], 1e9), torch.linalg.norm(sp[:, :, :2].double(), dim=-1).float())
+        assert torch.all(d[:, 1:] >= d[:, :-1] - 1e-5)
+        a = torch.randn(N, 2, device="cuda", generator=gen)
+        oa, ra, da, ia = a_env.step_device(a)
+        ob_, rb, db, ib = b_env.step_device(a)
+        o0, r0, d0, i0 = s0.step_device(a[: N // 2].contiguous())
+        o1, r1, d1, i1 = s1.step_device(a[N // 2:].contiguous())
+        assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(ia, ib)
+        assert torch.equal(ra, torch.cat([r0, r1])) and torch.equal(da, torch.cat([d0, d1]))
+        # done <=> info in {Timeout, Collision, ReachGoal}
+        assert torch.equal(da.bool(), (ia >= 1) & (ia <= 3))
+        dones += int(da.sum())
+        sc = torch.from_numpy(a_env.get_state("step_count"))
+        assert torch.all(sc[da.cpu().bool()] == 0)
+    assert dones > 0
+    # every env that finished was re-seeded with case_counter advanced by nenv_total
+    cc = a_env.get_state("case_counter")
+    assert np.all(cc % N == 0) and cc.max() >= N
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    import ctypes as C
+    from crowdnav_prediction_attngraph_b200 import _capi
+    N, H = 32, 20
+    e1, e2 = _engine(num_envs=N, human_num=H, seed=9), _engine(num_envs=N, human_num=H, seed=9)
+    e1.reset(), e2.reset()
+    a = np.random.RandomState(0).uniform(-1, 1, (N, 2)).astype(np.float32)
+    obs, rew, done, info = e1.step_device(torch.from_numpy(a).cuda())
+    h_ob = dict(robot_node=np.zeros((N, 1, 7), np.float32), temporal_edges=np.zeros((N, 1, 2), np.float32),
+                spatial_edges=np.zeros((N, H, 12), np.float32), detected_human_num=np.zeros((N, 1), np.float32))
+    h_out = dict(reward=np.zeros(N, np.float32), done=np.zeros(N, np.uint8), info=np.zeros(N, np.int32),
+                 info_aux=np.zeros(N, np.float32), ep_ret=np.zeros(N), ep_len=np.zeros(N, np.int32))
+    obp = _capi.CnObsPtrs(*[h_ob[k].ctypes.data if k in h_ob else None for k, _ in _capi.CnObsPtrs._fields_])
+    outp = _capi.CnStepPtrs(*[h_out[k].ctypes.data for k, _ in _capi.CnStepPtrs._fields_])
+    _capi.check(e2.lib, e2.lib.cn_env_step_host(e2._h, a.ctypes.data, C.byref(obp), C.byref(outp)), "step_host")
+    for k in h_ob:
+        assert np.array_equal(obs[k].cpu().numpy(), h_ob[k])
+    assert np.array_equal(rew.cpu().numpy(), h_out["reward"]) and np.array_equal(done.cpu().numpy(), h_out["done"])
