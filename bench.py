@@ -56,6 +56,11 @@ def _cpu_worker(args):
     import numpy as np
     import torch
     torch.set_num_threads(1)
+    try:                       # numpy's BLAS pool must not oversubscribe the cores (one worker per core)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     from oracle.crowd_env import EnvConfig, OracleVecEnv
     from oracle.policy_ref import PolicyRef
     env = OracleVecEnv(EnvConfig(human_num=HUMANS), k, seed=seed, rank_offset=widx * k, nenv_total=1 << 20)
@@ -80,7 +85,9 @@ def _cpu_worker(args):
 def cpu_rollout_rate(steps, warmup, envs_per_worker=4, workers=None):
     """env-steps/s of the oracle port using every host core (fork workers, like ShmemVecEnv)."""
     import multiprocessing as mp
-    workers = workers or (os.cpu_count() or 1)
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    workers = workers or len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         times = pool.map(_cpu_worker, [(w, envs_per_worker, warmup, steps, 425) for w in range(workers)])

@@ -1,0 +1,258 @@
+// tcgen05 / TMEM / TMA GEMM for the policy's 512-wide projections (sm_100a only).
+//
+//   C[M,N] = act( (A_hi + A_lo)[M,K] . (B_hi + B_lo)[N,K]^T * (1/scale_b) + bias[N] )
+//
+// "3xFP16" error-compensated product: every fp32 operand is split into two fp16 pieces
+// (hi = rn(x), lo = rn(x - hi): 22 significand bits) and the three significant partial
+// products  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi  are accumulated by the 5th-gen tensor cores in
+// an fp32 TMEM accumulator.  Measured against the fp32 reference policy this keeps the action
+// mean / value within 2e-5 (same as a plain fp32 CUDA-core GEMM), where single-pass TF32/BF16
+// would break the 1e-4 tolerance.  Weights are pre-scaled by 2^6 so their lo
+// pieces stay in fp16's normal range; the epilogue undoes the power-of-two scale exactly.
+//
+// Tiling: one 128 x 256 output tile per CTA, K in blocks of 64 fp16 (= one 128-byte swizzle
+// atom), 2-stage TMA->smem ring (4 operand tiles = 96 KB per stage), accumulator 128 lanes x 256
+// columns of TMEM.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global, each warp owns
+// the TMEM lane quadrant warp_id % 4).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TC_BM 128
+#define TC_BN 256
+#define TC_BK 64
+#define TC_STAGES 2
+#define TC_A_TILE_BYTES (TC_BM * TC_BK * 2)           // 16 KB
+#define TC_B_TILE_BYTES (TC_BN * TC_BK * 2)           // 32 KB
+#define TC_STAGE_BYTES (2 * TC_A_TILE_BYTES + 2 * TC_B_TILE_BYTES)   // 96 KB
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
+#define TC_THREADS 192
+
+struct TcEpilogue {
+  const float* bias;     // [N] or null
+  float inv_scale;       // 1 / scale_b
+  int act;               // CN_ACT_*
+  float* c32;            // fp32 output [M, ldc] or null
+  int ldc;
+  __half* out_hi;        // split fp16 output [M, ldh] or null (A operand of the next GEMM)
+  __half* out_lo;
+  int ldh;
+};
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) |
+//   [32,46) SBO >> 4 (8 rows * 128 B = 1024 B) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, K-major
+__device__ __forceinline__ uint32_t make_idesc() {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+         ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                  const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, int M, int N,
+                  int K, TcEpilogue ep) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t raw = tc::smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* base_ptr = tc_smem_raw + (base - raw);
+  const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;  // barriers after the operand ring
+  // full[s] = bar_base + 8 s ; empty[s] = bar_base + 16 + 8 s ; tmem_full = bar_base + 32 ; tmem ptr at +40
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 40);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int num_kb = K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      tc::mbar_init(bar_base + 8 * s, 1);         // full: producer's arrive.expect_tx
+      tc::mbar_init(bar_base + 16 + 8 * s, 1);    // empty: one tcgen05.commit
+    }
+    tc::mbar_init(bar_base + 32, 1);              // accumulator ready
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+  }
+  if (warp == 1) {
+    // allocate 256 TMEM columns (power of two >= 32); the same warp frees them at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr_smem)),
+                 "r"((uint32_t)TC_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        tc::mbar_wait(bar_base + 16 + 8 * s, ph ^ 1u);            // slot free (first pass returns immediately)
+        const uint32_t full = bar_base + 8 * s;
+        tc::mbar_expect_tx(full, TC_STAGE_BYTES);
+        const uint32_t st = base + s * TC_STAGE_BYTES;
+        tc::tma_load_2d(st, &map_ahi, full, kb * TC_BK, m0);
+        tc::tma_load_2d(st + TC_A_TILE_BYTES, &map_alo, full, kb * TC_BK, m0);
+        tc::tma_load_2d(st + 2 * TC_A_TILE_BYTES, &map_bhi, full, kb * TC_BK, n0);
+        tc::tma_load_2d(st + 2 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &map_blo, full, kb * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        tc::mbar_wait(bar_base + 8 * s, ph);                      // TMA bytes landed
+        tc::tcgen05_fence_after();
+        const uint32_t st = base + s * TC_STAGE_BYTES;
+        const uint32_t a_hi = st, a_lo = st + TC_A_TILE_BYTES, b_hi = st + 2 * TC_A_TILE_BYTES,
+                       b_lo = st + 2 * TC_A_TILE_BYTES + TC_B_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t koff = k * 32;                           // 16 fp16 = 32 bytes inside the swizzle atom
+          const uint64_t dah = tc::make_desc(a_hi + koff), dal = tc::make_desc(a_lo + koff);
+          const uint64_t dbh = tc::make_desc(b_hi + koff), dbl = tc::make_desc(b_lo + koff);
+          tc::mma_f16(tmem_acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc::mma_f16(tmem_acc, dah, dbl, idesc, 1u);
+          tc::mma_f16(tmem_acc, dal, dbh, idesc, 1u);
+        }
+        tc::mma_commit(bar_base + 16 + 8 * s);                    // frees the smem slot when the MMAs retire
+      }
+      tc::mma_commit(bar_base + 32);                              // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                                       // TMEM lane quadrant this warp may access
+    tc::mbar_wait(bar_base + 32, 0);
+    tc::tcgen05_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      const int nb = n0 + c * 32;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) * ep.inv_scale;
+        if (ep.bias) x += __ldg(ep.bias + nb + j);
+        if (ep.act == 1) x = x > 0.0f ? x : 0.0f;
+        else if (ep.act == 2) x = tanhf(x);
+        v[j] = x;
+      }
+      if (row_ok) {
+        if (ep.c32) {
+          float4* dst = reinterpret_cast<float4*>(ep.c32 + (size_t)row * ep.ldc + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (ep.out_hi) {
+          uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + (size_t)row * ep.ldh + nb);
+          uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + (size_t)row * ep.ldh + nb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float x0 = fminf(fmaxf(v[8 * j + 2 * t], -65504.0f), 65504.0f);
+              const float x1 = fminf(fmaxf(v[8 * j + 2 * t + 1], -65504.0f), 65504.0f);
+              const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+              const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+              ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            dh[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            dl[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
+        }
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TC_BN) : "memory");
+  }
+}
+
+// fp32 -> (hi, lo) fp16 split with an exact power-of-two pre-scale (weights at finalize time,
+// and the generic "split this activation" helper).
+__global__ void cn_split_f16_kernel(const float* __restrict__ src, float scale, __half* __restrict__ hi,
+                                    __half* __restrict__ lo, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float x = fminf(fmaxf(src[i] * scale, -65504.0f), 65504.0f);
+  const __half h = __float2half_rn(x);
+  hi[i] = h;
+  lo[i] = __float2half_rn(x - __half2float(h));
+}

@@ -16,6 +16,7 @@
 #include "../../include/crowdnav_b200.h"
 #include "cn_host_util.h"
 #include "cn_policy_kernels.cuh"
+#include "cn_gemm_tc.cuh"
 
 struct cn_policy {
   cn_policy_config cfg;
@@ -29,6 +30,10 @@ struct cn_policy {
   float *W1, *b1, *W2, *b2, *Wqkv, *bqkv, *Wos, *bos;
   float *Wr, *br, *Wet, *bet, *WsT, *bs, *Wa, *ba, *Wih, *bih, *Whh, *bhh, *Wo, *bo;
   float *Wac1, *bac1, *Wa2, *ba2, *Wc2, *bc2, *wv_, *bv, *Wm, *bm, *logstd;
+  // tcgen05 path (gemm_mode 1): split-fp16 activations / weights and their TMA descriptors
+  __half *e1h, *e1l, *e2h, *e2l, *aoh, *aol;
+  __half *W2h, *W2l, *Wqkvh, *Wqkvl, *Wosh, *Wosl;
+  CUtensorMap m_e1h, m_e1l, m_e2h, m_e2l, m_aoh, m_aol, m_W2h, m_W2l, m_Wqkvh, m_Wqkvl, m_Wosh, m_Wosl;
   // optional per-stage profiling
   bool profile;
   std::vector<cudaEvent_t> ev;
@@ -64,6 +69,61 @@ const std::vector<float>* get(cn_policy* p, const char* key, size_t count) {
     return nullptr;
   }
   return &it->second;
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major [rows, K] tensor, box = 64 (K) x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows) {
+  EncodeFn enc = get_encode();
+  if (!enc) return cn_set_error("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cn_set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K);
+  return 0;
+}
+
+int halloc16(cn_policy* p, __half** ptr, size_t count) {
+  float* q = nullptr;
+  int rc = palloc(p, &q, (count + 1) / 2);
+  *ptr = reinterpret_cast<__half*>(q);
+  return rc;
+}
+
+// tcgen05 GEMM launch: C = act((Ahi+Alo)(Bhi+Blo)^T / scale + bias)
+void gemm_tc(cn_policy* p, cudaStream_t st, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+             const CUtensorMap& bl, int M, int N, int K, const float* bias, int act, float* c32, int ldc, __half* oh,
+             __half* ol, int ldh) {
+  TcEpilogue ep;
+  ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.c32 = c32; ep.ldc = ldc; ep.out_hi = oh; ep.out_lo = ol;
+  ep.ldh = ldh;
+  dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
+  cn_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ah, al, bh, bl, M, N, K, ep);
+  p->launches += 1;
+}
+
+void split16(cn_policy* p, cudaStream_t st, const float* src, float scale, __half* hi, __half* lo, size_t count) {
+  cn_split_f16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(src, scale, hi, lo, count);
+  p->launches += 1;
 }
 
 void gemm(cn_policy* p, cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias,
@@ -132,6 +192,24 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   WS(xr, N * 16); WS(rs, N * 256); WS(t1, N * 128); WS(u, N * 256); WS(wv, N * 256); WS(h0, N * 128);
   WS(gi, N * 384); WS(gh, N * 384); WS(outb, N * 256); WS(ac1, N * 512); WS(a2, N * 256); WS(c2, N * 256);
 #undef WS
+  if (!rc && cfg->gemm_mode == 1) {
+    rc = halloc16(p, &p->e1h, M * 128);
+    if (!rc) rc = halloc16(p, &p->e1l, M * 128);
+    if (!rc) rc = halloc16(p, &p->e2h, M * 512);
+    if (!rc) rc = halloc16(p, &p->e2l, M * 512);
+    if (!rc) rc = halloc16(p, &p->aoh, M * 512);
+    if (!rc) rc = halloc16(p, &p->aol, M * 512);
+    if (!rc) rc = make_map(&p->m_e1h, p->e1h, p->M, 128, TC_BM);
+    if (!rc) rc = make_map(&p->m_e1l, p->e1l, p->M, 128, TC_BM);
+    if (!rc) rc = make_map(&p->m_e2h, p->e2h, p->M, 512, TC_BM);
+    if (!rc) rc = make_map(&p->m_e2l, p->e2l, p->M, 512, TC_BM);
+    if (!rc) rc = make_map(&p->m_aoh, p->aoh, p->M, 512, TC_BM);
+    if (!rc) rc = make_map(&p->m_aol, p->aol, p->M, 512, TC_BM);
+    if (!rc) {
+      cudaError_t e2 = cudaFuncSetAttribute(cn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+      if (e2 != cudaSuccess) rc = cn_set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e2));
+    }
+  }
   if (rc) { cn_policy_destroy(p); return rc; }
   p->ws_allocs = p->allocs.size();
   const size_t attn_smem = ((size_t)p->H * 65 + (size_t)p->H * 64 + 256) * sizeof(float);
@@ -262,6 +340,26 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
   // Wos = Wsl (256x512) @ Wout (512x512);  bos = Wsl @ bout + bsl
   cn_fold_mm_kernel<<<dim3(4, 256), 128, 0, st>>>(d_wsl, d_wout, p->Wos, 256, 512, 512);
   cn_fold_mv_kernel<<<2, 128, 0, st>>>(d_wsl, d_bout, d_bsl, p->bos, 256, 512);
+  if (p->cfg.gemm_mode == 1) {
+    // fp16 (hi, lo) split of the tensor-core weights, pre-scaled by 2^6 (exact) so lo stays normal
+    if (!rc) rc = halloc16(p, &p->W2h, (size_t)512 * 128);
+    if (!rc) rc = halloc16(p, &p->W2l, (size_t)512 * 128);
+    if (!rc) rc = halloc16(p, &p->Wqkvh, (size_t)1536 * 512);
+    if (!rc) rc = halloc16(p, &p->Wqkvl, (size_t)1536 * 512);
+    if (!rc) rc = halloc16(p, &p->Wosh, (size_t)256 * 512);
+    if (!rc) rc = halloc16(p, &p->Wosl, (size_t)256 * 512);
+    if (rc) return rc;
+    split16(p, st, p->W2, 64.0f, p->W2h, p->W2l, (size_t)512 * 128);
+    split16(p, st, p->Wqkv, 64.0f, p->Wqkvh, p->Wqkvl, (size_t)1536 * 512);
+    split16(p, st, p->Wos, 64.0f, p->Wosh, p->Wosl, (size_t)256 * 512);
+    rc = make_map(&p->m_W2h, p->W2h, 512, 128, TC_BN);
+    if (!rc) rc = make_map(&p->m_W2l, p->W2l, 512, 128, TC_BN);
+    if (!rc) rc = make_map(&p->m_Wqkvh, p->Wqkvh, 1536, 512, TC_BN);
+    if (!rc) rc = make_map(&p->m_Wqkvl, p->Wqkvl, 1536, 512, TC_BN);
+    if (!rc) rc = make_map(&p->m_Wosh, p->Wosh, 256, 512, TC_BN);
+    if (!rc) rc = make_map(&p->m_Wosl, p->Wosl, 256, 512, TC_BN);
+    if (rc) return rc;
+  }
   cudaError_t err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) return cn_set_error("cn_policy_finalize: %s", cudaGetErrorString(err));
   p->finalized = true;
@@ -288,18 +386,24 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   // 1. human-human branch over all N*H rows
   mark(p, st, 1);
   gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU);
+  const bool tcm = p->cfg.gemm_mode == 1;
+  if (tcm) split16(p, st, p->e1, 1.0f, p->e1h, p->e1l, (size_t)M * 128);
   mark(p, st, 2);
-  gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU);
+  if (tcm) gemm_tc(p, st, p->m_e1h, p->m_e1l, p->m_W2h, p->m_W2l, M, 512, 128, p->b2, CN_ACT_RELU, nullptr, 0, p->e2h, p->e2l, 512);
+  else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU);
   mark(p, st, 3);
-  gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE);
+  if (tcm) gemm_tc(p, st, p->m_e2h, p->m_e2l, p->m_Wqkvh, p->m_Wqkvl, M, 1536, 512, p->bqkv, CN_ACT_NONE, p->qkv, 1536, nullptr, nullptr, 0);
+  else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE);
   mark(p, st, 4);
   {
     const size_t smem = ((size_t)H * 65 + (size_t)H * 64 + 256) * sizeof(float);
     cn_hh_attention_kernel<<<dim3(N, 8), 128, smem, st>>>(p->qkv, d->detected_human_num, H, p->ao);
     p->launches += 1;
   }
+  if (tcm) split16(p, st, p->ao, 1.0f, p->aoh, p->aol, (size_t)M * 512);
   mark(p, st, 5);
-  gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU);
+  if (tcm) gemm_tc(p, st, p->m_aoh, p->m_aol, p->m_Wosh, p->m_Wosl, M, 256, 512, p->bos, CN_ACT_RELU, p->sout, 256, nullptr, nullptr, 0);
+  else gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU);
   // 2. robot branch
   mark(p, st, 6);
   gemm(p, st, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
@@ -331,5 +435,33 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
 }
 
 int64_t cn_policy_launch_count(cn_policy* p) { return p ? p->launches : 0; }
+
+// Internal test hook (not part of the public header): C = act(A[M,K] W[N,K]^T + bias) through the
+// tcgen05 3xFP16 kernel, fp32 device pointers in/out.  Used by tests/test_gpu_gemm_tc.py.
+int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, float* dC, int M, int N, int K, int act) {
+  if (N % TC_BN || K % TC_BK) return cn_set_error("cn_internal_gemm_tc: need N %% 256 == 0 and K %% 64 == 0");
+  cn_policy tmp;
+  tmp.launches = 0;
+  __half *ah, *al, *bh, *bl;
+  int rc = halloc16(&tmp, &ah, (size_t)M * K);
+  if (!rc) rc = halloc16(&tmp, &al, (size_t)M * K);
+  if (!rc) rc = halloc16(&tmp, &bh, (size_t)N * K);
+  if (!rc) rc = halloc16(&tmp, &bl, (size_t)N * K);
+  CUtensorMap mah, mal, mbh, mbl;
+  if (!rc) rc = make_map(&mah, ah, M, K, TC_BM);
+  if (!rc) rc = make_map(&mal, al, M, K, TC_BM);
+  if (!rc) rc = make_map(&mbh, bh, N, K, TC_BN);
+  if (!rc) rc = make_map(&mbl, bl, N, K, TC_BN);
+  if (!rc) {
+    cudaFuncSetAttribute(cn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    split16(&tmp, 0, dA, 1.0f, ah, al, (size_t)M * K);
+    split16(&tmp, 0, dW, 64.0f, bh, bl, (size_t)N * K);
+    gemm_tc(&tmp, 0, mah, mal, mbh, mbl, M, N, K, dbias, act, dC, N, nullptr, nullptr, 0);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) rc = cn_set_error("cn_internal_gemm_tc: %s", cudaGetErrorString(err));
+  }
+  for (void* q : tmp.allocs) cudaFree(q);
+  return rc;
+}
 
 }  // extern "C"
