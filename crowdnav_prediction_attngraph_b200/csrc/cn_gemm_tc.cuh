@@ -40,6 +40,7 @@ struct TcEpilogue {
   __half* out_hi;        // split fp16 output [M, ldh] or null (A operand of the next GEMM)
   __half* out_lo;
   int ldh;
+  const int* m_ptr;      // optional device-side row count (compacted rows); tiles past it exit
 };
 
 namespace tc {
@@ -112,6 +113,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                   const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, int M, int N,
                   int K, TcEpilogue ep) {
+  if (ep.m_ptr) { const int mc = *ep.m_ptr; M = mc < M ? mc : M; }
+  if ((int)(blockIdx.y * TC_BM) >= M) return;       // uniform for the whole CTA: before any barrier / TMEM use
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = tc::smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment

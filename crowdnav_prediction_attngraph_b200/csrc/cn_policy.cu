@@ -38,6 +38,7 @@ struct cn_policy {
   bool profile;
   std::vector<cudaEvent_t> ev;
   // workspace
+  int *row_start, *mc;
   float *x16, *e1, *e2, *qkv, *ao, *sout, *xr, *rs, *t1, *u, *wv, *h0, *gi, *gh, *outb, *ac1, *a2, *c2;
 };
 
@@ -112,8 +113,9 @@ int halloc16(cn_policy* p, __half** ptr, size_t count) {
 // tcgen05 GEMM launch: C = act((Ahi+Alo)(Bhi+Blo)^T / scale + bias)
 void gemm_tc(cn_policy* p, cudaStream_t st, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
              const CUtensorMap& bl, int M, int N, int K, const float* bias, int act, float* c32, int ldc, __half* oh,
-             __half* ol, int ldh) {
+             __half* ol, int ldh, const int* m_ptr = nullptr) {
   TcEpilogue ep;
+  ep.m_ptr = m_ptr;
   ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.c32 = c32; ep.ldc = ldc; ep.out_hi = oh; ep.out_lo = ol;
   ep.ldh = ldh;
   dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
@@ -127,9 +129,10 @@ void split16(cn_policy* p, cudaStream_t st, const float* src, float scale, __hal
 }
 
 void gemm(cn_policy* p, cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias,
-          float* C, int ldc, int M, int N, int K, int act, int act_lo = 0, int act_hi = 1 << 30) {
+          float* C, int ldc, int M, int N, int K, int act, int act_lo = 0, int act_hi = 1 << 30,
+          const int* m_ptr = nullptr, __half* oh = nullptr, __half* ol = nullptr) {
   dim3 grid((N + CN_GEMM_BN - 1) / CN_GEMM_BN, (M + CN_GEMM_BM - 1) / CN_GEMM_BM);
-  cn_gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, act_lo, act_hi);
+  cn_gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, act_lo, act_hi, m_ptr, oh, ol);
   p->launches += 1;
 }
 
@@ -188,6 +191,11 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   const size_t M = (size_t)p->M, N = (size_t)p->N;
   int rc = 0;
 #define WS(name, count) if (!rc) rc = palloc(p, &p->name, (count))
+  {
+    float* q = nullptr;
+    if (!rc) rc = palloc(p, &q, N + 2); p->row_start = reinterpret_cast<int*>(q);
+    if (!rc) rc = palloc(p, &q, 4); p->mc = reinterpret_cast<int*>(q);
+  }
   WS(x16, M * 16); WS(e1, M * 128); WS(e2, M * 512); WS(qkv, M * 1536); WS(ao, M * 512); WS(sout, M * 256);
   WS(xr, N * 16); WS(rs, N * 256); WS(t1, N * 128); WS(u, N * 256); WS(wv, N * 256); WS(h0, N * 128);
   WS(gi, N * 384); WS(gh, N * 384); WS(outb, N * 256); WS(ac1, N * 512); WS(a2, N * 256); WS(c2, N * 256);
@@ -376,41 +384,44 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int N = p->N, H = p->H, M = p->M;
   mark(p, st, 0);
-  // 0. pack / pad inputs, h0 = h * mask
+  // 0. compaction offsets, pack / pad inputs, h0 = h * mask
   {
+    cn_row_offsets_kernel<<<1, 1024, 0, st>>>(d->detected_human_num, N, H, p->row_start, p->mc);
     const int total = M * 16 > N * 128 ? M * 16 : N * 128;
-    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, M, p->x16, d->temporal_edges,
-                                                               d->robot_node, d->h_in, d->masks, N, p->xr, p->h0);
-    p->launches += 1;
+    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->x16,
+                                                               d->temporal_edges, d->robot_node, d->h_in, d->masks, p->xr,
+                                                               p->h0);
+    p->launches += 2;
   }
-  // 1. human-human branch over all N*H rows
-  mark(p, st, 1);
-  gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU);
+  // 1. human-human branch over the Mc = sum_e n_e valid rows (device-side count p->mc)
   const bool tcm = p->cfg.gemm_mode == 1;
-  if (tcm) split16(p, st, p->e1, 1.0f, p->e1h, p->e1l, (size_t)M * 128);
+  const int* mc = p->mc;
+  mark(p, st, 1);
+  if (tcm) gemm(p, st, p->x16, 16, p->W1, 16, p->b1, nullptr, 128, M, 128, 16, CN_ACT_RELU, 0, 1 << 30, mc, p->e1h, p->e1l);
+  else gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU, 0, 1 << 30, mc);
   mark(p, st, 2);
-  if (tcm) gemm_tc(p, st, p->m_e1h, p->m_e1l, p->m_W2h, p->m_W2l, M, 512, 128, p->b2, CN_ACT_RELU, nullptr, 0, p->e2h, p->e2l, 512);
-  else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU);
+  if (tcm) gemm_tc(p, st, p->m_e1h, p->m_e1l, p->m_W2h, p->m_W2l, M, 512, 128, p->b2, CN_ACT_RELU, nullptr, 0, p->e2h, p->e2l, 512, mc);
+  else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU, 0, 1 << 30, mc);
   mark(p, st, 3);
-  if (tcm) gemm_tc(p, st, p->m_e2h, p->m_e2l, p->m_Wqkvh, p->m_Wqkvl, M, 1536, 512, p->bqkv, CN_ACT_NONE, p->qkv, 1536, nullptr, nullptr, 0);
-  else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE);
+  if (tcm) gemm_tc(p, st, p->m_e2h, p->m_e2l, p->m_Wqkvh, p->m_Wqkvl, M, 1536, 512, p->bqkv, CN_ACT_NONE, p->qkv, 1536, nullptr, nullptr, 0, mc);
+  else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, 1 << 30, mc);
   mark(p, st, 4);
   {
     const size_t smem = ((size_t)H * 65 + (size_t)H * 64 + 256) * sizeof(float);
-    cn_hh_attention_kernel<<<dim3(N, 8), 128, smem, st>>>(p->qkv, d->detected_human_num, H, p->ao);
+    cn_hh_attention_kernel<<<dim3(N, 8), 128, smem, st>>>(p->qkv, p->row_start, H, tcm ? nullptr : p->ao,
+                                                          tcm ? p->aoh : nullptr, tcm ? p->aol : nullptr);
     p->launches += 1;
   }
-  if (tcm) split16(p, st, p->ao, 1.0f, p->aoh, p->aol, (size_t)M * 512);
   mark(p, st, 5);
-  if (tcm) gemm_tc(p, st, p->m_aoh, p->m_aol, p->m_Wosh, p->m_Wosl, M, 256, 512, p->bos, CN_ACT_RELU, p->sout, 256, nullptr, nullptr, 0);
-  else gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU);
+  if (tcm) gemm_tc(p, st, p->m_aoh, p->m_aol, p->m_Wosh, p->m_Wosl, M, 256, 512, p->bos, CN_ACT_RELU, p->sout, 256, nullptr, nullptr, 0, mc);
+  else gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU, 0, 1 << 30, mc);
   // 2. robot branch
   mark(p, st, 6);
   gemm(p, st, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
   gemm(p, st, p->rs, 256, p->Wet, 256, p->bet, p->t1, 128, N, 128, 256, CN_ACT_RELU, 0, 64);   // [enc | te]
   gemm(p, st, p->t1 + 64, 128, p->WsT, 64, nullptr, p->u, 256, N, 256, 64, CN_ACT_NONE);        // u = W_s^T te
   mark(p, st, 7);
-  cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, d->detected_human_num, N, H,
+  cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, p->row_start, N, H,
                                                       p->wv);
   p->launches += 1;
   mark(p, st, 8);

@@ -5,6 +5,7 @@
 //   rl/networks/selfAttn_srnn_temp_node.py:262-285 + srnn_model.py:35-47 (EndRNN / GRU step)
 //   rl/networks/distributions.py:76-95,36-44       (DiagGaussian / FixedNormal)
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,7 +30,11 @@ __global__ void __launch_bounds__(256) cn_gemm_f32_kernel(const float* __restric
                                                           const float* __restrict__ W, int ldw,
                                                           const float* __restrict__ bias, float* __restrict__ Cout,
                                                           int ldc, int M, int N, int K, int act, int act_lo,
-                                                          int act_hi) {
+                                                          int act_hi, const int* __restrict__ m_ptr,
+                                                          __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  // m_ptr: optional device-side row count (compacted human rows); tiles past it exit immediately
+  if (m_ptr) { const int mc = *m_ptr; M = mc < M ? mc : M; }
+  if ((int)(blockIdx.y * CN_GEMM_BM) >= M) return;
   __shared__ __align__(16) float As[2][CN_GEMM_BK][CN_GEMM_BM + CN_GEMM_PAD];
   __shared__ __align__(16) float Bs[2][CN_GEMM_BK][CN_GEMM_BN + CN_GEMM_PAD];
   const int tid = threadIdx.x;
@@ -106,6 +111,17 @@ __global__ void __launch_bounds__(256) cn_gemm_f32_kernel(const float* __restric
         }
         v[j] = x;
       }
+      if (out_hi) {    // (hi, lo) fp16 split for the tensor-core consumer; same leading dimension
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (nb + j < N) {
+            const float c = fminf(fmaxf(v[j], -65504.0f), 65504.0f);
+            const __half hh = __float2half_rn(c);
+            out_hi[(size_t)m * ldc + nb + j] = hh;
+            out_lo[(size_t)m * ldc + nb + j] = __float2half_rn(c - __half2float(hh));
+          }
+        if (!Cout) continue;
+      }
       float* dst = Cout + (size_t)m * ldc + nb;
       if (nb + 3 < N && ((ldc & 3) == 0)) {
         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -139,16 +155,57 @@ __global__ void cn_fold_mv_kernel(const float* __restrict__ A, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------
-// Input packing: x16[M,16] = spatial_edges rows zero-padded to K=16;
+// Row compaction.  Humans are sorted by distance and rows j >= n_e = detected_human_num[e] are
+// padding: as attention KEYS they are masked (key_padding_mask), and as attention QUERIES their
+// outputs only reach the robot-human softmax, where masked_fill(-1e9) gives them weight exactly 0
+// (selfAttn_srnn_temp_node.py:49-60,165-170).  They cannot influence any output, so the per-human
+// pipeline runs on the compacted valid rows only:  row_start[e] = sum_{e' < e} n_e',  *mc = total.
+// Single CTA, 1024 threads, chunked inclusive scan (N <= a few 10^4).
+__global__ void __launch_bounds__(1024) cn_row_offsets_kernel(const float* __restrict__ detected, int N, int H,
+                                                              int* __restrict__ row_start, int* __restrict__ mc) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int e = base + tid;
+    int n = 0;
+    if (e < N) { n = (int)detected[e]; n = n < 1 ? 1 : (n > H ? H : n); }
+    int x = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int incl = x + (warp > 0 ? warp_sums[warp - 1] : 0) + carry;
+    if (e < N) row_start[e] = incl - n;
+    __syncthreads();
+    if (tid == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (tid == 0) { *mc = carry; row_start[N] = carry; }
+}
+
+// Input packing: x16[row_start[e] + j, 16] = spatial_edges[e, j] zero-padded to K=16 for j < n_e;
 // xr[N,16] = cat(temporal_edges(2), robot_node(7)) zero padded; h0 = h_in * mask.
-__global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win, int M, float* __restrict__ x16,
+__global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win, int H, int N,
+                                      const int* __restrict__ row_start, float* __restrict__ x16,
                                       const float* __restrict__ temporal, const float* __restrict__ robot,
-                                      const float* __restrict__ h_in, const float* __restrict__ masks, int N,
+                                      const float* __restrict__ h_in, const float* __restrict__ masks,
                                       float* __restrict__ xr, float* __restrict__ h0) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < M * 16) {
+  if (idx < N * H * 16) {
     const int r = idx >> 4, c = idx & 15;
-    x16[idx] = c < Win ? spatial[(size_t)r * Win + c] : 0.0f;
+    const int e = r / H, j = r - e * H;
+    const int rs = row_start[e], n = row_start[e + 1] - rs;
+    if (j < n) x16[(size_t)(rs + j) * 16 + c] = c < Win ? spatial[(size_t)r * Win + c] : 0.0f;
   }
   if (idx < N * 16) {
     const int e = idx >> 4, c = idx & 15;
@@ -166,17 +223,17 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
 // Keys j >= n_e are padding (key_padding_mask); query rows >= n_e are never consumed
 // downstream (their robot-human attention weight is exactly 0), they are written as zeros.
 __global__ void __launch_bounds__(128) cn_hh_attention_kernel(const float* __restrict__ qkv,
-                                                              const float* __restrict__ detected, int H,
-                                                              float* __restrict__ out /* [N*H,512] */) {
+                                                              const int* __restrict__ row_start, int H,
+                                                              float* __restrict__ out /* [Mc,512] or null */,
+                                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   extern __shared__ float sm[];
   const int e = blockIdx.x, hd = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int n = (int)detected[e];
-  n = n < 1 ? 1 : (n > H ? H : n);
+  const size_t row0 = (size_t)row_start[e];
+  const int n = row_start[e + 1] - row_start[e];      // valid (compacted) humans of this environment
   float* Ks = sm;                    // [H][65]
   float* Vs = sm + (size_t)H * 65;   // [H][64]
   float* Qs = Vs + (size_t)H * 64;   // [4 warps][64]
-  const size_t row0 = (size_t)e * H;
   for (int idx = threadIdx.x; idx < n * 64; idx += blockDim.x) {
     const int j = idx >> 6, d = idx & 63;
     const float* src = qkv + (row0 + j) * 1536 + hd * 64 + d;
@@ -185,12 +242,7 @@ __global__ void __launch_bounds__(128) cn_hh_attention_kernel(const float* __res
   }
   __syncthreads();
   const float scale = 0.125f;   // 1/sqrt(head_dim = 64)
-  for (int i = warp; i < H; i += 4) {
-    float* orow = out + (row0 + i) * 512 + hd * 64;
-    if (i >= n) {
-      orow[lane] = 0.0f; orow[lane + 32] = 0.0f;
-      continue;
-    }
+  for (int i = warp; i < n; i += 4) {
     const float* qsrc = qkv + (row0 + i) * 1536 + hd * 64;
     float* q = Qs + warp * 64;
     q[lane] = qsrc[lane] * scale; q[lane + 32] = qsrc[lane + 32] * scale;   // torch scales q before q k^T
@@ -230,7 +282,15 @@ __global__ void __launch_bounds__(128) cn_hh_attention_kernel(const float* __res
       o0 = fmaf(pj, Vs[j * 64 + lane], o0);
       o1 = fmaf(pj, Vs[j * 64 + lane + 32], o1);
     }
-    orow[lane] = o0; orow[lane + 32] = o1;
+    const size_t off = (row0 + i) * 512 + hd * 64;
+    if (out) { out[off + lane] = o0; out[off + lane + 32] = o1; }
+    if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
+      const float c0 = fminf(fmaxf(o0, -65504.0f), 65504.0f), c1 = fminf(fmaxf(o1, -65504.0f), 65504.0f);
+      const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
+      out_hi[off + lane] = h0; out_hi[off + lane + 32] = h1;
+      out_lo[off + lane] = __float2half_rn(c0 - __half2float(h0));
+      out_lo[off + lane + 32] = __float2half_rn(c1 - __half2float(h1));
+    }
     __syncwarp();
   }
 }
@@ -244,13 +304,13 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
                                                               const float* __restrict__ u /* [N,256] */,
                                                               const float* __restrict__ te /* [N, ldte] cols te_off.. */,
                                                               int ldte, int te_off, const float* __restrict__ b_s,
-                                                              const float* __restrict__ detected, int N, int H,
+                                                              const int* __restrict__ row_start, int N, int H,
                                                               float* __restrict__ wv /* [N,256] */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 4 + warp;
   if (e >= N) return;
-  int n = (int)detected[e];
-  n = n < 1 ? 1 : (n > H ? H : n);
+  const size_t row0 = (size_t)row_start[e];
+  const int n = row_start[e + 1] - row_start[e];
   float ur[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) ur[t] = u[(size_t)e * 256 + lane + 32 * t];
@@ -261,7 +321,7 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
   // scores for valid humans; lanes cooperate on each 256-d dot product
   float sc[4] = {-1e9f, -1e9f, -1e9f, -1e9f};   // lane holds score of human lane + 32 t
   for (int j = 0; j < n; ++j) {
-    const float* sr = s_out + ((size_t)e * H + j) * 256;
+    const float* sr = s_out + (row0 + j) * 256;
     float d = 0.0f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) d = fmaf(ur[t], sr[lane + 32 * t], d);
@@ -287,7 +347,7 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = 0; j < n; ++j) {
     const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31) * inv;
-    const float* sr = s_out + ((size_t)e * H + j) * 256;
+    const float* sr = s_out + (row0 + j) * 256;
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = fmaf(pj, sr[lane + 32 * t], acc[t]);
   }
