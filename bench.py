@@ -285,6 +285,7 @@ def run_ours(a):
         rollouts.insert(nobs, {'human_node_rnn': h_new}, action, logp, value, rew, (1.0 - done.float()).unsqueeze(1))
     lib.cn_policy_profile(eng._h, 0)
     stages = dict(zip(names, acc))
+    rows_valid = int(lib.cn_policy_last_rows(eng._h))          # compacted human rows of the last act
 
     # max over ranks
     t = torch.tensor([ms_value, ms_e2e, wall_e2e], device=dev, dtype=torch.float64)
@@ -308,10 +309,24 @@ def run_ours(a):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     hbm = peaks.get("hbm_gbs", 6650.0)
-    M = N * HUMANS
-    qkv_flops = 2.0 * M * 1536 * 512
+    # QKV projection: algorithmic FLOPs of ONE launch = 2 * rows * 1536 * 512 over the rows actually
+    # processed (padded humans are compacted out; the dense row count is reported next to it)
+    qkv_flops = 2.0 * rows_valid * 1536 * 512
     qkv_ms = stages.get("qkv_gemm", 0.0)
-    ach = qkv_flops / (qkv_ms / 1000.0) / 1e12 if qkv_ms > 0 else 0.0
+    qkv_tf = qkv_flops / (qkv_ms / 1000.0) / 1e12 if qkv_ms > 0 else 0.0
+    gemm_kernel = "cn_gemm_tc_kernel (tcgen05 3xFP16)" if a.gemm_mode == 1 else "cn_gemm_f32_kernel"
+    roof_gemm = {"kernel": "%s QKV projection, rows=%d N=1536 K=512" % (gemm_kernel, rows_valid), "bound": "tensor",
+                 "achieved": qkv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": qkv_tf / peak_tf if peak_tf else None,
+                 "traffic": None, "peak_source": peak_src, "launch_ms": qkv_ms, "algorithmic_flops_per_launch": qkv_flops,
+                 "mma_flops_issued_per_launch": qkv_flops * (3 if a.gemm_mode == 1 else 1), "dense_rows": N * HUMANS}
+    # environment step: algorithmic bytes per launch = B_env * N / CUDA-event time
+    env_gbs = B_ENV * N / (env_ms / 1000.0) / 1e9 if env_ms > 0 else 0.0
+    roof_env = {"kernel": "cn_env_step_kernel + cn_env_reset_kernel (one rollout step of %d envs)" % N, "bound": "hbm",
+                "achieved": env_gbs, "peak": hbm, "unit": "GB/s", "frac": env_gbs / hbm, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", "launch_ms": env_ms,
+                "algorithmic_bytes_per_launch": B_ENV * N,
+                "note": "latency/divergence bound by construction (per-human ORCA LP), see DESIGN.md"}
+    dominant_is_env = env_ms >= max(stages.values())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_value / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -325,10 +340,9 @@ def run_ours(a):
                 "d2h_bytes_per_step": N * (4 + 1 + 4 + 4 + 8 + 4),   # reward, done, info, aux, ep_ret, ep_len
                 "ms_per_step": e2e_ms / a.steps, "ms_per_step_cuda_events": ms_e2e / a.steps},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "cn_gemm_f32_kernel (QKV projection, M=%d N=1536 K=512)" % M, "bound": "tensor",
-                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-                     "traffic": None, "peak_source": peak_src, "launch_ms": qkv_ms,
-                     "algorithmic_flops_per_launch": qkv_flops},
+        "roofline": roof_env if dominant_is_env else roof_gemm,
+        "roofline_other": roof_gemm if dominant_is_env else roof_env,
+        "valid_human_rows": rows_valid, "mean_detected_humans": rows_valid / float(N),
         "breakdown_ms": {"env_step_kernel": env_ms, **stages},
         "hbm_roofline": {"bytes_per_env_step": B_ENV + B_POL, "achieved_gbs": value * (B_ENV + B_POL) / 1e9,
                          "peak_gbs": hbm, "frac": value * (B_ENV + B_POL) / 1e9 / hbm},

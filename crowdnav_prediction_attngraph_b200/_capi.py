@@ -48,7 +48,7 @@ EXPORTS = [
     "cn_last_error", "cn_abi_version", "cn_env_create", "cn_env_destroy", "cn_env_reset", "cn_env_step",
     "cn_env_step_host", "cn_env_state_bytes", "cn_env_state_copy", "cn_env_launch_count",
     "cn_policy_create", "cn_policy_destroy", "cn_policy_set_param", "cn_policy_finalize",
-    "cn_policy_act", "cn_policy_launch_count", "cn_policy_profile", "cn_policy_stage_count",
+    "cn_policy_act", "cn_policy_launch_count", "cn_policy_last_rows", "cn_policy_profile", "cn_policy_stage_count",
     "cn_policy_stage_name", "cn_policy_stage_ms",
 ]
 
@@ -109,6 +109,8 @@ def load_library(path=None):
     lib.cn_policy_act.argtypes = [C.c_void_p, C.POINTER(CnActPtrs), C.c_void_p]
     lib.cn_policy_launch_count.restype = C.c_int64
     lib.cn_policy_launch_count.argtypes = [C.c_void_p]
+    lib.cn_policy_last_rows.restype = C.c_int64
+    lib.cn_policy_last_rows.argtypes = [C.c_void_p]
     lib.cn_policy_profile.argtypes = [C.c_void_p, C.c_int]
     lib.cn_policy_stage_count.restype = C.c_int
     lib.cn_policy_stage_name.restype = C.c_char_p

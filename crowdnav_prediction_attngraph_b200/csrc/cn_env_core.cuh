@@ -142,35 +142,30 @@ CN_HD void cn_phase_orca(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   const float invTimeHorizon = 1.0f / p.orca_time_horizon;
   const float timeStep = (float)p.time_step;
 
-  // --- neighbour selection: dist^2 < neighborDist^2, ascending, ties in insertion (index) order
-  float dist[MAXH];
-  uint32_t dummy_mask[(MAXH + 31) / 32];
-  for (int w = 0; w < (MAXH + 31) / 32; ++w) dummy_mask[w] = 0u;
-  for (int j = 0; j < H; ++j) {
-    if (j == h) { dist[j] = -1.0f; continue; }
-    const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
-    if (!v) dummy_mask[j >> 5] |= (1u << (j & 31));
-    const CnF2 op = v ? f2(s.fx[j], s.fy[j]) : f2(7.0f, 7.0f);     // dummy_human (crowd_sim.py:130-133)
-    const float d = f2abssq(f2sub(pos, op));
-    dist[j] = (d < rangeSq) ? d : -1.0f;
-  }
+  // --- neighbour selection: dist^2 < neighborDist^2, ascending, ties in insertion (index) order.
+  // Pass 1 compresses the in-range neighbours; pass 2 ranks them among themselves (O(nv^2) instead
+  // of O(H^2)) and builds each ORCA line directly at its sorted position.
+  float vd[MAXH];
+  uint8_t vj[MAXH];          // bit 7 = dummy (invisible) neighbour, bits 0..6 = human index
   int nl = 0;
   for (int j = 0; j < H; ++j) {
-    const float dj = dist[j];
-    if (dj < 0.0f) continue;
+    if (j == h) continue;
+    const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
+    const CnF2 op = v ? f2(s.fx[j], s.fy[j]) : f2(7.0f, 7.0f);     // dummy_human (crowd_sim.py:130-133)
+    const float d = f2abssq(f2sub(pos, op));
+    if (d < rangeSq) { vd[nl] = d; vj[nl] = (uint8_t)(j | (v ? 0 : 0x80)); ++nl; }
+  }
+  for (int a = 0; a < nl; ++a) {
+    const float da = vd[a];
     int rank = 0;
-    for (int k = 0; k < H; ++k) {
-      const float dk = dist[k];
-      if (dk < 0.0f) continue;
-      rank += (dk < dj || (dk == dj && k < j)) ? 1 : 0;
-    }
-    const bool dummy = (dummy_mask[j >> 5] >> (j & 31)) & 1u;
+    for (int b = 0; b < nl; ++b) rank += (vd[b] < da || (vd[b] == da && b < a)) ? 1 : 0;
+    const int j = vj[a] & 0x7f;
+    const bool dummy = (vj[a] & 0x80) != 0;
     const CnF2 op = dummy ? f2(7.0f, 7.0f) : f2(s.fx[j], s.fy[j]);
     const CnF2 ov = dummy ? f2(0.0f, 0.0f) : f2(s.vx[j], s.vy[j]);
     const float orad = p.randomize ? g.sim_rother[i * H + j]
                                    : (float)((dummy ? 0.3 : s.rad[j]) + pad + p.orca_safety_space);
     lines.set(rank, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
-    ++nl;
   }
   CnF2 result;
   const int lineFail = cn_lp2(lines, nl, vmax, pref, false, result);
@@ -241,28 +236,31 @@ CN_HD void cn_phase_integrate(const CnParams& p, CnEnvSh& s, int h) {
 // RNG-consuming pieces (leader thread only, serial — they share one MT19937 stream).
 struct CnSpawn { double px, py, vpref, rad; };
 
-CN_HD void cn_new_human_attrs(const CnParams& p, const CnState& g, int e, CnRng& rng, double& vpref, double& rad) {
+CN_HD void cn_new_human_attrs(const CnParams& p, const CnState& g, int e, CnRng& rng, const CnCoop& co,
+                              double& vpref, double& rad) {
   vpref = p.human_vpref; rad = p.human_radius;
   if (p.randomize) {                      // agent.py:20-23 then agent.py:44-50
-    g.nd_global[e] = cn_rng_uniform(rng, 5, 10);
-    vpref = cn_rng_uniform(rng, 0.5, 1.5);
-    rad = cn_rng_uniform(rng, 0.3, 0.5);
+    const double nd = cn_rng_uniform(rng, co, 5, 10);
+    if (co.lane == 0) g.nd_global[e] = nd;
+    vpref = cn_rng_uniform(rng, co, 0.5, 1.5);
+    rad = cn_rng_uniform(rng, co, 0.3, 0.5);
   }
 }
 
-// generate_circle_crossing_human (crowd_sim_var_num.py:116-146) against robot + humans[0..n_present)
+// generate_circle_crossing_human (crowd_sim_var_num.py:116-146) against robot + humans[0..n_present).
+// Replicated execution: every lane draws the same numbers; the collision scan is lane-strided.
 CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, const CnEnvSh& s, int e,
-                                       CnRng& rng, int n_present) {
+                                       CnRng& rng, const CnCoop& co, int n_present) {
   CnSpawn sp;
-  cn_new_human_attrs(p, g, e, rng, sp.vpref, sp.rad);
+  cn_new_human_attrs(p, g, e, rng, co, sp.vpref, sp.rad);
   for (;;) {
-    const double angle = cn_rng_double(rng) * CN_PI * 2;
-    const double px_noise = cn_rng_uniform(rng, 0, 1) * 2;
-    const double py_noise = cn_rng_uniform(rng, 0, 1) * 2;
+    const double angle = cn_rng_double(rng, co) * CN_PI * 2;
+    const double px_noise = cn_rng_uniform(rng, co, 0, 1) * 2;
+    const double py_noise = cn_rng_uniform(rng, co, 0, 1) * 2;
     const double px = p.circle_radius * cos(angle) + px_noise;
     const double py = p.circle_radius * sin(angle) + py_noise;
     bool collide = false;
-    for (int k = -1; k < n_present; ++k) {
+    for (int k = -1 + co.lane; k < n_present; k += co.nlanes) {
       double ax, ay, agx, agy, ar;
       if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
       else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
@@ -271,43 +269,53 @@ CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, cons
         collide = true; break;
       }
     }
-    if (!collide) { sp.px = px; sp.py = py; break; }
+    if (!cn_any(co, collide)) { sp.px = px; sp.py = py; break; }
   }
   return sp;
 }
 
-// reset (crowd_sim_var_num.py:303-363), leader only.  Rewrites the shared working set.
-CN_HD void cn_reset_leader(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
+// reset (crowd_sim_var_num.py:303-363).  `key` = 624-word MT19937 scratch (shared memory in the
+// reset kernel); every lane of `co` runs this function (replicated), lane 0 owns the writes.
+CN_HD void cn_reset_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
   const int H = p.H;
-  CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = 624;
+  CnRng rng; rng.key = key; rng.pos = 624;
   const uint32_t cc = g.case_counter[e];
   const uint32_t this_seed = p.seed_base + (uint32_t)e;
-  cn_rng_seed(rng, p.phase_offset + cc + this_seed);
+  cn_rng_seed(rng, p.phase_offset + cc + this_seed, co);
   for (;;) {
-    const double px = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
-    const double py = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
-    const double gx = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
-    const double gy = cn_rng_uniform(rng, -p.arena_size, p.arena_size);
-    if (cn_norm_dot(px - gx, py - gy) >= 8) { s.rpx = px; s.rpy = py; s.rgx = gx; s.rgy = gy; break; }
+    const double px = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
+    const double py = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
+    const double gx = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
+    const double gy = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
+    if (cn_norm_dot(px - gx, py - gy) >= 8) {
+      if (co.lane == 0) { s.rpx = px; s.rpy = py; s.rgx = gx; s.rgy = gy; s.rvx = 0.0f; s.rvy = 0.0f; }
+      break;
+    }
   }
-  s.rvx = 0.0f; s.rvy = 0.0f;
+  cn_coop_sync(co);
   for (int i = 0; i < H; ++i) {
-    const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, i);
-    s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
-    s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
-    s.fx[i] = (float)sp.px; s.fy[i] = (float)sp.py;
-    const size_t gi = cn_idx(p, e, i);
-    g.sim_exists[gi] = 0;
-    g.bpx[gi] = 0; g.bpy[gi] = 0; g.bvx[gi] = 0; g.bvy[gi] = 0; g.brad[gi] = 0;   // last_human_states = zeros
+    const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, co, i);
+    if (co.lane == 0) {
+      s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
+      s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
+      s.fx[i] = (float)sp.px; s.fy[i] = (float)sp.py;
+      const size_t gi = cn_idx(p, e, i);
+      g.sim_exists[gi] = 0;
+      g.bpx[gi] = 0; g.bpy[gi] = 0; g.bvx[gi] = 0; g.bvy[gi] = 0; g.brad[gi] = 0;   // last_human_states = zeros
+    }
+    cn_coop_sync(co);
   }
-  // case_counter = (case_counter + nenv) % case_size['train'] with case_size = UINT32_MAX - 2000
-  const uint64_t case_size = 4294967295ull - 2000ull;
-  g.case_counter[e] = (uint32_t)(((uint64_t)cc + (uint64_t)p.nenv_total) % case_size);
-  g.potential[e] = -fabs(cn_norm_dot(s.rgx - s.rpx, s.rgy - s.rpy));
-  g.step_count[e] = 0;
-  g.ep_ret[e] = 0.0; g.ep_len[e] = 0;
-  g.mt_pos[e] = rng.pos;
-  s.reset_flag = 1;
+  if (co.lane == 0) {
+    // case_counter = (case_counter + nenv) % case_size['train'] with case_size = UINT32_MAX - 2000
+    const uint64_t case_size = 4294967295ull - 2000ull;
+    g.case_counter[e] = (uint32_t)(((uint64_t)cc + (uint64_t)p.nenv_total) % case_size);
+    g.potential[e] = -fabs(cn_norm_dot(s.rgx - s.rpx, s.rgy - s.rpy));
+    g.step_count[e] = 0;
+    g.ep_ret[e] = 0.0; g.ep_len[e] = 0;
+    g.mt_pos[e] = rng.pos;
+    s.reset_flag = 1; s.done = 0; s.nvis = 0;
+  }
+  cn_coop_sync(co);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -405,19 +413,20 @@ CN_HD void cn_phase_obs_c(const CnParams& p, CnEnvSh& s, int e, int h, const CnO
 CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
   const int H = p.H;
   CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = g.mt_pos[e];
+  const CnCoop co = {0, 1};
   const int step = g.step_count[e];
   // global_time % 5 == 0 with global_time = step * 0.25 accumulated exactly
   const double gt = step * p.time_step;
   if (p.goal_changing && fmod(gt, 5.0) == 0.0) {
     for (int i = 0; i < H; ++i) {
       if (s.vpref[i] == 0) continue;
-      if (cn_rng_double(rng) <= p.goal_change_chance) {
+      if (cn_rng_double(rng, co) <= p.goal_change_chance) {
         double gx, gy;
         for (;;) {
-          const double angle = cn_rng_double(rng) * CN_PI * 2;
+          const double angle = cn_rng_double(rng, co) * CN_PI * 2;
           const double vp = (s.vpref[i] == 0) ? 1.0 : s.vpref[i];
-          const double gx_noise = (cn_rng_double(rng) - 0.5) * vp;
-          const double gy_noise = (cn_rng_double(rng) - 0.5) * vp;
+          const double gx_noise = (cn_rng_double(rng, co) - 0.5) * vp;
+          const double gy_noise = (cn_rng_double(rng, co) - 0.5) * vp;
           gx = p.circle_radius * cos(angle) + gx_noise;
           gy = p.circle_radius * sin(angle) + gy_noise;
           bool collide = false;
@@ -440,7 +449,7 @@ CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s
   if (p.end_goal_changing) {
     for (int i = 0; i < H; ++i) {
       if (cn_norm_dot(s.gx[i] - s.px[i], s.gy[i] - s.py[i]) < s.rad[i]) {
-        const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, H);
+        const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, co, H);
         s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
         s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
         g.sim_exists[cn_idx(p, e, i)] = 0;       // new Human => new ORCA policy => new rvo2 sim

@@ -50,10 +50,11 @@ __device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L,
   return s;
 }
 
-// mode 0: step (+ auto-reset where done); mode 1: reset every environment.
+// One rollout step of every environment (no reset inside: environments that finish are flagged in
+// out.done and re-initialised by cn_env_reset_kernel, launched right behind on the same stream).
 template <int MAXH, int MAXW>
 __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
-                                                          CnObs ob, CnStepOut out, int epb, int mode) {
+                                                          CnObs ob, CnStepOut out, int epb, int line_cap) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.H;
   const int le = threadIdx.x / H;
@@ -67,34 +68,72 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
     if (h == 0) env_view(smem + (size_t)le * L.per_env, L, H);
   }
   __syncthreads();
+  float4 ovf[MAXH];            // overflow lines (k >= line_cap): local memory, rarely touched
   CnLineStore lines;
   lines.base = reinterpret_cast<float4*>(smem + align16((size_t)epb * L.per_env)) + threadIdx.x;
   lines.stride = blockDim.x;
+  lines.cap = line_cap;
+  lines.ovf = ovf;
 
-  if (active) cn_phase_load(p, g, *s, e, h, mode == 0 ? action : nullptr);
+  if (active) cn_phase_load(p, g, *s, e, h, action);
   __syncthreads();
-  if (mode == 0) {
-    if (active) cn_phase_orca<MAXH>(p, g, *s, e, h, lines);
-    __syncthreads();
-    if (active) {
-      if (h == 0) cn_phase_reward(p, g, *s, e, out);
-      cn_phase_integrate(p, *s, h);
-    }
-    __syncthreads();
-  }
-  if (active && h == 0 && (mode == 1 || s->done)) cn_reset_leader(p, g, *s, e);
-  __syncthreads();
-  float row[MAXW];
-  if (active) cn_phase_obs_a<MAXW>(p, g, *s, e, h, row);
-  __syncthreads();
-  if (active) cn_phase_obs_b(p, g, *s, e, h, row, ob);
+  if (active) cn_phase_orca<MAXH>(p, g, *s, e, h, lines);
   __syncthreads();
   if (active) {
-    cn_phase_obs_c(p, *s, e, h, ob);
-    if (h == 0 && mode == 0 && !s->done) cn_phase_goals_leader(p, g, *s, e);
+    if (h == 0) cn_phase_reward(p, g, *s, e, out);
+    cn_phase_integrate(p, *s, h);
   }
   __syncthreads();
-  if (active) cn_phase_store(p, g, *s, e, h);
+  const bool live = active && !s->done;      // finished episodes: observation comes from the reset kernel
+  float row[MAXW];
+  if (live) cn_phase_obs_a<MAXW>(p, g, *s, e, h, row);
+  __syncthreads();
+  if (live) cn_phase_obs_b(p, g, *s, e, h, row, ob);
+  __syncthreads();
+  if (live) {
+    cn_phase_obs_c(p, *s, e, h, ob);
+    if (h == 0) cn_phase_goals_leader(p, g, *s, e);
+  }
+  __syncthreads();
+  if (live) cn_phase_store(p, g, *s, e, h);
+}
+
+// Episode (re)initialisation: ONE WARP per environment.  CrowdSimVarNum.reset needs the legacy
+// numpy MT19937 stream (624-word state): it is seeded and twisted in shared memory (lane-parallel
+// twist), the rejection-sampling collision checks are lane-strided, then the first observation is
+// generated with lanes over humans.  Warps whose environment did not finish exit immediately.
+#define CN_RESET_WARPS 4
+template <int MAXW>
+__global__ void __launch_bounds__(CN_RESET_WARPS * 32) cn_env_reset_kernel(CnParams p, CnState g, CnObs ob,
+                                                                           const uint8_t* __restrict__ done, int force,
+                                                                           size_t per_warp_bytes) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * CN_RESET_WARPS + warp;
+  if (e >= p.N) return;
+  if (!force && !done[e]) return;
+  const int H = p.H;
+  const EnvSmemLayout L = env_layout(H);
+  unsigned char* base = smem + (size_t)warp * per_warp_bytes;
+  CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
+  if (lane == 0) {
+    env_view(base, L, H);
+    s->done = 0; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0;
+  }
+  __syncwarp();
+  uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
+  float* rows = reinterpret_cast<float*>(base + L.per_env + 624 * sizeof(uint32_t));
+  const CnCoop co = {lane, 32};
+  cn_reset_env(p, g, *s, e, key, co);
+  for (int h = lane; h < H; h += 32) cn_phase_obs_a<MAXW>(p, g, *s, e, h, rows + (size_t)h * MAXW);
+  __syncwarp();
+  for (int h = lane; h < H; h += 32) cn_phase_obs_b(p, g, *s, e, h, rows + (size_t)h * MAXW, ob);
+  __syncwarp();
+  for (int h = lane; h < H; h += 32) {
+    cn_phase_obs_c(p, *s, e, h, ob);
+    cn_phase_store(p, g, *s, e, h);
+  }
+  for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
 }
 
 struct Field {
@@ -112,6 +151,8 @@ struct cn_env {
   int epb;
   int threads;
   size_t smem_bytes;
+  int line_cap;
+  size_t reset_warp_bytes;
   int maxh;
   int64_t launches;
   std::map<std::string, Field> fields;
@@ -146,24 +187,34 @@ KernelFn pick_kernel(int maxh) {
   return cn_env_step_kernel<128, 16>;
 }
 
-int launch(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const cn_step_ptrs* r, int mode,
-           cudaStream_t stream) {
+CnObs to_obs(const cn_obs_ptrs* o) {
   CnObs ob;
   ob.robot_node = o->robot_node; ob.temporal_edges = o->temporal_edges; ob.spatial_edges = o->spatial_edges;
   ob.detected_human_num = o->detected_human_num; ob.visible_masks = o->visible_masks;
+  return ob;
+}
+
+int launch_reset(cn_env* env, const cn_obs_ptrs* o, const uint8_t* d_done, int force, cudaStream_t stream) {
+  const int grid = (env->p.N + CN_RESET_WARPS - 1) / CN_RESET_WARPS;
+  cn_env_reset_kernel<16><<<grid, CN_RESET_WARPS * 32, CN_RESET_WARPS * env->reset_warp_bytes, stream>>>(
+      env->p, env->g, to_obs(o), d_done, force, env->reset_warp_bytes);
+  env->launches += 1;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return cn_set_error("cn_env_reset_kernel launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const cn_step_ptrs* r, cudaStream_t stream) {
   CnStepOut out;
-  memset(&out, 0, sizeof(out));
-  if (r) {
-    out.reward = r->reward; out.done = r->done; out.info = r->info; out.info_aux = r->info_aux;
-    out.ep_ret = r->ep_ret; out.ep_len = r->ep_len;
-  }
+  out.reward = r->reward; out.done = r->done; out.info = r->info; out.info_aux = r->info_aux;
+  out.ep_ret = r->ep_ret; out.ep_len = r->ep_len;
   const int grid = (env->p.N + env->epb - 1) / env->epb;
   KernelFn fn = pick_kernel(env->maxh);
-  fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, ob, out, env->epb, mode);
+  fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, to_obs(o), out, env->epb, env->line_cap);
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel launch: %s", cudaGetErrorString(err));
-  return 0;
+  return launch_reset(env, o, r->done, 0, stream);
 }
 
 }  // namespace
@@ -255,28 +306,42 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.ep_len, N);
   if (rc) { cn_env_destroy(env); return rc; }
 
-  // launch geometry: EPB whole environments per CTA, <= 256 threads, lines in shared memory
+  // launch geometry: EPB whole environments per CTA (<= 256 threads).  The first `line_cap` ORCA
+  // lines of every thread live in shared memory; the cap is lowered until the whole launch is
+  // resident in ONE wave (shared memory is the occupancy limiter; a 1.16-wave launch costs 2x).
   env->maxh = p.H <= 32 ? 32 : (p.H <= 64 ? 64 : 128);
   const EnvSmemLayout L = env_layout(p.H);
-  const size_t smem_cap = 200 * 1024;
   int epb = 256 / p.H;
   if (epb < 1) epb = 1;
-  for (;;) {
-    const size_t need = align16((size_t)epb * L.per_env) + (size_t)(p.H - 1 > 0 ? p.H - 1 : 1) * epb * p.H * sizeof(float4);
-    if (need <= smem_cap || epb == 1) { env->smem_bytes = need; break; }
-    --epb;
-  }
   env->epb = epb;
   env->threads = ((epb * p.H + 31) / 32) * 32;
-  if (env->threads > 256) return cn_env_destroy(env), cn_set_error("internal: %d threads", env->threads);
-  // lines are indexed [line][thread] with stride blockDim.x
-  env->smem_bytes = align16((size_t)epb * L.per_env) + (size_t)(p.H > 1 ? p.H - 1 : 1) * env->threads * sizeof(float4);
-  if (env->smem_bytes > 227 * 1024) {
-    cn_env_destroy(env);
-    return cn_set_error("cn_env_create: human_num %d needs %zu B shared memory per CTA", p.H, env->smem_bytes);
+  if (env->threads > 256) { cn_env_destroy(env); return cn_set_error("internal: %d threads", env->threads); }
+  int nsm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
+  const int grid = (p.N + epb - 1) / epb;
+  KernelFn fn = pick_kernel(env->maxh);
+  int cap = p.H > 1 ? p.H - 1 : 1;
+  for (;;) {
+    const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * env->threads * sizeof(float4);
+    bool ok = need <= 227 * 1024;
+    if (ok) {
+      err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+      int per_sm = 0;
+      if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, env->threads, need);
+      if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("occupancy query: %s", cudaGetErrorString(err)); }
+      ok = (long long)per_sm * nsm >= grid || cap <= 4;
+    }
+    if (ok) { env->smem_bytes = need; env->line_cap = cap; break; }
+    if (cap <= 1) { cn_env_destroy(env); return cn_set_error("cn_env_create: human_num %d does not fit shared memory", p.H); }
+    --cap;
   }
-  err = cudaFuncSetAttribute(pick_kernel(env->maxh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+  err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+  // reset kernel: per-warp working set + MT19937 state + observation rows
+  env->reset_warp_bytes = align16(L.per_env + 624 * sizeof(uint32_t) + (size_t)p.H * 16 * sizeof(float));
+  err = cudaFuncSetAttribute(cn_env_reset_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(CN_RESET_WARPS * env->reset_warp_bytes));
+  if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }
   *out = env;
   return 0;
 }
@@ -293,7 +358,7 @@ int cn_env_reset(cn_env* env, const cn_obs_ptrs* d_obs, void* stream) {
   if (!env || !d_obs) return cn_set_error("cn_env_reset: null argument");
   cudaSetDevice(env->device);
   // a reset of the whole vec env restarts Monitor bookkeeping but NOT case_counter (it keeps advancing)
-  return launch(env, nullptr, d_obs, nullptr, 1, (cudaStream_t)stream);
+  return launch_reset(env, d_obs, nullptr, 1, (cudaStream_t)stream);
 }
 
 int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, const cn_step_ptrs* d_out,
@@ -302,7 +367,7 @@ int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, co
   if (!d_out->reward || !d_out->done || !d_out->info || !d_out->info_aux || !d_out->ep_ret || !d_out->ep_len)
     return cn_set_error("cn_env_step: every cn_step_ptrs field must be set");
   cudaSetDevice(env->device);
-  return launch(env, d_action, d_obs, d_out, 0, (cudaStream_t)stream);
+  return launch_step(env, d_action, d_obs, d_out, (cudaStream_t)stream);
 }
 
 int cn_env_step_host(cn_env* env, const float* h_action, const cn_obs_ptrs* h_obs, const cn_step_ptrs* h_out) {
@@ -312,7 +377,7 @@ int cn_env_step_host(cn_env* env, const float* h_action, const cn_obs_ptrs* h_ob
   cudaStream_t st = 0;
   cudaError_t err = cudaMemcpyAsync(env->d_action, h_action, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st);
   if (err != cudaSuccess) return cn_set_error("H2D action: %s", cudaGetErrorString(err));
-  int rc = launch(env, env->d_action, &env->d_obs, &env->d_out, 0, st);
+  int rc = launch_step(env, env->d_action, &env->d_obs, &env->d_out, st);
   if (rc) return rc;
 #define D2H(dst, src, bytes) if (dst) { err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); \
     if (err != cudaSuccess) return cn_set_error("D2H " #dst ": %s", cudaGetErrorString(err)); }

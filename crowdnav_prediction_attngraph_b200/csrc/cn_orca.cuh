@@ -38,17 +38,23 @@ struct CnLine {
   CnF2 point, dir;
 };
 
-// Strided line store: element k at base[k * stride] as 4 floats (point.x, point.y, dir.x, dir.y).
+// Two-tier strided line store.  The first `cap` lines of a thread live in shared memory
+// (element k at base[k * stride]: [line][thread] layout, conflict-free 16-byte accesses); lines
+// beyond `cap` (only reached when an agent has more than `cap` neighbours inside neighborDist)
+// spill to a per-thread overflow array.  Keeping cap < H-1 is what lets all environments of a
+// launch be resident in ONE wave (shared memory is the occupancy limiter of the step kernel).
 struct CnLineStore {
   float4* base;
   int stride;
+  int cap;
+  float4* ovf;     // per-thread overflow storage for k >= cap
   CN_HD CnLine get(int k) const {
-    const float4 v = base[(size_t)k * stride];
+    const float4 v = (k < cap) ? base[(size_t)k * stride] : ovf[k - cap];
     CnLine l; l.point = f2(v.x, v.y); l.dir = f2(v.z, v.w); return l;
   }
   CN_HD void set(int k, const CnLine& l) {
     float4 v; v.x = l.point.x; v.y = l.point.y; v.z = l.dir.x; v.w = l.dir.y;
-    base[(size_t)k * stride] = v;
+    if (k < cap) base[(size_t)k * stride] = v; else ovf[k - cap] = v;
   }
 };
 

@@ -447,6 +447,15 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
 
 int64_t cn_policy_launch_count(cn_policy* p) { return p ? p->launches : 0; }
 
+int64_t cn_policy_last_rows(cn_policy* p) {
+  if (!p) return -1;
+  cudaSetDevice(p->cfg.device);
+  int v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(&v, p->mc, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return v;
+}
+
 // Internal test hook (not part of the public header): C = act(A[M,K] W[N,K]^T + bias) through the
 // tcgen05 3xFP16 kernel, fp32 device pointers in/out.  Used by tests/test_gpu_gemm_tc.py.
 int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, float* dC, int M, int N, int K, int act) {

@@ -15,33 +15,66 @@ struct CnRng {
   int pos;
 };
 
-CN_HD void cn_rng_seed(CnRng& r, uint32_t seed) {
-  for (int i = 0; i < 624; ++i) {
-    r.key[i] = seed;
-    seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)(i + 1);
+// Cooperative execution context.  The reset kernel runs ONE environment per warp with every lane
+// executing the same (replicated, warp-uniform) control flow; only the data-parallel inner loops
+// (MT19937 twist, rejection-sampling collision checks) are split across lanes.  {0, 1} = a single
+// thread (the step kernel's leader, the CPU test harness).
+struct CnCoop {
+  int lane, nlanes;
+};
+CN_HD bool cn_any(const CnCoop& c, bool pred) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) return __any_sync(0xffffffffu, pred) != 0;
+#endif
+  return pred;
+}
+CN_HD void cn_coop_sync(const CnCoop& c) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) __syncwarp();
+#endif
+  (void)c;
+}
+
+CN_HD void cn_rng_seed(CnRng& r, uint32_t seed, const CnCoop& c) {
+  // inherently serial recurrence: lane 0 only
+  if (c.lane == 0) {
+    for (int i = 0; i < 624; ++i) {
+      r.key[i] = seed;
+      seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)(i + 1);
+    }
   }
+  cn_coop_sync(c);
   r.pos = 624;
 }
 
-CN_HD void cn_rng_twist(CnRng& r) {
-  const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
-  int i;
-  uint32_t y;
-  for (i = 0; i < 624 - 397; ++i) {
-    y = (r.key[i] & UPPER) | (r.key[i + 1] & LOWER);
-    r.key[i] = r.key[i + 397] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+CN_HD uint32_t cn_rng_mix(uint32_t a, uint32_t b, uint32_t m) {
+  const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// genrand twist.  Sequential semantics: key[i] <- f(key[i], key[i+1], key[(i+397) % 624]) for i = 0..623
+// in order.  Chunks of `nlanes` consecutive i are independent (every operand a chunk reads is either
+// not yet overwritten or was produced >= 227 positions earlier), so each chunk is read by all lanes,
+// synchronised, then written.
+CN_HD void cn_rng_twist(CnRng& r, const CnCoop& c) {
+  const int nl = c.nlanes;
+  for (int base = 0; base < 624; base += nl) {
+    const int i = base + c.lane;
+    uint32_t v = 0;
+    if (i < 624) {
+      const int i1 = (i + 1 == 624) ? 0 : i + 1;
+      const int im = (i + 397 < 624) ? i + 397 : i + 397 - 624;
+      v = cn_rng_mix(r.key[i], r.key[i1], r.key[im]);
+    }
+    cn_coop_sync(c);
+    if (i < 624) r.key[i] = v;
+    cn_coop_sync(c);
   }
-  for (; i < 623; ++i) {
-    y = (r.key[i] & UPPER) | (r.key[i + 1] & LOWER);
-    r.key[i] = r.key[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
-  }
-  y = (r.key[623] & UPPER) | (r.key[0] & LOWER);
-  r.key[623] = r.key[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
   r.pos = 0;
 }
 
-CN_HD uint32_t cn_rng_u32(CnRng& r) {
-  if (r.pos >= 624) cn_rng_twist(r);
+CN_HD uint32_t cn_rng_u32(CnRng& r, const CnCoop& c) {
+  if (r.pos >= 624) cn_rng_twist(r, c);
   uint32_t y = r.key[r.pos++];
   y ^= (y >> 11);
   y ^= (y << 7) & 0x9d2c5680u;
@@ -50,15 +83,15 @@ CN_HD uint32_t cn_rng_u32(CnRng& r) {
   return y;
 }
 
-CN_HD double cn_rng_double(CnRng& r) {
-  const uint32_t a = cn_rng_u32(r) >> 5, b = cn_rng_u32(r) >> 6;
+CN_HD double cn_rng_double(CnRng& r, const CnCoop& c) {
+  const uint32_t a = cn_rng_u32(r, c) >> 5, b = cn_rng_u32(r, c) >> 6;
   return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
 }
 
 // np.random.uniform(lo, hi): lo + (hi - lo) * random_sample()   (two roundings, no fma)
-CN_HD double cn_rng_uniform(CnRng& r, double lo, double hi) {
+CN_HD double cn_rng_uniform(CnRng& r, const CnCoop& c, double lo, double hi) {
   const double scale = hi - lo;
-  const double u = cn_rng_double(r);
+  const double u = cn_rng_double(r, c);
 #if defined(__CUDA_ARCH__)
   return __dadd_rn(lo, __dmul_rn(scale, u));
 #else

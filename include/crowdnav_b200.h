@@ -148,6 +148,9 @@ typedef struct cn_act_ptrs {
 /* replaces: Policy.act (rl/networks/model.py:56-74) with infer=True.                           */
 int cn_policy_act(cn_policy *pol, const cn_act_ptrs *d, void *stream);
 int64_t cn_policy_launch_count(cn_policy *pol);
+/* Rows (valid humans, sum over envs of detected_human_num) the last cn_policy_act processed;
+ * synchronises the device.  The per-human pipeline runs on these compacted rows only.          */
+int64_t cn_policy_last_rows(cn_policy *pol);
 
 /* Per-stage device timing of cn_policy_act (CUDA events on the launching stream), for bench.py's
  * roofline line.  enable != 0 records events around every stage of subsequent calls;

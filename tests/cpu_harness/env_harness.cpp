@@ -47,20 +47,25 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     s.t0 = s.vpref + H; s.t1 = s.t0 + H;
     s.vx = f.data(); s.vy = s.vx + H; s.fx = s.vy + H; s.fy = s.fx + H; s.nvx = s.fy + H; s.nvy = s.nvx + H;
     s.visr = u.data();
-    for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, mode == 0 ? action : nullptr);
-    if (mode == 0) {
+    const CnCoop co = {0, 1};
+    if (mode == 1) {
+      s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0;
+      cn_reset_env(p, g, s, e, g.mt + (size_t)e * 624, co);
+    } else {
+      for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, action);
       for (int h = 0; h < H; ++h) {
         CnLineStore ls; ls.base = lines.data() + (size_t)h * H; ls.stride = 1;
+        ls.cap = 3; ls.ovf = lines.data() + (size_t)h * H + 3;      // exercise both storage tiers
         cn_phase_orca<MAXH>(p, g, s, e, h, ls);
       }
       cn_phase_reward(p, g, s, e, out);
       for (int h = 0; h < H; ++h) cn_phase_integrate(p, s, h);
+      if (s.done) cn_reset_env(p, g, s, e, g.mt + (size_t)e * 624, co);   // = cn_env_reset_kernel for this env
     }
-    if (mode == 1 || s.done) cn_reset_leader(p, g, s, e);
     for (int h = 0; h < H; ++h) cn_phase_obs_a<16>(p, g, s, e, h, rows.data() + (size_t)h * 16);
     for (int h = 0; h < H; ++h) cn_phase_obs_b(p, g, s, e, h, rows.data() + (size_t)h * 16, ob);
     for (int h = 0; h < H; ++h) cn_phase_obs_c(p, s, e, h, ob);
-    if (mode == 0 && !s.done) cn_phase_goals_leader(p, g, s, e);
+    if (mode == 0 && !s.reset_flag) cn_phase_goals_leader(p, g, s, e);
     for (int h = 0; h < H; ++h) cn_phase_store(p, g, s, e, h);
   }
 }
@@ -137,8 +142,9 @@ int harness_state_copy(void* h, const char* name, void* buf, size_t bytes, int d
 void harness_rng_doubles(uint32_t seed, int n, double* out) {
   uint32_t key[624];
   CnRng r; r.key = key; r.pos = 624;
-  cn_rng_seed(r, seed);
-  for (int i = 0; i < n; ++i) out[i] = cn_rng_double(r);
+  const CnCoop co = {0, 1};
+  cn_rng_seed(r, seed, co);
+  for (int i = 0; i < n; ++i) out[i] = cn_rng_double(r, co);
 }
 
 }  // extern "C"
