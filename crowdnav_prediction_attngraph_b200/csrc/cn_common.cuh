@@ -73,6 +73,9 @@ struct CnState {
   // diagnostics of the last step (parity tests)
   float *last_hvx, *last_hvy;        // ORCA output velocities [N][H]
   int *orca_nlines, *orca_fail;      // [N][H]
+  // per-step event flags written by the step kernel, consumed by the event kernel:
+  // 0 = nothing, 1 = goal dynamics (respawn / goal change) pending, 2 = episode finished (reset)
+  uint8_t *evt;                      // [N]
 };
 
 // Caller-owned observation/result buffers (PyTorch tensors in the host mirror).

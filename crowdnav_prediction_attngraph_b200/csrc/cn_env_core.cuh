@@ -55,6 +55,7 @@ struct CnEnvSh {
   double reward;
   int done, info, reset_flag;
   int nvis;
+  int goal_flag;         // some human is within its radius of its goal (respawn pending)
 };
 
 CN_HD size_t cn_idx(const CnParams& p, int e, int h) { return (size_t)e * p.H + h; }
@@ -90,7 +91,7 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   if (h == 0) {
     s.rpx = g.rpx[e]; s.rpy = g.rpy[e]; s.rgx = g.rgx[e]; s.rgy = g.rgy[e];
     s.rvx = g.rvx[e]; s.rvy = g.rvy[e];
-    s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0;
+    s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
     if (action) {
       float ax = action[2 * e], ay = action[2 * e + 1];
       const float nrm = sqrtf(ax * ax + ay * ay);          // np.linalg.norm(float32[2])
@@ -230,6 +231,17 @@ CN_HD void cn_phase_integrate(const CnParams& p, CnEnvSh& s, int h) {
   s.px[h] = s.px[h] + (double)s.nvx[h] * p.time_step;
   s.py[h] = s.py[h] + (double)s.nvy[h] * p.time_step;
   s.vx[h] = s.nvx[h]; s.vy[h] = s.nvy[h];
+  // end-goal respawn is due when a human is within its radius of its goal (crowd_sim_pred.py:207-211);
+  // the RNG-consuming work itself runs in the event kernel.  (benign race: all writers store 1)
+  if (p.end_goal_changing && cn_norm_dot(s.gx[h] - s.px[h], s.gy[h] - s.py[h]) < s.rad[h]) s.goal_flag = 1;
+}
+
+// Event flag of one environment after the step (leader): 2 = finished, 1 = goal dynamics pending.
+CN_HD int cn_event_flag(const CnParams& p, const CnState& g, const CnEnvSh& s, int e) {
+  if (s.done) return 2;
+  if (s.goal_flag) return 1;
+  if (p.goal_changing && fmod(g.step_count[e] * p.time_step, 5.0) == 0.0) return 1;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -408,12 +420,12 @@ CN_HD void cn_phase_obs_c(const CnParams& p, CnEnvSh& s, int e, int h, const CnO
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase GOALS (leader, only when the episode continues): random goal changes every 5 s and
-// end-goal respawns (crowd_sim_pred.py:202-211).
-CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
+// Phase GOALS (only when the episode continues): random goal changes every 5 s and end-goal respawns
+// (crowd_sim_pred.py:202-211).  Replicated execution over the lanes of `co` (see CnCoop): every lane
+// draws the same random numbers from `key`; collision scans are lane-strided; lane 0 owns the writes.
+CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
   const int H = p.H;
-  CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = g.mt_pos[e];
-  const CnCoop co = {0, 1};
+  CnRng rng; rng.key = key; rng.pos = g.mt_pos[e];
   const int step = g.step_count[e];
   // global_time % 5 == 0 with global_time = step * 0.25 accumulated exactly
   const double gt = step * p.time_step;
@@ -430,7 +442,7 @@ CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s
           gx = p.circle_radius * cos(angle) + gx_noise;
           gy = p.circle_radius * sin(angle) + gy_noise;
           bool collide = false;
-          for (int k = -1; k < H; ++k) {
+          for (int k = -1 + co.lane; k < H; k += co.nlanes) {
             if (k == i) continue;
             double ax, ay, agx, agy, ar;
             if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
@@ -440,9 +452,11 @@ CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s
               collide = true; break;
             }
           }
-          if (!collide) break;
+          if (!cn_any(co, collide)) break;
         }
-        s.gx[i] = gx; s.gy[i] = gy;
+        cn_coop_sync(co);
+        if (co.lane == 0) { s.gx[i] = gx; s.gy[i] = gy; }
+        cn_coop_sync(co);
       }
     }
   }
@@ -450,13 +464,17 @@ CN_HD void cn_phase_goals_leader(const CnParams& p, const CnState& g, CnEnvSh& s
     for (int i = 0; i < H; ++i) {
       if (cn_norm_dot(s.gx[i] - s.px[i], s.gy[i] - s.py[i]) < s.rad[i]) {
         const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, co, H);
-        s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
-        s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
-        g.sim_exists[cn_idx(p, e, i)] = 0;       // new Human => new ORCA policy => new rvo2 sim
+        cn_coop_sync(co);
+        if (co.lane == 0) {
+          s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
+          s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
+          g.sim_exists[cn_idx(p, e, i)] = 0;       // new Human => new ORCA policy => new rvo2 sim
+        }
+        cn_coop_sync(co);
       }
     }
   }
-  g.mt_pos[e] = rng.pos;
+  if (co.lane == 0) g.mt_pos[e] = rng.pos;
 }
 
 // Phase STORE: write the working set back to HBM.

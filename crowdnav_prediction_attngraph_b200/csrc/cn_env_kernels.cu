@@ -79,10 +79,9 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
   __syncthreads();
   if (active) cn_phase_orca<MAXH>(p, g, *s, e, h, lines);
   __syncthreads();
-  if (active) {
-    if (h == 0) cn_phase_reward(p, g, *s, e, out);
-    cn_phase_integrate(p, *s, h);
-  }
+  if (active && h == 0) cn_phase_reward(p, g, *s, e, out);
+  __syncthreads();
+  if (active) cn_phase_integrate(p, *s, h);
   __syncthreads();
   const bool live = active && !s->done;      // finished episodes: observation comes from the reset kernel
   float row[MAXW];
@@ -92,46 +91,55 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
   __syncthreads();
   if (live) {
     cn_phase_obs_c(p, *s, e, h, ob);
-    if (h == 0) cn_phase_goals_leader(p, g, *s, e);
+    cn_phase_store(p, g, *s, e, h);
   }
-  __syncthreads();
-  if (live) cn_phase_store(p, g, *s, e, h);
+  if (active && h == 0) g.evt[e] = (uint8_t)cn_event_flag(p, g, *s, e);
 }
 
-// Episode (re)initialisation: ONE WARP per environment.  CrowdSimVarNum.reset needs the legacy
-// numpy MT19937 stream (624-word state): it is seeded and twisted in shared memory (lane-parallel
-// twist), the rejection-sampling collision checks are lane-strided, then the first observation is
-// generated with lanes over humans.  Warps whose environment did not finish exit immediately.
-#define CN_RESET_WARPS 4
+// Event kernel: ONE WARP per environment, for everything that consumes the legacy numpy MT19937
+// stream (624-word state per environment): episode reset (CrowdSimVarNum.reset), end-goal respawns
+// and random goal changes.  The state is staged in shared memory (lane-parallel twist), rejection
+// sampling collision checks are lane-strided, and after a reset the first observation is generated
+// with lanes over humans.  Warps whose environment has no event (g.evt == 0) exit immediately.
+#define CN_EVENT_WARPS 4
 template <int MAXW>
-__global__ void __launch_bounds__(CN_RESET_WARPS * 32) cn_env_reset_kernel(CnParams p, CnState g, CnObs ob,
-                                                                           const uint8_t* __restrict__ done, int force,
+__global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnParams p, CnState g, CnObs ob, int force,
                                                                            size_t per_warp_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * CN_RESET_WARPS + warp;
+  const int e = blockIdx.x * CN_EVENT_WARPS + warp;
   if (e >= p.N) return;
-  if (!force && !done[e]) return;
+  const int evt = force ? 2 : g.evt[e];
+  if (evt == 0) return;
   const int H = p.H;
   const EnvSmemLayout L = env_layout(H);
   unsigned char* base = smem + (size_t)warp * per_warp_bytes;
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
-  if (lane == 0) {
-    env_view(base, L, H);
-    s->done = 0; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0;
-  }
+  if (lane == 0) env_view(base, L, H);
   __syncwarp();
   uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
   float* rows = reinterpret_cast<float*>(base + L.per_env + 624 * sizeof(uint32_t));
   const CnCoop co = {lane, 32};
-  cn_reset_env(p, g, *s, e, key, co);
-  for (int h = lane; h < H; h += 32) cn_phase_obs_a<MAXW>(p, g, *s, e, h, rows + (size_t)h * MAXW);
-  __syncwarp();
-  for (int h = lane; h < H; h += 32) cn_phase_obs_b(p, g, *s, e, h, rows + (size_t)h * MAXW, ob);
-  __syncwarp();
-  for (int h = lane; h < H; h += 32) {
-    cn_phase_obs_c(p, *s, e, h, ob);
-    cn_phase_store(p, g, *s, e, h);
+  if (evt == 2) {
+    if (lane == 0) { s->done = 0; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; }
+    __syncwarp();
+    cn_reset_env(p, g, *s, e, key, co);
+    for (int h = lane; h < H; h += 32) cn_phase_obs_a<MAXW>(p, g, *s, e, h, rows + (size_t)h * MAXW);
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) cn_phase_obs_b(p, g, *s, e, h, rows + (size_t)h * MAXW, ob);
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) {
+      cn_phase_obs_c(p, *s, e, h, ob);
+      cn_phase_store(p, g, *s, e, h);
+    }
+  } else {
+    // goal dynamics on the state the step kernel just stored
+    for (int h = lane; h < H; h += 32) cn_phase_load(p, g, *s, e, h, nullptr);
+    for (int i = lane; i < 624; i += 32) key[i] = g.mt[(size_t)e * 624 + i];
+    __syncwarp();
+    cn_phase_goals(p, g, *s, e, key, co);
+    __syncwarp();
+    for (int h = lane; h < H; h += 32) cn_phase_store(p, g, *s, e, h);
   }
   for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
 }
@@ -194,13 +202,13 @@ CnObs to_obs(const cn_obs_ptrs* o) {
   return ob;
 }
 
-int launch_reset(cn_env* env, const cn_obs_ptrs* o, const uint8_t* d_done, int force, cudaStream_t stream) {
-  const int grid = (env->p.N + CN_RESET_WARPS - 1) / CN_RESET_WARPS;
-  cn_env_reset_kernel<16><<<grid, CN_RESET_WARPS * 32, CN_RESET_WARPS * env->reset_warp_bytes, stream>>>(
-      env->p, env->g, to_obs(o), d_done, force, env->reset_warp_bytes);
+int launch_events(cn_env* env, const cn_obs_ptrs* o, int force, cudaStream_t stream) {
+  const int grid = (env->p.N + CN_EVENT_WARPS - 1) / CN_EVENT_WARPS;
+  cn_env_event_kernel<16><<<grid, CN_EVENT_WARPS * 32, CN_EVENT_WARPS * env->reset_warp_bytes, stream>>>(
+      env->p, env->g, to_obs(o), force, env->reset_warp_bytes);
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return cn_set_error("cn_env_reset_kernel launch: %s", cudaGetErrorString(err));
+  if (err != cudaSuccess) return cn_set_error("cn_env_event_kernel launch: %s", cudaGetErrorString(err));
   return 0;
 }
 
@@ -214,7 +222,7 @@ int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const 
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel launch: %s", cudaGetErrorString(err));
-  return launch_reset(env, o, r->done, 0, stream);
+  return launch_events(env, o, 0, stream);
 }
 
 }  // namespace
@@ -281,7 +289,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH);
   A(sim_rother, p.randomize ? NH * p.H : (size_t)4);
   A(mt, N * 624); A(mt_pos, N);
-  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N);
 #undef A
   if (!rc) {
     // nd_global starts at the configured value (config.orca.neighbor_dist)
@@ -339,8 +347,8 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
   // reset kernel: per-warp working set + MT19937 state + observation rows
   env->reset_warp_bytes = align16(L.per_env + 624 * sizeof(uint32_t) + (size_t)p.H * 16 * sizeof(float));
-  err = cudaFuncSetAttribute(cn_env_reset_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(CN_RESET_WARPS * env->reset_warp_bytes));
+  err = cudaFuncSetAttribute(cn_env_event_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(CN_EVENT_WARPS * env->reset_warp_bytes));
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }
   *out = env;
   return 0;
@@ -358,7 +366,7 @@ int cn_env_reset(cn_env* env, const cn_obs_ptrs* d_obs, void* stream) {
   if (!env || !d_obs) return cn_set_error("cn_env_reset: null argument");
   cudaSetDevice(env->device);
   // a reset of the whole vec env restarts Monitor bookkeeping but NOT case_counter (it keeps advancing)
-  return launch_reset(env, d_obs, nullptr, 1, (cudaStream_t)stream);
+  return launch_events(env, d_obs, 1, (cudaStream_t)stream);
 }
 
 int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, const cn_step_ptrs* d_out,

@@ -34,6 +34,11 @@ struct cn_policy {
   __half *e1h, *e1l, *e2h, *e2l, *aoh, *aol;
   __half *W2h, *W2l, *Wqkvh, *Wqkvl, *Wosh, *Wosl;
   CUtensorMap m_e1h, m_e1l, m_e2h, m_e2l, m_aoh, m_aol, m_W2h, m_W2l, m_Wqkvh, m_Wqkvl, m_Wosh, m_Wosl;
+  // per-environment tail on tensor cores: output_linear, actor.0|critic.0, actor.2, critic.2
+  __half *h1h, *h1l, *outh, *outl, *ac1h, *ac1l;
+  __half *Woh, *Wol, *Wac1h, *Wac1l, *Wa2h, *Wa2l, *Wc2h, *Wc2l;
+  CUtensorMap m_h1h, m_h1l, m_outh, m_outl, m_a1h, m_a1l, m_c1h, m_c1l;
+  CUtensorMap m_Woh, m_Wol, m_Wac1h, m_Wac1l, m_Wa2h, m_Wa2l, m_Wc2h, m_Wc2l;
   // optional per-stage profiling
   bool profile;
   std::vector<cudaEvent_t> ev;
@@ -89,11 +94,11 @@ EncodeFn get_encode() {
 }
 
 // 2-D fp16 row-major [rows, K] tensor, box = 64 (K) x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows) {
+int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch = 0) {
   EncodeFn enc = get_encode();
   if (!enc) return cn_set_error("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)K * sizeof(__half)};
+  cuuint64_t gstride[1] = {(cuuint64_t)(pitch ? pitch : K) * sizeof(__half)};
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstride, box, estr,
@@ -213,6 +218,20 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
     if (!rc) rc = make_map(&p->m_e2l, p->e2l, p->M, 512, TC_BM);
     if (!rc) rc = make_map(&p->m_aoh, p->aoh, p->M, 512, TC_BM);
     if (!rc) rc = make_map(&p->m_aol, p->aol, p->M, 512, TC_BM);
+    if (!rc) rc = halloc16(p, &p->h1h, N * 128);
+    if (!rc) rc = halloc16(p, &p->h1l, N * 128);
+    if (!rc) rc = halloc16(p, &p->outh, N * 256);
+    if (!rc) rc = halloc16(p, &p->outl, N * 256);
+    if (!rc) rc = halloc16(p, &p->ac1h, N * 512);
+    if (!rc) rc = halloc16(p, &p->ac1l, N * 512);
+    if (!rc) rc = make_map(&p->m_h1h, p->h1h, p->N, 128, TC_BM);
+    if (!rc) rc = make_map(&p->m_h1l, p->h1l, p->N, 128, TC_BM);
+    if (!rc) rc = make_map(&p->m_outh, p->outh, p->N, 256, TC_BM);
+    if (!rc) rc = make_map(&p->m_outl, p->outl, p->N, 256, TC_BM);
+    if (!rc) rc = make_map(&p->m_a1h, p->ac1h, p->N, 256, TC_BM, 512);          // actor half: cols 0..255
+    if (!rc) rc = make_map(&p->m_a1l, p->ac1l, p->N, 256, TC_BM, 512);
+    if (!rc) rc = make_map(&p->m_c1h, p->ac1h + 256, p->N, 256, TC_BM, 512);    // critic half: cols 256..511
+    if (!rc) rc = make_map(&p->m_c1l, p->ac1l + 256, p->N, 256, TC_BM, 512);
     if (!rc) {
       cudaError_t e2 = cudaFuncSetAttribute(cn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
       if (e2 != cudaSuccess) rc = cn_set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e2));
@@ -360,6 +379,22 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
     split16(p, st, p->W2, 64.0f, p->W2h, p->W2l, (size_t)512 * 128);
     split16(p, st, p->Wqkv, 64.0f, p->Wqkvh, p->Wqkvl, (size_t)1536 * 512);
     split16(p, st, p->Wos, 64.0f, p->Wosh, p->Wosl, (size_t)256 * 512);
+    {
+      struct { float* src; __half** hi; __half** lo; CUtensorMap* mh; CUtensorMap* ml; int rows, k; } tw[4] = {
+          {p->Wo, &p->Woh, &p->Wol, &p->m_Woh, &p->m_Wol, 256, 128},
+          {p->Wac1, &p->Wac1h, &p->Wac1l, &p->m_Wac1h, &p->m_Wac1l, 512, 256},
+          {p->Wa2, &p->Wa2h, &p->Wa2l, &p->m_Wa2h, &p->m_Wa2l, 256, 256},
+          {p->Wc2, &p->Wc2h, &p->Wc2l, &p->m_Wc2h, &p->m_Wc2l, 256, 256}};
+      for (auto& t : tw) {
+        if (!rc) rc = halloc16(p, t.hi, (size_t)t.rows * t.k);
+        if (!rc) rc = halloc16(p, t.lo, (size_t)t.rows * t.k);
+        if (rc) return rc;
+        split16(p, st, t.src, 64.0f, *t.hi, *t.lo, (size_t)t.rows * t.k);
+        rc = make_map(t.mh, *t.hi, t.rows, t.k, TC_BN);
+        if (!rc) rc = make_map(t.ml, *t.lo, t.rows, t.k, TC_BN);
+        if (rc) return rc;
+      }
+    }
     rc = make_map(&p->m_W2h, p->W2h, 512, 128, TC_BN);
     if (!rc) rc = make_map(&p->m_W2l, p->W2l, 512, 128, TC_BN);
     if (!rc) rc = make_map(&p->m_Wqkvh, p->Wqkvh, 1536, 512, TC_BN);
@@ -429,13 +464,21 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   gemm(p, st, p->wv, 256, p->Wa, 256, p->ba, p->t1 + 64, 128, N, 64, 256, CN_ACT_RELU);
   gemm(p, st, p->t1, 128, p->Wih, 128, p->bih, p->gi, 384, N, 384, 128, CN_ACT_NONE);
   gemm(p, st, p->h0, 128, p->Whh, 128, p->bhh, p->gh, 384, N, 384, 128, CN_ACT_NONE);
-  cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out);
+  cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out, tcm ? p->h1h : nullptr,
+                                                            tcm ? p->h1l : nullptr);
   p->launches += 1;
   mark(p, st, 9);
-  gemm(p, st, d->h_out, 128, p->Wo, 128, p->bo, p->outb, 256, N, 256, 128, CN_ACT_NONE);
-  gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);      // [actor.0 | critic.0]
-  gemm(p, st, p->ac1, 512, p->Wa2, 256, p->ba2, p->a2, 256, N, 256, 256, CN_ACT_TANH);
-  gemm(p, st, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
+  if (tcm) {
+    gemm_tc(p, st, p->m_h1h, p->m_h1l, p->m_Woh, p->m_Wol, N, 256, 128, p->bo, CN_ACT_NONE, nullptr, 0, p->outh, p->outl, 256);
+    gemm_tc(p, st, p->m_outh, p->m_outl, p->m_Wac1h, p->m_Wac1l, N, 512, 256, p->bac1, CN_ACT_TANH, nullptr, 0, p->ac1h, p->ac1l, 512);
+    gemm_tc(p, st, p->m_a1h, p->m_a1l, p->m_Wa2h, p->m_Wa2l, N, 256, 256, p->ba2, CN_ACT_TANH, p->a2, 256, nullptr, nullptr, 0);
+    gemm_tc(p, st, p->m_c1h, p->m_c1l, p->m_Wc2h, p->m_Wc2l, N, 256, 256, p->bc2, CN_ACT_TANH, p->c2, 256, nullptr, nullptr, 0);
+  } else {
+    gemm(p, st, d->h_out, 128, p->Wo, 128, p->bo, p->outb, 256, N, 256, 128, CN_ACT_NONE);
+    gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);      // [actor.0 | critic.0]
+    gemm(p, st, p->ac1, 512, p->Wa2, 256, p->ba2, p->a2, 256, N, 256, 256, CN_ACT_TANH);
+    gemm(p, st, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
+  }
   cn_heads_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->a2, 256, p->c2, 256, p->wv_, p->bv, p->Wm, p->bm, p->logstd, d->noise, N,
                                                d->value, d->action, d->log_prob, d->action_mean);
   p->launches += 1;

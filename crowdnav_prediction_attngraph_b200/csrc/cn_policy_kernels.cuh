@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
 __device__ __forceinline__ float cn_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __global__ void cn_gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
-                                   const float* __restrict__ h0, int N, float* __restrict__ h1) {
+                                   const float* __restrict__ h0, int N, float* __restrict__ h1,
+                                   __half* __restrict__ h1_hi, __half* __restrict__ h1_lo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * 128) return;
   const int e = idx >> 7, c = idx & 127;
@@ -369,7 +370,13 @@ __global__ void cn_gru_gate_kernel(const float* __restrict__ gi, const float* __
   const float r = cn_sigmoid(a[c] + b[c]);
   const float z = cn_sigmoid(a[128 + c] + b[128 + c]);
   const float n = tanhf(a[256 + c] + r * b[256 + c]);
-  h1[idx] = (1.0f - z) * n + z * h0[idx];
+  const float hv = (1.0f - z) * n + z * h0[idx];
+  h1[idx] = hv;
+  if (h1_hi) {       // (hi, lo) fp16 split for the tensor-core output_linear
+    const __half hh = __float2half_rn(hv);
+    h1_hi[idx] = hh;
+    h1_lo[idx] = __float2half_rn(hv - __half2float(hh));
+  }
 }
 
 // ------------------------------------------------------------------------------------------

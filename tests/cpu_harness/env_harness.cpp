@@ -49,7 +49,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     s.visr = u.data();
     const CnCoop co = {0, 1};
     if (mode == 1) {
-      s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0;
+      s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
       cn_reset_env(p, g, s, e, g.mt + (size_t)e * 624, co);
     } else {
       for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, action);
@@ -65,7 +65,8 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     for (int h = 0; h < H; ++h) cn_phase_obs_a<16>(p, g, s, e, h, rows.data() + (size_t)h * 16);
     for (int h = 0; h < H; ++h) cn_phase_obs_b(p, g, s, e, h, rows.data() + (size_t)h * 16, ob);
     for (int h = 0; h < H; ++h) cn_phase_obs_c(p, s, e, h, ob);
-    if (mode == 0 && !s.reset_flag) cn_phase_goals_leader(p, g, s, e);
+    // event kernel, goal-dynamics branch (runs only when the step kernel flagged it)
+    if (mode == 0 && !s.reset_flag && cn_event_flag(p, g, s, e) == 1) cn_phase_goals(p, g, s, e, g.mt + (size_t)e * 624, co);
     for (int h = 0; h < H; ++h) cn_phase_store(p, g, s, e, h);
   }
 }
@@ -103,7 +104,7 @@ void* harness_create(const cn_config* cfg) {
   A(bpx, NH); A(bpy, NH); A(bvx, NH); A(bvy, NH); A(brad, NH); A(vis, NH);
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH); A(sim_rother, NH * p.H);
   A(mt, N * 624); A(mt_pos, N);
-  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N);
 #undef A
   for (size_t e = 0; e < N; ++e) g.nd_global[e] = cfg->orca_neighbor_dist;
   return hn;
