@@ -206,12 +206,7 @@ def run_ours(a):
 
     # ---------------------------------------------------------------- device-resident rollout (value)
     def device_step():
-        s = rollouts.step
-        o = {k: rollouts.obs[k][s] for k in rollouts.obs}
-        value, action, logp, h_new = eng.act(o, rollouts.recurrent_hidden_states['human_node_rnn'][s], rollouts.masks[s])
-        nobs, rew, done, info = env.step_device(action)
-        masks = (1.0 - done.float()).unsqueeze(1)
-        rollouts.insert(nobs, {'human_node_rnn': h_new}, action, logp, value, rew, masks)
+        rollouts.rollout_step_zero_copy(eng, env)
         if rollouts.step == 0:
             rollouts.after_update()
 

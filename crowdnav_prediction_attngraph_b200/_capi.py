@@ -29,7 +29,7 @@ class CnObsPtrs(C.Structure):
 
 class CnStepPtrs(C.Structure):
     _fields_ = [("reward", C.c_void_p), ("done", C.c_void_p), ("info", C.c_void_p), ("info_aux", C.c_void_p),
-                ("ep_ret", C.c_void_p), ("ep_len", C.c_void_p)]
+                ("ep_ret", C.c_void_p), ("ep_len", C.c_void_p), ("not_done", C.c_void_p)]
 
 
 class CnPolicyConfig(C.Structure):

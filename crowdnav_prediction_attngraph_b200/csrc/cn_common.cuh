@@ -94,4 +94,5 @@ struct CnStepOut {
   float *info_aux;     // [N] Danger.min_dist (0 in train phase)
   double *ep_ret;      // [N] episode return at done (bench.Monitor 'r')
   int32_t *ep_len;     // [N] episode length at done
+  float *not_done;     // [N] optional: 1 - done (rollout-storage mask row)
 };

@@ -218,6 +218,7 @@ CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int 
   out.done[e] = (uint8_t)done;
   out.info[e] = info;
   out.info_aux[e] = 0.0f;
+  if (out.not_done) out.not_done[e] = done ? 0.0f : 1.0f;
   if (done) { out.ep_ret[e] = ret; out.ep_len[e] = len; }
   // robot.step(action) (agent.py:170-183); time
   s.rpx = s.rpx + (double)s.ax * p.time_step;

@@ -215,7 +215,7 @@ int launch_events(cn_env* env, const cn_obs_ptrs* o, int force, cudaStream_t str
 int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const cn_step_ptrs* r, cudaStream_t stream) {
   CnStepOut out;
   out.reward = r->reward; out.done = r->done; out.info = r->info; out.info_aux = r->info_aux;
-  out.ep_ret = r->ep_ret; out.ep_len = r->ep_len;
+  out.ep_ret = r->ep_ret; out.ep_len = r->ep_len; out.not_done = r->not_done;
   const int grid = (env->p.N + env->epb - 1) / env->epb;
   KernelFn fn = pick_kernel(env->maxh);
   fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, to_obs(o), out, env->epb, env->line_cap);
@@ -312,6 +312,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.info_aux, N);
   if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.ep_ret, N);
   if (!rc) rc = dev_alloc(env, nullptr, &env->d_out.ep_len, N);
+  env->d_out.not_done = nullptr;
   if (rc) { cn_env_destroy(env); return rc; }
 
   // launch geometry: EPB whole environments per CTA (<= 256 threads).  The first `line_cap` ORCA

@@ -22,6 +22,7 @@ struct cn_policy {
   cn_policy_config cfg;
   int N, H, Win, M;
   int64_t launches;
+  int attn_hpc;        // heads per CTA of the HH attention kernel
   bool finalized;
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> allocs;
@@ -239,7 +240,9 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   }
   if (rc) { cn_policy_destroy(p); return rc; }
   p->ws_allocs = p->allocs.size();
-  const size_t attn_smem = ((size_t)p->H * 65 + (size_t)p->H * 64 + 256) * sizeof(float);
+  p->attn_hpc = 8;
+  while (p->attn_hpc > 1 && p->attn_hpc * ((size_t)p->H * 129 + 64) * sizeof(float) > 200 * 1024) p->attn_hpc /= 2;
+  const size_t attn_smem = p->attn_hpc * ((size_t)p->H * 129 + 64) * sizeof(float);
   err = cudaFuncSetAttribute(cn_hh_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem);
   if (err != cudaSuccess) { cn_policy_destroy(p); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
   *out = p;
@@ -442,8 +445,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, 1 << 30, mc);
   mark(p, st, 4);
   {
-    const size_t smem = ((size_t)H * 65 + (size_t)H * 64 + 256) * sizeof(float);
-    cn_hh_attention_kernel<<<dim3(N, 8), 128, smem, st>>>(p->qkv, p->row_start, H, tcm ? nullptr : p->ao,
+    const size_t smem = p->attn_hpc * ((size_t)H * 129 + 64) * sizeof(float);
+    cn_hh_attention_kernel<<<dim3(N, 8 / p->attn_hpc), p->attn_hpc * 32, smem, st>>>(p->qkv, p->row_start, H, tcm ? nullptr : p->ao,
                                                           tcm ? p->aoh : nullptr, tcm ? p->aol : nullptr);
     p->launches += 1;
   }

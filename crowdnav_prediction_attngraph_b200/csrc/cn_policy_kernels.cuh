@@ -222,29 +222,32 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
 // qkv: [N*H, 1536] rows = (q | k | v), head hd uses columns hd*64..hd*64+63 of each third.
 // Keys j >= n_e are padding (key_padding_mask); query rows >= n_e are never consumed
 // downstream (their robot-human attention weight is exactly 0), they are written as zeros.
-__global__ void __launch_bounds__(128) cn_hh_attention_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __restrict__ qkv,
                                                               const int* __restrict__ row_start, int H,
                                                               float* __restrict__ out /* [Mc,512] or null */,
                                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  // One CTA per (environment, group of heads), one WARP per head (blockDim.x / 32 heads per CTA:
+  // 8 when shared memory allows).  The environment has n <= H valid (compacted) humans; each warp
+  // keeps K and V of its head in shared memory and walks the n queries.
   extern __shared__ float sm[];
-  const int e = blockIdx.x, hd = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hd = blockIdx.y * (blockDim.x >> 5) + wib;
   const size_t row0 = (size_t)row_start[e];
-  const int n = row_start[e + 1] - row_start[e];      // valid (compacted) humans of this environment
-  float* Ks = sm;                    // [H][65]
-  float* Vs = sm + (size_t)H * 65;   // [H][64]
-  float* Qs = Vs + (size_t)H * 64;   // [4 warps][64]
-  for (int idx = threadIdx.x; idx < n * 64; idx += blockDim.x) {
+  const int n = row_start[e + 1] - row_start[e];
+  float* Ks = sm + (size_t)wib * ((size_t)H * 129 + 64);  // [H][65]
+  float* Vs = Ks + (size_t)H * 65;                        // [H][64]
+  float* q = Vs + (size_t)H * 64;                         // [64]
+  for (int idx = lane; idx < n * 64; idx += 32) {
     const int j = idx >> 6, d = idx & 63;
     const float* src = qkv + (row0 + j) * 1536 + hd * 64 + d;
     Ks[j * 65 + d] = src[512];
     Vs[j * 64 + d] = src[1024];
   }
-  __syncthreads();
+  __syncwarp();
   const float scale = 0.125f;   // 1/sqrt(head_dim = 64)
-  for (int i = warp; i < n; i += 4) {
+  for (int i = 0; i < n; ++i) {
     const float* qsrc = qkv + (row0 + i) * 1536 + hd * 64;
-    float* q = Qs + warp * 64;
     q[lane] = qsrc[lane] * scale; q[lane + 32] = qsrc[lane + 32] * scale;   // torch scales q before q k^T
     __syncwarp();
     // scores: lanes over keys

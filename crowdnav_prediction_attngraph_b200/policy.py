@@ -120,12 +120,20 @@ class CudaPolicy(object):
         with torch.cuda.device(self.device):
             _capi.check(self.lib, self.lib.cn_policy_finalize(self._h, self._stream()), "cn_policy_finalize")
 
-    def act(self, obs, h, masks, deterministic=False, return_mean=False, noise=None):
+    def act(self, obs, h, masks, deterministic=False, return_mean=False, noise=None, out=None):
         """obs: dict of device tensors; h: [N,1,128]; masks: [N,1].  Returns value, action, log_prob, h_new
-        (views of internal double buffers: valid until the call after next)."""
+        (views of internal double buffers: valid until the call after next).  `out` (optional dict with
+        contiguous float32 device tensors value/action/log_prob/h_out) makes the kernels write straight
+        into caller memory, e.g. the rollout-storage slot (zero-copy rollout)."""
         N = self.N
         self._flip ^= 1
         b = self._bufs[self._flip]
+        if out is not None:
+            b = dict(b)
+            for k in ("value", "action", "log_prob", "h_out"):
+                if k in out:
+                    assert out[k].is_cuda and out[k].is_contiguous() and out[k].dtype == torch.float32, k
+                    b[k] = out[k]
         if not deterministic and noise is None:
             noise = torch.randn(N, 2, device=self.device)      # torch.normal(mean, std) == randn * std + mean
         sp = obs["spatial_edges"]

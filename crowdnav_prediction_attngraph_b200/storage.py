@@ -64,6 +64,20 @@ class RolloutStorage(object):
             self.bad_masks[s + 1].copy_(bad_masks, non_blocking=True)
         self.step = (s + 1) % self.num_steps
 
+    def rollout_step_zero_copy(self, engine, env, deterministic=False):
+        """One device-resident rollout step with NO copies: the policy kernels write value / action /
+        log-prob / hidden state and the env kernels write observation / reward / mask straight into
+        this storage's slots (equivalent to act -> envs.step -> insert of train.py:152-191)."""
+        s = self.step
+        o = {k: v[s] for k, v in self.obs.items()}
+        hn = self.recurrent_hidden_states['human_node_rnn']
+        engine.act(o, hn[s], self.masks[s], deterministic=deterministic,
+                   out=dict(value=self.value_preds[s], action=self.actions[s], log_prob=self.action_log_probs[s],
+                            h_out=hn[s + 1]))
+        env.step_device(self.actions[s], obs_out={k: v[s + 1] for k, v in self.obs.items()},
+                        reward_out=self.rewards[s], not_done_out=self.masks[s + 1])
+        self.step = (s + 1) % self.num_steps
+
     def after_update(self):
         for key in self.obs:
             self.obs[key][0].copy_(self.obs[key][-1])

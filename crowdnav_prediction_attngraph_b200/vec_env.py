@@ -168,7 +168,8 @@ class CudaCrowdVecEnv(object):
                          info_aux=torch.zeros(N, dtype=torch.float32, device=dev),
                          ep_ret=torch.zeros(N, dtype=torch.float64, device=dev),
                          ep_len=torch.zeros(N, dtype=torch.int32, device=dev))
-        self._outp = _capi.CnStepPtrs(*[self._out[k].data_ptr() for k, _ in _capi.CnStepPtrs._fields_])
+        self._outp = _capi.CnStepPtrs(*[self._out[k].data_ptr() if k in self._out else None
+                                        for k, _ in _capi.CnStepPtrs._fields_])
         # one packed pinned host buffer for the per-step D2H of (reward, done, info, aux, ep_ret, ep_len)
         self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self._out.items()}
         self.closed = False
@@ -193,18 +194,39 @@ class CudaCrowdVecEnv(object):
             _capi.check(self.lib, self.lib.cn_env_reset(self._h, C.byref(ptrs), self._stream()), "cn_env_reset")
         return dict(obs)
 
-    def step_device(self, actions):
+    def step_device(self, actions, obs_out=None, reward_out=None, not_done_out=None):
         """Device-resident step: returns (obs, reward[N] f32, done[N] u8, info[N] i32) as device tensors
-        (views of internal buffers, valid until the next step)."""
+        (views of internal buffers, valid until the next step).
+
+        Zero-copy rollout: `obs_out` (dict of contiguous float32 device tensors shaped like the
+        observation), `reward_out` ([N] or [N,1]) and `not_done_out` ([N] or [N,1], receives 1 - done)
+        let the kernel write straight into the rollout storage slot instead of internal buffers."""
         if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
             actions = actions.to(self.device, torch.float32).contiguous()
         assert actions.shape == (self.num_envs, 2)
-        self._flip ^= 1
-        obs, ptrs = self._obs_bufs[self._flip]
+        if obs_out is None:
+            self._flip ^= 1
+            obs, ptrs = self._obs_bufs[self._flip]
+        else:
+            obs = obs_out
+            for k, t in obs.items():
+                assert t.is_cuda and t.is_contiguous(), k
+            ptrs = _capi.CnObsPtrs(*[obs[k].data_ptr() if k in obs else None for k, _ in _capi.CnObsPtrs._fields_])
+        outp, reward = self._outp, self._out["reward"]
+        if reward_out is not None or not_done_out is not None:
+            vals = {k: self._out[k].data_ptr() for k in self._out}
+            if reward_out is not None:
+                assert reward_out.is_contiguous() and reward_out.numel() == self.num_envs and reward_out.dtype == torch.float32
+                vals["reward"] = reward_out.data_ptr()
+                reward = reward_out
+            if not_done_out is not None:
+                assert not_done_out.is_contiguous() and not_done_out.numel() == self.num_envs
+                vals["not_done"] = not_done_out.data_ptr()
+            outp = _capi.CnStepPtrs(*[vals.get(k) for k, _ in _capi.CnStepPtrs._fields_])
         with torch.cuda.device(self.device):
             _capi.check(self.lib, self.lib.cn_env_step(self._h, C.c_void_p(actions.data_ptr()), C.byref(ptrs),
-                                                       C.byref(self._outp), self._stream()), "cn_env_step")
-        return dict(obs), self._out["reward"], self._out["done"], self._out["info"]
+                                                       C.byref(outp), self._stream()), "cn_env_step")
+        return dict(obs), reward, self._out["done"], self._out["info"]
 
     def step_async(self, actions):
         self._pending = self.step_device(actions)

@@ -76,6 +76,7 @@ typedef struct cn_step_ptrs {
   float *info_aux;     /* [N] Danger.min_dist                                                  */
   double *ep_ret;      /* [N] info['episode']['r'] (valid where done)                          */
   int32_t *ep_len;     /* [N] info['episode']['l'] (valid where done)                          */
+  float *not_done;     /* [N] optional (may be NULL): 1 - done, the `masks` row train.py:185 builds */
 } cn_step_ptrs;
 
 typedef struct cn_env cn_env;

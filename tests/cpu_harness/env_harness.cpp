@@ -35,7 +35,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
   CnObs ob{o->robot_node, o->temporal_edges, o->spatial_edges, o->detected_human_num, o->visible_masks};
   CnStepOut out;
   memset(&out, 0, sizeof(out));
-  if (r) out = CnStepOut{r->reward, r->done, r->info, r->info_aux, r->ep_ret, r->ep_len};
+  if (r) out = CnStepOut{r->reward, r->done, r->info, r->info_aux, r->ep_ret, r->ep_len, r->not_done};
   std::vector<double> d(8 * H);
   std::vector<float> f(6 * H);
   std::vector<uint8_t> u(H);

@@ -58,7 +58,8 @@ class HarnessEnv(object):
                         info_aux=np.zeros(N, np.float32), ep_ret=np.zeros(N, np.float64), ep_len=np.zeros(N, np.int32))
         self.obp = _capi.CnObsPtrs(*[self.ob[k].ctypes.data if k in self.ob else None
                                      for k, _ in _capi.CnObsPtrs._fields_])
-        self.outp = _capi.CnStepPtrs(*[self.out[k].ctypes.data for k, _ in _capi.CnStepPtrs._fields_])
+        self.outp = _capi.CnStepPtrs(*[self.out[k].ctypes.data if k in self.out else None
+                                       for k, _ in _capi.CnStepPtrs._fields_])
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layout_matches_header():
     # 12 int32 + 20 double, no padding surprises
     assert C.sizeof(_capi.CnConfig) == 12 * 4 + 20 * 8
-    assert C.sizeof(_capi.CnObsPtrs) == 5 * 8 and C.sizeof(_capi.CnStepPtrs) == 6 * 8
+    assert C.sizeof(_capi.CnObsPtrs) == 5 * 8 and C.sizeof(_capi.CnStepPtrs) == 7 * 8
     assert C.sizeof(_capi.CnActPtrs) == 12 * 8 and C.sizeof(_capi.CnPolicyConfig) == 5 * 4
 
 

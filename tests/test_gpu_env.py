@@ -116,7 +116,7 @@ def test_host_buffer_entry_point_matches_device_path():
     h_out = dict(reward=np.zeros(N, np.float32), done=np.zeros(N, np.uint8), info=np.zeros(N, np.int32),
                  info_aux=np.zeros(N, np.float32), ep_ret=np.zeros(N), ep_len=np.zeros(N, np.int32))
     obp = _capi.CnObsPtrs(*[h_ob[k].ctypes.data if k in h_ob else None for k, _ in _capi.CnObsPtrs._fields_])
-    outp = _capi.CnStepPtrs(*[h_out[k].ctypes.data for k, _ in _capi.CnStepPtrs._fields_])
+    outp = _capi.CnStepPtrs(*[h_out[k].ctypes.data if k in h_out else None for k, _ in _capi.CnStepPtrs._fields_])
     _capi.check(e2.lib, e2.lib.cn_env_step_host(e2._h, a.ctypes.data, C.byref(obp), C.byref(outp)), "step_host")
     for k in h_ob:
         assert np.array_equal(obs[k].cpu().numpy(), h_ob[k])
