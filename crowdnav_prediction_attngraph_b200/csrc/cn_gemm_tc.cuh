@@ -10,9 +10,10 @@
 // would break the 1e-4 tolerance.  Weights are pre-scaled by 2^6 so their lo
 // pieces stay in fp16's normal range; the epilogue undoes the power-of-two scale exactly.
 //
-// Tiling: one 128 x 256 output tile per CTA, K in blocks of 64 fp16 (= one 128-byte swizzle
-// atom), 2-stage TMA->smem ring (4 operand tiles = 96 KB per stage), accumulator 128 lanes x 256
-// columns of TMEM.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// Tiling: one 128 x BN output tile per CTA (BN = 256 for the large per-human GEMMs, BN = 64 for the
+// per-environment layers where M is only a few thousand rows and more CTAs matter more than tile
+// efficiency), K in blocks of 64 fp16 (= one 128-byte swizzle atom), TMA->smem ring of 2 (BN=256,
+// 96 KB per stage) or 4 (BN=64, 48 KB per stage) stages, accumulator 128 lanes x BN columns of TMEM.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
 // tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global, each warp owns
 // the TMEM lane quadrant warp_id % 4).
 #pragma once
@@ -22,19 +23,24 @@
 #include <stdint.h>
 
 #define TC_BM 128
-#define TC_BN 256
 #define TC_BK 64
-#define TC_STAGES 2
 #define TC_A_TILE_BYTES (TC_BM * TC_BK * 2)           // 16 KB
-#define TC_B_TILE_BYTES (TC_BN * TC_BK * 2)           // 32 KB
-#define TC_STAGE_BYTES (2 * TC_A_TILE_BYTES + 2 * TC_B_TILE_BYTES)   // 96 KB
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/)
 #define TC_THREADS 192
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN >= 256) ? 2 : 4;
+  static constexpr int kBTile = BN * TC_BK * 2;
+  static constexpr int kStageBytes = 2 * TC_A_TILE_BYTES + 2 * kBTile;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
 
 struct TcEpilogue {
   const float* bias;     // [N] or null
   float inv_scale;       // 1 / scale_b
-  int act;               // CN_ACT_*
+  int act;               // CN_ACT_* applied to columns [act_lo, act_hi)
+  int act_lo, act_hi;
   float* c32;            // fp32 output [M, ldc] or null
   int ldc;
   __half* out_hi;        // split fp16 output [M, ldh] or null (A operand of the next GEMM)
@@ -79,9 +85,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = F16, K-major
-__device__ __forceinline__ uint32_t make_idesc() {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(bn >> 3) << 17) |
          ((uint32_t)(TC_BM >> 4) << 24);
+}
+// tanh to ~1e-6 absolute (the 1e-4 policy tolerance leaves two orders of magnitude of slack)
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -109,19 +120,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 }  // namespace tc
 
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                   const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, int M, int N,
                   int K, TcEpilogue ep) {
   if (ep.m_ptr) { const int mc = *ep.m_ptr; M = mc < M ? mc : M; }
   if ((int)(blockIdx.y * TC_BM) >= M) return;       // uniform for the whole CTA: before any barrier / TMEM use
+  constexpr int TC_STAGES = TcCfg<BN>::kStages;
+  constexpr int TC_B_TILE_BYTES = TcCfg<BN>::kBTile;
+  constexpr int TC_STAGE_BYTES = TcCfg<BN>::kStageBytes;
+  constexpr int TC_BN = BN;
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = tc::smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* base_ptr = tc_smem_raw + (base - raw);
   const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;  // barriers after the operand ring
-  // full[s] = bar_base + 8 s ; empty[s] = bar_base + 16 + 8 s ; tmem_full = bar_base + 32 ; tmem ptr at +40
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 40);
+  // full[s] = bar_base + 8 s ; empty[s] = bar_base + 32 + 8 s ; tmem_full = bar_base + 64 ; tmem ptr at +72
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 72);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
@@ -130,9 +146,9 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       tc::mbar_init(bar_base + 8 * s, 1);         // full: producer's arrive.expect_tx
-      tc::mbar_init(bar_base + 16 + 8 * s, 1);    // empty: one tcgen05.commit
+      tc::mbar_init(bar_base + 32 + 8 * s, 1);    // empty: one tcgen05.commit
     }
-    tc::mbar_init(bar_base + 32, 1);              // accumulator ready
+    tc::mbar_init(bar_base + 64, 1);              // accumulator ready
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
@@ -142,7 +158,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   if (warp == 1) {
     // allocate 256 TMEM columns (power of two >= 32); the same warp frees them at the end
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)TC_BN) : "memory");
+                 "r"((uint32_t)TcCfg<BN>::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc::tcgen05_fence_before();
@@ -156,7 +172,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        tc::mbar_wait(bar_base + 16 + 8 * s, ph ^ 1u);            // slot free (first pass returns immediately)
+        tc::mbar_wait(bar_base + 32 + 8 * s, ph ^ 1u);            // slot free (first pass returns immediately)
         const uint32_t full = bar_base + 8 * s;
         tc::mbar_expect_tx(full, TC_STAGE_BYTES);
         const uint32_t st = base + s * TC_STAGE_BYTES;
@@ -169,7 +185,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc();
+      const uint32_t idesc = tc::make_idesc(BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
@@ -187,14 +203,14 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
           tc::mma_f16(tmem_acc, dah, dbl, idesc, 1u);
           tc::mma_f16(tmem_acc, dal, dbh, idesc, 1u);
         }
-        tc::mma_commit(bar_base + 16 + 8 * s);                    // frees the smem slot when the MMAs retire
+        tc::mma_commit(bar_base + 32 + 8 * s);                    // frees the smem slot when the MMAs retire
       }
-      tc::mma_commit(bar_base + 32);                              // accumulator complete
+      tc::mma_commit(bar_base + 64);                              // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                       // TMEM lane quadrant this warp may access
-    tc::mbar_wait(bar_base + 32, 0);
+    tc::mbar_wait(bar_base + 64, 0);
     tc::tcgen05_fence_after();
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < M;
@@ -208,8 +224,10 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(r[j]) * ep.inv_scale;
         if (ep.bias) x += __ldg(ep.bias + nb + j);
-        if (ep.act == 1) x = x > 0.0f ? x : 0.0f;
-        else if (ep.act == 2) x = tanhf(x);
+        if (nb + j >= ep.act_lo && nb + j < ep.act_hi) {
+          if (ep.act == 1) x = x > 0.0f ? x : 0.0f;
+          else if (ep.act == 2) x = tc::fast_tanh(x);
+        }
         v[j] = x;
       }
       if (row_ok) {
@@ -244,7 +262,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc::tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TC_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TcCfg<BN>::kTmemCols) : "memory");
   }
 }
 

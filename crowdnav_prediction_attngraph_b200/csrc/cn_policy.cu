@@ -6,6 +6,10 @@
 //   q/k/v_linear  o  MultiheadAttention.in_proj   ->  one 512 -> 1536 projection
 //   MultiheadAttention.out_proj  o  spatial_linear -> one 512 -> 256 projection (ReLU after)
 //   spatial_edge_layer folded into the robot side of the dot-product attention (u = W_s^T te)
+//
+// gemm_mode 0: every layer on the fp32 CUDA-core GEMM (cn_gemm_f32_kernel).
+// gemm_mode 1: every layer with K >= 64 on the tcgen05 3xFP16 GEMM (cn_gemm_tc_kernel): activations
+//              travel between layers as (hi, lo) fp16 pairs written by the producing kernel's epilogue.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -18,6 +22,13 @@
 #include "cn_policy_kernels.cuh"
 #include "cn_gemm_tc.cuh"
 
+// A split-fp16 matrix [rows, K] (row pitch `pitch` elements) and its TMA descriptors.
+struct TcMat {
+  __half *hi = nullptr, *lo = nullptr;
+  CUtensorMap mh, ml;
+  int pitch = 0;
+};
+
 struct cn_policy {
   cn_policy_config cfg;
   int N, H, Win, M;
@@ -27,19 +38,15 @@ struct cn_policy {
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> allocs;
   size_t ws_allocs;   // allocs[0..ws_allocs) = workspace (kept); the rest = parameters of the last finalize
-  // device parameters (kernel layouts)
+  // device parameters (fp32 kernel layouts)
   float *W1, *b1, *W2, *b2, *Wqkv, *bqkv, *Wos, *bos;
   float *Wr, *br, *Wet, *bet, *WsT, *bs, *Wa, *ba, *Wih, *bih, *Whh, *bhh, *Wo, *bo;
   float *Wac1, *bac1, *Wa2, *ba2, *Wc2, *bc2, *wv_, *bv, *Wm, *bm, *logstd;
-  // tcgen05 path (gemm_mode 1): split-fp16 activations / weights and their TMA descriptors
-  __half *e1h, *e1l, *e2h, *e2l, *aoh, *aol;
-  __half *W2h, *W2l, *Wqkvh, *Wqkvl, *Wosh, *Wosl;
-  CUtensorMap m_e1h, m_e1l, m_e2h, m_e2l, m_aoh, m_aol, m_W2h, m_W2l, m_Wqkvh, m_Wqkvl, m_Wosh, m_Wosl;
-  // per-environment tail on tensor cores: output_linear, actor.0|critic.0, actor.2, critic.2
-  __half *h1h, *h1l, *outh, *outl, *ac1h, *ac1l;
-  __half *Woh, *Wol, *Wac1h, *Wac1l, *Wa2h, *Wa2l, *Wc2h, *Wc2l;
-  CUtensorMap m_h1h, m_h1l, m_outh, m_outl, m_a1h, m_a1l, m_c1h, m_c1l;
-  CUtensorMap m_Woh, m_Wol, m_Wac1h, m_Wac1l, m_Wa2h, m_Wa2l, m_Wc2h, m_Wc2l;
+  // tcgen05 path: split weights (B operands; tile rows = 256 for per-human layers, 64 for per-env layers)
+  TcMat tW2, tWqkv, tWos, tWet, tWsT, tWa, tWih, tWhh, tWo, tWac1, tWa2, tWc2;
+  // tcgen05 path: split activations (A operands)
+  TcMat tE1, tE2, tAo;                                  // per human rows
+  TcMat tRs, tT1, tTe, tWv, tH0, tH1, tOut, tAc1, tA1, tC1;   // per environment rows (tTe / tA1 / tC1 = column views)
   // optional per-stage profiling
   bool profile;
   std::vector<cudaEvent_t> ev;
@@ -94,12 +101,12 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// 2-D fp16 row-major [rows, K] tensor, box = 64 (K) x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch = 0) {
+// 2-D fp16 row-major [rows, K] tensor with row pitch `pitch`, box = 64 (K) x box_rows, 128-byte swizzle
+int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch) {
   EncodeFn enc = get_encode();
   if (!enc) return cn_set_error("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)(pitch ? pitch : K) * sizeof(__half)};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(__half)};
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstride, box, estr,
@@ -116,22 +123,56 @@ int halloc16(cn_policy* p, __half** ptr, size_t count) {
   return rc;
 }
 
-// tcgen05 GEMM launch: C = act((Ahi+Alo)(Bhi+Blo)^T / scale + bias)
-void gemm_tc(cn_policy* p, cudaStream_t st, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-             const CUtensorMap& bl, int M, int N, int K, const float* bias, int act, float* c32, int ldc, __half* oh,
-             __half* ol, int ldh, const int* m_ptr = nullptr) {
-  TcEpilogue ep;
-  ep.m_ptr = m_ptr;
-  ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.c32 = c32; ep.ldc = ldc; ep.out_hi = oh; ep.out_lo = ol;
-  ep.ldh = ldh;
-  dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
-  cn_gemm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(ah, al, bh, bl, M, N, K, ep);
-  p->launches += 1;
+// allocate a split matrix [rows, K] and build its maps (box_rows = 128 for A operands, BN for B operands)
+int tc_alloc(cn_policy* p, TcMat& t, int rows, int K, int box_rows) {
+  int rc = halloc16(p, &t.hi, (size_t)rows * K);
+  if (!rc) rc = halloc16(p, &t.lo, (size_t)rows * K);
+  t.pitch = K;
+  if (!rc) rc = make_map(&t.mh, t.hi, rows, K, box_rows, K);
+  if (!rc) rc = make_map(&t.ml, t.lo, rows, K, box_rows, K);
+  return rc;
+}
+// view of columns [col0, col0 + K) of an existing split matrix
+int tc_view(TcMat& v, const TcMat& src, int col0, int rows, int K, int box_rows) {
+  v.hi = src.hi + col0; v.lo = src.lo + col0; v.pitch = src.pitch;
+  int rc = make_map(&v.mh, v.hi, rows, K, box_rows, src.pitch);
+  if (!rc) rc = make_map(&v.ml, v.lo, rows, K, box_rows, src.pitch);
+  return rc;
 }
 
 void split16(cn_policy* p, cudaStream_t st, const float* src, float scale, __half* hi, __half* lo, size_t count) {
   cn_split_f16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(src, scale, hi, lo, count);
   p->launches += 1;
+}
+
+// tcgen05 GEMM launch: C = act((Ahi+Alo)(Bhi+Blo)^T / 64 + bias); bn = B tile rows (256 or 64)
+struct TcOut {
+  float* c32 = nullptr; int ldc = 0;
+  __half *oh = nullptr, *ol = nullptr; int ldh = 0;
+};
+void gemm_tc(cn_policy* p, cudaStream_t st, const TcMat& A, const TcMat& B, int M, int N, int K, int bn, const float* bias,
+             int act, const TcOut& o, const int* m_ptr = nullptr, int act_lo = 0, int act_hi = 1 << 30) {
+  TcEpilogue ep;
+  ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.act_lo = act_lo; ep.act_hi = act_hi;
+  ep.c32 = o.c32; ep.ldc = o.ldc; ep.out_hi = o.oh; ep.out_lo = o.ol; ep.ldh = o.ldh; ep.m_ptr = m_ptr;
+  dim3 grid(N / bn, (M + TC_BM - 1) / TC_BM);
+  if (bn == 256)
+    cn_gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, M, N, K, ep);
+  else
+    cn_gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, M, N, K, ep);
+  p->launches += 1;
+}
+TcOut out32(float* c, int ldc) { TcOut o; o.c32 = c; o.ldc = ldc; return o; }
+TcOut out16(const TcMat& t) { TcOut o; o.oh = t.hi; o.ol = t.lo; o.ldh = t.pitch; return o; }
+TcOut out_both(float* c, int ldc, const TcMat& t) { TcOut o = out16(t); o.c32 = c; o.ldc = ldc; return o; }
+
+int tc_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(cn_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       TcCfg<256>::kSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(cn_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
+  if (e != cudaSuccess) return cn_set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e));
+  return 0;
 }
 
 void gemm(cn_policy* p, cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias,
@@ -190,61 +231,44 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   if (cfg->device < 0 || cfg->device >= ndev) return cn_set_error("cn_policy_create: bad device %d", cfg->device);
   cudaSetDevice(cfg->device);
   cn_policy* p = new cn_policy();
-  memset(static_cast<void*>(&p->cfg), 0, sizeof(p->cfg));
   p->cfg = *cfg;
   p->N = cfg->num_envs; p->H = cfg->human_num; p->Win = cfg->input_size; p->M = p->N * p->H;
   p->launches = 0; p->finalized = false; p->profile = false;
   const size_t M = (size_t)p->M, N = (size_t)p->N;
+  const int Mi = p->M, Ni = p->N;
   int rc = 0;
 #define WS(name, count) if (!rc) rc = palloc(p, &p->name, (count))
   {
     float* q = nullptr;
-    if (!rc) rc = palloc(p, &q, N + 2); p->row_start = reinterpret_cast<int*>(q);
-    if (!rc) rc = palloc(p, &q, 4); p->mc = reinterpret_cast<int*>(q);
+    if (!rc) rc = palloc(p, &q, N + 2);
+    p->row_start = reinterpret_cast<int*>(q);
+    if (!rc) rc = palloc(p, &q, 4);
+    p->mc = reinterpret_cast<int*>(q);
   }
   WS(x16, M * 16); WS(e1, M * 128); WS(e2, M * 512); WS(qkv, M * 1536); WS(ao, M * 512); WS(sout, M * 256);
   WS(xr, N * 16); WS(rs, N * 256); WS(t1, N * 128); WS(u, N * 256); WS(wv, N * 256); WS(h0, N * 128);
   WS(gi, N * 384); WS(gh, N * 384); WS(outb, N * 256); WS(ac1, N * 512); WS(a2, N * 256); WS(c2, N * 256);
 #undef WS
   if (!rc && cfg->gemm_mode == 1) {
-    rc = halloc16(p, &p->e1h, M * 128);
-    if (!rc) rc = halloc16(p, &p->e1l, M * 128);
-    if (!rc) rc = halloc16(p, &p->e2h, M * 512);
-    if (!rc) rc = halloc16(p, &p->e2l, M * 512);
-    if (!rc) rc = halloc16(p, &p->aoh, M * 512);
-    if (!rc) rc = halloc16(p, &p->aol, M * 512);
-    if (!rc) rc = make_map(&p->m_e1h, p->e1h, p->M, 128, TC_BM);
-    if (!rc) rc = make_map(&p->m_e1l, p->e1l, p->M, 128, TC_BM);
-    if (!rc) rc = make_map(&p->m_e2h, p->e2h, p->M, 512, TC_BM);
-    if (!rc) rc = make_map(&p->m_e2l, p->e2l, p->M, 512, TC_BM);
-    if (!rc) rc = make_map(&p->m_aoh, p->aoh, p->M, 512, TC_BM);
-    if (!rc) rc = make_map(&p->m_aol, p->aol, p->M, 512, TC_BM);
-    if (!rc) rc = halloc16(p, &p->h1h, N * 128);
-    if (!rc) rc = halloc16(p, &p->h1l, N * 128);
-    if (!rc) rc = halloc16(p, &p->outh, N * 256);
-    if (!rc) rc = halloc16(p, &p->outl, N * 256);
-    if (!rc) rc = halloc16(p, &p->ac1h, N * 512);
-    if (!rc) rc = halloc16(p, &p->ac1l, N * 512);
-    if (!rc) rc = make_map(&p->m_h1h, p->h1h, p->N, 128, TC_BM);
-    if (!rc) rc = make_map(&p->m_h1l, p->h1l, p->N, 128, TC_BM);
-    if (!rc) rc = make_map(&p->m_outh, p->outh, p->N, 256, TC_BM);
-    if (!rc) rc = make_map(&p->m_outl, p->outl, p->N, 256, TC_BM);
-    if (!rc) rc = make_map(&p->m_a1h, p->ac1h, p->N, 256, TC_BM, 512);          // actor half: cols 0..255
-    if (!rc) rc = make_map(&p->m_a1l, p->ac1l, p->N, 256, TC_BM, 512);
-    if (!rc) rc = make_map(&p->m_c1h, p->ac1h + 256, p->N, 256, TC_BM, 512);    // critic half: cols 256..511
-    if (!rc) rc = make_map(&p->m_c1l, p->ac1l + 256, p->N, 256, TC_BM, 512);
-    if (!rc) {
-      cudaError_t e2 = cudaFuncSetAttribute(cn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-      if (e2 != cudaSuccess) rc = cn_set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e2));
-    }
+    // A operands: box rows = 128 (TC_BM)
+    rc = tc_alloc(p, p->tE1, Mi, 128, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tE2, Mi, 512, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tAo, Mi, 512, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tRs, Ni, 256, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tT1, Ni, 128, TC_BM);                 // [enc | te] then [enc | emb]
+    if (!rc) rc = tc_view(p->tTe, p->tT1, 64, Ni, 64, TC_BM);           // te = columns 64..127
+    if (!rc) rc = tc_alloc(p, p->tWv, Ni, 256, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tH0, Ni, 128, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tH1, Ni, 128, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tOut, Ni, 256, TC_BM);
+    if (!rc) rc = tc_alloc(p, p->tAc1, Ni, 512, TC_BM);
+    if (!rc) rc = tc_view(p->tA1, p->tAc1, 0, Ni, 256, TC_BM);          // actor.0 half
+    if (!rc) rc = tc_view(p->tC1, p->tAc1, 256, Ni, 256, TC_BM);        // critic.0 half
+    if (!rc) rc = tc_set_attrs();
   }
   if (rc) { cn_policy_destroy(p); return rc; }
   p->ws_allocs = p->allocs.size();
   p->attn_hpc = 8;
-  while (p->attn_hpc > 1 && p->attn_hpc * ((size_t)p->H * 129 + 64) * sizeof(float) > 200 * 1024) p->attn_hpc /= 2;
-  const size_t attn_smem = p->attn_hpc * ((size_t)p->H * 129 + 64) * sizeof(float);
-  err = cudaFuncSetAttribute(cn_hh_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem);
-  if (err != cudaSuccess) { cn_policy_destroy(p); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
   *out = p;
   return 0;
 }
@@ -344,6 +368,7 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
   UP(Wac1, cat(*wa0, *wc0)); UP(bac1, cat(*ba0, *bc0));      // rows 0..255 actor.0, 256..511 critic.0
   UP(Wa2, *wa2); UP(ba2, *ba2); UP(Wc2, *wc2); UP(bc2, *bc2);
   UP(wv_, *wcl); UP(bv, *bcl); UP(Wm, *wm); UP(bm, *bm); UP(logstd, *ls);
+#undef UP
   // folded projections
   float *d_win = nullptr, *d_bin = nullptr, *d_wl[3] = {nullptr, nullptr, nullptr}, *d_bl[3] = {nullptr, nullptr, nullptr};
   float *d_wout = nullptr, *d_bout = nullptr, *d_wsl = nullptr, *d_bsl = nullptr;
@@ -371,40 +396,18 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
   cn_fold_mm_kernel<<<dim3(4, 256), 128, 0, st>>>(d_wsl, d_wout, p->Wos, 256, 512, 512);
   cn_fold_mv_kernel<<<2, 128, 0, st>>>(d_wsl, d_bout, d_bsl, p->bos, 256, 512);
   if (p->cfg.gemm_mode == 1) {
-    // fp16 (hi, lo) split of the tensor-core weights, pre-scaled by 2^6 (exact) so lo stays normal
-    if (!rc) rc = halloc16(p, &p->W2h, (size_t)512 * 128);
-    if (!rc) rc = halloc16(p, &p->W2l, (size_t)512 * 128);
-    if (!rc) rc = halloc16(p, &p->Wqkvh, (size_t)1536 * 512);
-    if (!rc) rc = halloc16(p, &p->Wqkvl, (size_t)1536 * 512);
-    if (!rc) rc = halloc16(p, &p->Wosh, (size_t)256 * 512);
-    if (!rc) rc = halloc16(p, &p->Wosl, (size_t)256 * 512);
-    if (rc) return rc;
-    split16(p, st, p->W2, 64.0f, p->W2h, p->W2l, (size_t)512 * 128);
-    split16(p, st, p->Wqkv, 64.0f, p->Wqkvh, p->Wqkvl, (size_t)1536 * 512);
-    split16(p, st, p->Wos, 64.0f, p->Wosh, p->Wosl, (size_t)256 * 512);
-    {
-      struct { float* src; __half** hi; __half** lo; CUtensorMap* mh; CUtensorMap* ml; int rows, k; } tw[4] = {
-          {p->Wo, &p->Woh, &p->Wol, &p->m_Woh, &p->m_Wol, 256, 128},
-          {p->Wac1, &p->Wac1h, &p->Wac1l, &p->m_Wac1h, &p->m_Wac1l, 512, 256},
-          {p->Wa2, &p->Wa2h, &p->Wa2l, &p->m_Wa2h, &p->m_Wa2l, 256, 256},
-          {p->Wc2, &p->Wc2h, &p->Wc2l, &p->m_Wc2h, &p->m_Wc2l, 256, 256}};
-      for (auto& t : tw) {
-        if (!rc) rc = halloc16(p, t.hi, (size_t)t.rows * t.k);
-        if (!rc) rc = halloc16(p, t.lo, (size_t)t.rows * t.k);
-        if (rc) return rc;
-        split16(p, st, t.src, 64.0f, *t.hi, *t.lo, (size_t)t.rows * t.k);
-        rc = make_map(t.mh, *t.hi, t.rows, t.k, TC_BN);
-        if (!rc) rc = make_map(t.ml, *t.lo, t.rows, t.k, TC_BN);
-        if (rc) return rc;
-      }
+    // fp16 (hi, lo) split of the tensor-core weights, pre-scaled by 2^6 (exact) so lo stays normal.
+    // B-tile rows: 256 for the per-human layers (large M), 64 for the per-environment layers.
+    struct { float* src; TcMat* t; int rows, k, bn; } tw[12] = {
+        {p->W2, &p->tW2, 512, 128, 256},    {p->Wqkv, &p->tWqkv, 1536, 512, 256}, {p->Wos, &p->tWos, 256, 512, 256},
+        {p->Wet, &p->tWet, 128, 256, 64},   {p->WsT, &p->tWsT, 256, 64, 64},      {p->Wa, &p->tWa, 64, 256, 64},
+        {p->Wih, &p->tWih, 384, 128, 64},   {p->Whh, &p->tWhh, 384, 128, 64},     {p->Wo, &p->tWo, 256, 128, 64},
+        {p->Wac1, &p->tWac1, 512, 256, 64}, {p->Wa2, &p->tWa2, 256, 256, 64},     {p->Wc2, &p->tWc2, 256, 256, 64}};
+    for (auto& t : tw) {
+      rc = tc_alloc(p, *t.t, t.rows, t.k, t.bn);
+      if (rc) return rc;
+      split16(p, st, t.src, 64.0f, t.t->hi, t.t->lo, (size_t)t.rows * t.k);
     }
-    rc = make_map(&p->m_W2h, p->W2h, 512, 128, TC_BN);
-    if (!rc) rc = make_map(&p->m_W2l, p->W2l, 512, 128, TC_BN);
-    if (!rc) rc = make_map(&p->m_Wqkvh, p->Wqkvh, 1536, 512, TC_BN);
-    if (!rc) rc = make_map(&p->m_Wqkvl, p->Wqkvl, 1536, 512, TC_BN);
-    if (!rc) rc = make_map(&p->m_Wosh, p->Wosh, 256, 512, TC_BN);
-    if (!rc) rc = make_map(&p->m_Wosl, p->Wosl, 256, 512, TC_BN);
-    if (rc) return rc;
   }
   cudaError_t err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) return cn_set_error("cn_policy_finalize: %s", cudaGetErrorString(err));
@@ -421,6 +424,9 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   cudaSetDevice(p->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = p->N, H = p->H, M = p->M;
+  const bool tcm = p->cfg.gemm_mode == 1;
+  const int* mc = p->mc;
+  const int ALL = 1 << 30;
   mark(p, st, 0);
   // 0. compaction offsets, pack / pad inputs, h0 = h * mask
   {
@@ -428,57 +434,68 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
     const int total = M * 16 > N * 128 ? M * 16 : N * 128;
     cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->x16,
                                                                d->temporal_edges, d->robot_node, d->h_in, d->masks, p->xr,
-                                                               p->h0);
+                                                               p->h0, tcm ? p->tH0.hi : nullptr, tcm ? p->tH0.lo : nullptr);
     p->launches += 2;
   }
   // 1. human-human branch over the Mc = sum_e n_e valid rows (device-side count p->mc)
-  const bool tcm = p->cfg.gemm_mode == 1;
-  const int* mc = p->mc;
   mark(p, st, 1);
-  if (tcm) gemm(p, st, p->x16, 16, p->W1, 16, p->b1, nullptr, 128, M, 128, 16, CN_ACT_RELU, 0, 1 << 30, mc, p->e1h, p->e1l);
-  else gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU, 0, 1 << 30, mc);
+  if (tcm) gemm(p, st, p->x16, 16, p->W1, 16, p->b1, nullptr, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc, p->tE1.hi, p->tE1.lo);
+  else gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc);
   mark(p, st, 2);
-  if (tcm) gemm_tc(p, st, p->m_e1h, p->m_e1l, p->m_W2h, p->m_W2l, M, 512, 128, p->b2, CN_ACT_RELU, nullptr, 0, p->e2h, p->e2l, 512, mc);
-  else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU, 0, 1 << 30, mc);
+  if (tcm) gemm_tc(p, st, p->tE1, p->tW2, M, 512, 128, 256, p->b2, CN_ACT_RELU, out16(p->tE2), mc);
+  else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU, 0, ALL, mc);
   mark(p, st, 3);
-  if (tcm) gemm_tc(p, st, p->m_e2h, p->m_e2l, p->m_Wqkvh, p->m_Wqkvl, M, 1536, 512, p->bqkv, CN_ACT_NONE, p->qkv, 1536, nullptr, nullptr, 0, mc);
-  else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, 1 << 30, mc);
+  if (tcm) gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc);
+  else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
   mark(p, st, 4);
   {
-    const size_t smem = p->attn_hpc * ((size_t)H * 129 + 64) * sizeof(float);
-    cn_hh_attention_kernel<<<dim3(N, 8 / p->attn_hpc), p->attn_hpc * 32, smem, st>>>(p->qkv, p->row_start, H, tcm ? nullptr : p->ao,
-                                                          tcm ? p->aoh : nullptr, tcm ? p->aol : nullptr);
+    cn_hh_attention_kernel<<<N, 256, 0, st>>>(
+        p->qkv, p->row_start, H, tcm ? nullptr : p->ao, tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
     p->launches += 1;
   }
   mark(p, st, 5);
-  if (tcm) gemm_tc(p, st, p->m_aoh, p->m_aol, p->m_Wosh, p->m_Wosl, M, 256, 512, p->bos, CN_ACT_RELU, p->sout, 256, nullptr, nullptr, 0, mc);
-  else gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU, 0, 1 << 30, mc);
-  // 2. robot branch
+  if (tcm) gemm_tc(p, st, p->tAo, p->tWos, M, 256, 512, 256, p->bos, CN_ACT_RELU, out32(p->sout, 256), mc);
+  else gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU, 0, ALL, mc);
+  // 2. robot branch:  rs = ReLU(W_r [te, rn]);  t1 = [ReLU(enc) | te];  u = W_s^T te
   mark(p, st, 6);
-  gemm(p, st, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
-  gemm(p, st, p->rs, 256, p->Wet, 256, p->bet, p->t1, 128, N, 128, 256, CN_ACT_RELU, 0, 64);   // [enc | te]
-  gemm(p, st, p->t1 + 64, 128, p->WsT, 64, nullptr, p->u, 256, N, 256, 64, CN_ACT_NONE);        // u = W_s^T te
+  if (tcm) {
+    gemm(p, st, p->xr, 16, p->Wr, 16, p->br, nullptr, 256, N, 256, 16, CN_ACT_RELU, 0, ALL, nullptr, p->tRs.hi, p->tRs.lo);
+    gemm_tc(p, st, p->tRs, p->tWet, N, 128, 256, 64, p->bet, CN_ACT_RELU, out_both(p->t1, 128, p->tT1), nullptr, 0, 64);
+    gemm_tc(p, st, p->tTe, p->tWsT, N, 256, 64, 64, nullptr, CN_ACT_NONE, out32(p->u, 256));
+  } else {
+    gemm(p, st, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
+    gemm(p, st, p->rs, 256, p->Wet, 256, p->bet, p->t1, 128, N, 128, 256, CN_ACT_RELU, 0, 64);   // [enc | te]
+    gemm(p, st, p->t1 + 64, 128, p->WsT, 64, nullptr, p->u, 256, N, 256, 64, CN_ACT_NONE);        // u = W_s^T te
+  }
   mark(p, st, 7);
-  cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, p->row_start, N, H,
-                                                      p->wv);
+  cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, p->row_start, N, H, p->wv,
+                                                      tcm ? p->tWv.hi : nullptr, tcm ? p->tWv.lo : nullptr);
   p->launches += 1;
+  // 3. GRU: emb overwrites the te half of t1 -> t1 = [enc | emb] = GRU input
   mark(p, st, 8);
-  // emb overwrites the te half of t1 -> t1 = [enc | emb] = GRU input
-  gemm(p, st, p->wv, 256, p->Wa, 256, p->ba, p->t1 + 64, 128, N, 64, 256, CN_ACT_RELU);
-  gemm(p, st, p->t1, 128, p->Wih, 128, p->bih, p->gi, 384, N, 384, 128, CN_ACT_NONE);
-  gemm(p, st, p->h0, 128, p->Whh, 128, p->bhh, p->gh, 384, N, 384, 128, CN_ACT_NONE);
-  cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out, tcm ? p->h1h : nullptr,
-                                                            tcm ? p->h1l : nullptr);
+  if (tcm) {
+    TcOut o; o.oh = p->tT1.hi + 64; o.ol = p->tT1.lo + 64; o.ldh = 128;
+    gemm_tc(p, st, p->tWv, p->tWa, N, 64, 256, 64, p->ba, CN_ACT_RELU, o);
+    gemm_tc(p, st, p->tT1, p->tWih, N, 384, 128, 64, p->bih, CN_ACT_NONE, out32(p->gi, 384));
+    gemm_tc(p, st, p->tH0, p->tWhh, N, 384, 128, 64, p->bhh, CN_ACT_NONE, out32(p->gh, 384));
+  } else {
+    gemm(p, st, p->wv, 256, p->Wa, 256, p->ba, p->t1 + 64, 128, N, 64, 256, CN_ACT_RELU);
+    gemm(p, st, p->t1, 128, p->Wih, 128, p->bih, p->gi, 384, N, 384, 128, CN_ACT_NONE);
+    gemm(p, st, p->h0, 128, p->Whh, 128, p->bhh, p->gh, 384, N, 384, 128, CN_ACT_NONE);
+  }
+  cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out, tcm ? p->tH1.hi : nullptr,
+                                                            tcm ? p->tH1.lo : nullptr);
   p->launches += 1;
+  // 4. output_linear, actor / critic MLPs, heads
   mark(p, st, 9);
   if (tcm) {
-    gemm_tc(p, st, p->m_h1h, p->m_h1l, p->m_Woh, p->m_Wol, N, 256, 128, p->bo, CN_ACT_NONE, nullptr, 0, p->outh, p->outl, 256);
-    gemm_tc(p, st, p->m_outh, p->m_outl, p->m_Wac1h, p->m_Wac1l, N, 512, 256, p->bac1, CN_ACT_TANH, nullptr, 0, p->ac1h, p->ac1l, 512);
-    gemm_tc(p, st, p->m_a1h, p->m_a1l, p->m_Wa2h, p->m_Wa2l, N, 256, 256, p->ba2, CN_ACT_TANH, p->a2, 256, nullptr, nullptr, 0);
-    gemm_tc(p, st, p->m_c1h, p->m_c1l, p->m_Wc2h, p->m_Wc2l, N, 256, 256, p->bc2, CN_ACT_TANH, p->c2, 256, nullptr, nullptr, 0);
+    gemm_tc(p, st, p->tH1, p->tWo, N, 256, 128, 64, p->bo, CN_ACT_NONE, out16(p->tOut));
+    gemm_tc(p, st, p->tOut, p->tWac1, N, 512, 256, 64, p->bac1, CN_ACT_TANH, out16(p->tAc1));    // [actor.0 | critic.0]
+    gemm_tc(p, st, p->tA1, p->tWa2, N, 256, 256, 64, p->ba2, CN_ACT_TANH, out32(p->a2, 256));
+    gemm_tc(p, st, p->tC1, p->tWc2, N, 256, 256, 64, p->bc2, CN_ACT_TANH, out32(p->c2, 256));
   } else {
     gemm(p, st, d->h_out, 128, p->Wo, 128, p->bo, p->outb, 256, N, 256, 128, CN_ACT_NONE);
-    gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);      // [actor.0 | critic.0]
+    gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);
     gemm(p, st, p->ac1, 512, p->Wa2, 256, p->ba2, p->a2, 256, N, 256, 256, CN_ACT_TANH);
     gemm(p, st, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
   }
@@ -503,26 +520,21 @@ int64_t cn_policy_last_rows(cn_policy* p) {
 }
 
 // Internal test hook (not part of the public header): C = act(A[M,K] W[N,K]^T + bias) through the
-// tcgen05 3xFP16 kernel, fp32 device pointers in/out.  Used by tests/test_gpu_gemm_tc.py.
-int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, float* dC, int M, int N, int K, int act) {
-  if (N % TC_BN || K % TC_BK) return cn_set_error("cn_internal_gemm_tc: need N %% 256 == 0 and K %% 64 == 0");
+// tcgen05 3xFP16 kernel with B-tile rows `bn` (256 or 64), fp32 device pointers in/out.
+int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, float* dC, int M, int N, int K, int act,
+                        int bn) {
+  if ((bn != 256 && bn != 64) || N % bn || K % TC_BK)
+    return cn_set_error("cn_internal_gemm_tc: need bn in {64,256}, N %% bn == 0 and K %% 64 == 0");
   cn_policy tmp;
   tmp.launches = 0;
-  __half *ah, *al, *bh, *bl;
-  int rc = halloc16(&tmp, &ah, (size_t)M * K);
-  if (!rc) rc = halloc16(&tmp, &al, (size_t)M * K);
-  if (!rc) rc = halloc16(&tmp, &bh, (size_t)N * K);
-  if (!rc) rc = halloc16(&tmp, &bl, (size_t)N * K);
-  CUtensorMap mah, mal, mbh, mbl;
-  if (!rc) rc = make_map(&mah, ah, M, K, TC_BM);
-  if (!rc) rc = make_map(&mal, al, M, K, TC_BM);
-  if (!rc) rc = make_map(&mbh, bh, N, K, TC_BN);
-  if (!rc) rc = make_map(&mbl, bl, N, K, TC_BN);
+  TcMat A, B;
+  int rc = tc_alloc(&tmp, A, M, K, TC_BM);
+  if (!rc) rc = tc_alloc(&tmp, B, N, K, bn);
+  if (!rc) rc = tc_set_attrs();
   if (!rc) {
-    cudaFuncSetAttribute(cn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    split16(&tmp, 0, dA, 1.0f, ah, al, (size_t)M * K);
-    split16(&tmp, 0, dW, 64.0f, bh, bl, (size_t)N * K);
-    gemm_tc(&tmp, 0, mah, mal, mbh, mbl, M, N, K, dbias, act, dC, N, nullptr, nullptr, 0);
+    split16(&tmp, 0, dA, 1.0f, A.hi, A.lo, (size_t)M * K);
+    split16(&tmp, 0, dW, 64.0f, B.hi, B.lo, (size_t)N * K);
+    gemm_tc(&tmp, 0, A, B, M, N, K, bn, dbias, act, out32(dC, N));
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) rc = cn_set_error("cn_internal_gemm_tc: %s", cudaGetErrorString(err));
   }

@@ -199,7 +199,8 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
                                       const int* __restrict__ row_start, float* __restrict__ x16,
                                       const float* __restrict__ temporal, const float* __restrict__ robot,
                                       const float* __restrict__ h_in, const float* __restrict__ masks,
-                                      float* __restrict__ xr, float* __restrict__ h0) {
+                                      float* __restrict__ xr, float* __restrict__ h0, __half* __restrict__ h0_hi,
+                                      __half* __restrict__ h0_lo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < N * H * 16) {
     const int r = idx >> 4, c = idx & 15;
@@ -214,7 +215,16 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
     else if (c < 9) v = robot[7 * e + (c - 2)];
     xr[idx] = v;
   }
-  if (idx < N * 128) h0[idx] = h_in[idx] * masks[idx >> 7];
+  if (idx < N * 128) {
+    const float hv = h_in[idx] * masks[idx >> 7];
+    h0[idx] = hv;
+    if (h0_hi) {
+      const float c = fminf(fmaxf(hv, -65504.0f), 65504.0f);
+      const __half hh = __float2half_rn(c);
+      h0_hi[idx] = hh;
+      h0_lo[idx] = __float2half_rn(c - __half2float(hh));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -226,31 +236,18 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
                                                               const int* __restrict__ row_start, int H,
                                                               float* __restrict__ out /* [Mc,512] or null */,
                                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  // One CTA per (environment, group of heads), one WARP per head (blockDim.x / 32 heads per CTA:
-  // 8 when shared memory allows).  The environment has n <= H valid (compacted) humans; each warp
-  // keeps K and V of its head in shared memory and walks the n queries.
-  extern __shared__ float sm[];
+  // One CTA per environment, one WARP per head.  An environment has only n <= H valid (compacted)
+  // humans (n ~ 4-8 on average), so K / V rows are read straight from global memory (L1/L2 resident,
+  // each row is re-read n times) instead of being staged: no shared memory, no block barrier, full
+  // occupancy.  Lanes own keys for the scores and output dims for P.V.
   const int e = blockIdx.x;
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hd = blockIdx.y * (blockDim.x >> 5) + wib;
+  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t row0 = (size_t)row_start[e];
   const int n = row_start[e + 1] - row_start[e];
-  float* Ks = sm + (size_t)wib * ((size_t)H * 129 + 64);  // [H][65]
-  float* Vs = Ks + (size_t)H * 65;                        // [H][64]
-  float* q = Vs + (size_t)H * 64;                         // [64]
-  for (int idx = lane; idx < n * 64; idx += 32) {
-    const int j = idx >> 6, d = idx & 63;
-    const float* src = qkv + (row0 + j) * 1536 + hd * 64 + d;
-    Ks[j * 65 + d] = src[512];
-    Vs[j * 64 + d] = src[1024];
-  }
-  __syncwarp();
   const float scale = 0.125f;   // 1/sqrt(head_dim = 64)
+  const float* base = qkv + row0 * 1536 + hd * 64;
   for (int i = 0; i < n; ++i) {
-    const float* qsrc = qkv + (row0 + i) * 1536 + hd * 64;
-    q[lane] = qsrc[lane] * scale; q[lane + 32] = qsrc[lane + 32] * scale;   // torch scales q before q k^T
-    __syncwarp();
-    // scores: lanes over keys
+    const float4* qv = reinterpret_cast<const float4*>(base + (size_t)i * 1536);   // broadcast loads
     float sc[4];
     float mx = -INFINITY;
 #pragma unroll
@@ -258,10 +255,15 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
       const int j = lane + 32 * t;
       float s = -INFINITY;
       if (j < n) {
+        const float4* kv = reinterpret_cast<const float4*>(base + (size_t)j * 1536 + 512);
         s = 0.0f;
-        const float* kr = Ks + j * 65;
-#pragma unroll 16
-        for (int d = 0; d < 64; ++d) s = fmaf(q[d], kr[d], s);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          const float4 a = __ldg(qv + d), b = __ldg(kv + d);
+          // torch scales q before q k^T
+          s = fmaf(a.x * scale, b.x, s); s = fmaf(a.y * scale, b.y, s);
+          s = fmaf(a.z * scale, b.z, s); s = fmaf(a.w * scale, b.w, s);
+        }
       }
       sc[t] = s;
       mx = fmaxf(mx, s);
@@ -278,12 +280,13 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
-    // O = P V: lanes over the 64 output dims (2 per lane)
+    // O = P V: lanes over the 64 output dims (2 per lane), coalesced V reads
     float o0 = 0.0f, o1 = 0.0f;
     for (int j = 0; j < n; ++j) {
       const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31) * inv;
-      o0 = fmaf(pj, Vs[j * 64 + lane], o0);
-      o1 = fmaf(pj, Vs[j * 64 + lane + 32], o1);
+      const float* vr = base + (size_t)j * 1536 + 1024;
+      o0 = fmaf(pj, __ldg(vr + lane), o0);
+      o1 = fmaf(pj, __ldg(vr + lane + 32), o1);
     }
     const size_t off = (row0 + i) * 512 + hd * 64;
     if (out) { out[off + lane] = o0; out[off + lane + 32] = o1; }
@@ -294,7 +297,6 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
       out_lo[off + lane] = __float2half_rn(c0 - __half2float(h0));
       out_lo[off + lane + 32] = __float2half_rn(c1 - __half2float(h1));
     }
-    __syncwarp();
   }
 }
 
@@ -308,7 +310,8 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
                                                               const float* __restrict__ te /* [N, ldte] cols te_off.. */,
                                                               int ldte, int te_off, const float* __restrict__ b_s,
                                                               const int* __restrict__ row_start, int N, int H,
-                                                              float* __restrict__ wv /* [N,256] */) {
+                                                              float* __restrict__ wv /* [N,256] */,
+                                                              __half* __restrict__ wv_hi, __half* __restrict__ wv_lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 4 + warp;
   if (e >= N) return;
@@ -355,7 +358,16 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
     for (int t = 0; t < 8; ++t) acc[t] = fmaf(pj, sr[lane + 32 * t], acc[t]);
   }
 #pragma unroll
-  for (int t = 0; t < 8; ++t) wv[(size_t)e * 256 + lane + 32 * t] = acc[t];
+  for (int t = 0; t < 8; ++t) {
+    const size_t o = (size_t)e * 256 + lane + 32 * t;
+    wv[o] = acc[t];
+    if (wv_hi) {
+      const float c = fminf(fmaxf(acc[t], -65504.0f), 65504.0f);
+      const __half hh = __float2half_rn(c);
+      wv_hi[o] = hh;
+      wv_lo[o] = __float2half_rn(c - __half2float(hh));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

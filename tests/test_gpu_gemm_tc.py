@@ -12,13 +12,16 @@ pytestmark = pytest.mark.gpu
 def _lib():
     from crowdnav_prediction_attngraph_b200 import _capi
     lib = _capi.load_library()
-    lib.cn_internal_gemm_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.cn_internal_gemm_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int]
     return lib, _capi
 
 
-@pytest.mark.parametrize("M,N,K,act", [(128, 256, 64, 0), (256, 256, 128, 0), (300, 512, 128, 1), (4096, 1536, 512, 0),
-                                       (1000, 256, 512, 1)])
-def test_gemm_tc_matches_fp64(M, N, K, act):
+@pytest.mark.parametrize("M,N,K,act,bn", [(128, 256, 64, 0, 256), (256, 256, 128, 0, 256), (300, 512, 128, 1, 256),
+                                          (4096, 1536, 512, 0, 256), (1000, 256, 512, 1, 256),
+                                          (128, 64, 64, 0, 64), (4096, 384, 128, 0, 64), (300, 128, 256, 1, 64),
+                                          (4096, 512, 256, 2, 64), (777, 256, 320, 0, 64)])
+def test_gemm_tc_matches_fp64(M, N, K, act, bn):
     lib, _capi = _lib()
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 2).cuda()
@@ -26,14 +29,17 @@ def test_gemm_tc_matches_fp64(M, N, K, act):
     W = (torch.randn(N, K, generator=g) * 0.05).cuda()
     b = torch.randn(N, generator=g).cuda()
     Cout = torch.full((M, N), float("nan"), device="cuda")
-    _capi.check(lib, lib.cn_internal_gemm_tc(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cout.data_ptr(), M, N, K, act),
+    _capi.check(lib, lib.cn_internal_gemm_tc(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cout.data_ptr(), M, N, K, act, bn),
                 "cn_internal_gemm_tc")
     ref = A.double() @ W.double().T + b.double()
     if act == 1:
         ref = ref.clamp_min(0)
+    if act == 2:
+        ref = torch.tanh(ref)
     err = (Cout.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    assert err < 3e-6 * max(1.0, scale), (err, scale)
+    tol = 2e-6 if act == 2 else 3e-6 * max(1.0, scale)       # fast tanh: ~1e-6 absolute
+    assert err < tol, (err, scale)
 
 
 @pytest.mark.parametrize("name,H", [("policy_h20", 20), ("policy_h50", 50)])
