@@ -103,9 +103,11 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase ORCA: one thread = one human's rvo2 simulator (crowd_sim.py:680-703, orca.py:64-117).
+// Phase ORCA, part 1 (per thread = one human's rvo2 simulator, crowd_sim.py:680-703, orca.py:64-117):
+// neighbour selection and ORCA half-plane construction into `lines` (sorted by distance).
 template <int MAXH>
-CN_HD void cn_phase_orca(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnLineStore lines) {
+CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnLineStore lines, int& nl_out,
+                         float& vmax_out, CnF2& pref_out) {
   const int H = p.H;
   const size_t i = cn_idx(p, e, h);
   const double fov = p.human_fov;
@@ -168,14 +170,16 @@ CN_HD void cn_phase_orca(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
                                    : (float)((dummy ? 0.3 : s.rad[j]) + pad + p.orca_safety_space);
     lines.set(rank, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
   }
-  CnF2 result;
-  const int lineFail = cn_lp2(lines, nl, vmax, pref, false, result);
-  if (lineFail < nl) cn_lp3<MAXH>(lines, nl, lineFail, vmax, result);
+  nl_out = nl; vmax_out = vmax; pref_out = pref;
+}
+
+// Phase ORCA, part 3 (per thread): publish the solved velocity + the robot-collision distance.
+CN_HD void cn_orca_finish(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnF2 result, int nl, int fail) {
+  const size_t i = cn_idx(p, e, h);
   s.nvx[h] = result.x; s.nvy[h] = result.y;
   g.last_hvx[i] = result.x; g.last_hvy[i] = result.y;
-  g.orca_nlines[i] = nl; g.orca_fail[i] = (lineFail < nl) ? lineFail : -1;
-
-  // --- collision distance to the robot for calc_reward (state BEFORE the action is applied)
+  g.orca_nlines[i] = nl; g.orca_fail[i] = fail;
+  // collision distance to the robot for calc_reward (state BEFORE the action is applied)
   const double dx = s.px[h] - s.rpx, dy = s.py[h] - s.rpy;
   s.t0[h] = sqrt(dx * dx + dy * dy) - s.rad[h] - p.robot_radius;
 }

@@ -68,16 +68,33 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
     if (h == 0) env_view(smem + (size_t)le * L.per_env, L, H);
   }
   __syncthreads();
-  float4 ovf[MAXH];            // overflow lines (k >= line_cap): local memory, rarely touched
-  CnLineStore lines;
-  lines.base = reinterpret_cast<float4*>(smem + align16((size_t)epb * L.per_env)) + threadIdx.x;
-  lines.stride = blockDim.x;
-  lines.cap = line_cap;
-  lines.ovf = ovf;
+  // ORCA line storage of this warp: first `line_cap` lines of every thread in shared memory
+  // ([line][thread]), the rest in a global scratch row per thread; projected lines of the
+  // cooperative linearProgram3 in a per-warp shared scratch.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* lines_smem = reinterpret_cast<float4*>(smem + align16((size_t)epb * L.per_env));
+  CnWarpLines W;
+  W.smem0 = lines_smem + warp * 32;
+  W.stride = blockDim.x;
+  W.cap = line_cap;
+  W.ovf_stride = g.ovf_stride;
+  W.ovf0 = reinterpret_cast<float4*>(g.line_ovf) + ((size_t)blockIdx.x * blockDim.x + warp * 32) * g.ovf_stride;
+  CnLineStore proj;
+  proj.base = lines_smem + (size_t)line_cap * blockDim.x + (size_t)warp * MAXH;
+  proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
+  const CnCoop co = {lane, 32};
 
   if (active) cn_phase_load(p, g, *s, e, h, action);
   __syncthreads();
-  if (active) cn_phase_orca<MAXH>(p, g, *s, e, h, lines);
+  {
+    int nl = 0, fail = -1;
+    float vmax = 0.0f;
+    CnF2 pref = f2(0.0f, 0.0f), result = f2(0.0f, 0.0f);
+    if (active) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref);
+    __syncwarp();
+    cn_orca_solve_coop(co, W, nl, vmax, pref, proj, result, fail);    // all 32 lanes, idle ones with nl = 0
+    if (active) cn_orca_finish(p, g, *s, e, h, result, nl, fail);
+  }
   __syncthreads();
   if (active && h == 0) cn_phase_reward(p, g, *s, e, out);
   __syncthreads();
@@ -331,7 +348,8 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   KernelFn fn = pick_kernel(env->maxh);
   int cap = p.H > 1 ? p.H - 1 : 1;
   for (;;) {
-    const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * env->threads * sizeof(float4);
+    const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * env->threads * sizeof(float4) +
+                        (size_t)(env->threads / 32) * env->maxh * sizeof(float4);   // + per-warp LP3 scratch
     bool ok = need <= 227 * 1024;
     if (ok) {
       err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
@@ -346,6 +364,14 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   }
   err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+  {
+    // global scratch for the overflow lines (k >= line_cap) of every step-kernel thread
+    float4* ovf = nullptr;
+    env->g.ovf_stride = (p.H - 1 - env->line_cap) > 0 ? (p.H - 1 - env->line_cap) : 1;
+    int rc2 = dev_alloc(env, nullptr, &ovf, (size_t)grid * env->threads * env->g.ovf_stride);
+    if (rc2) { cn_env_destroy(env); return rc2; }
+    env->g.line_ovf = ovf;
+  }
   // reset kernel: per-warp working set + MT19937 state + observation rows
   env->reset_warp_bytes = align16(L.per_env + 624 * sizeof(uint32_t) + (size_t)p.H * 16 * sizeof(float));
   err = cudaFuncSetAttribute(cn_env_event_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -12,6 +12,7 @@
 // per-thread local array.
 #pragma once
 #include "cn_common.cuh"
+#include "cn_rng.cuh"   // CnCoop and the warp collectives
 
 #define CN_RVO_EPS 0.00001f
 
@@ -211,4 +212,182 @@ CN_HD CnLine cn_orca_line(CnF2 pos, CnF2 vel, float radius, CnF2 opos, CnF2 ovel
   }
   line.point = f2add(vel, f2scale(0.5f, u));
   return line;
+}
+
+
+// ==========================================================================================
+// Warp-cooperative LP.  In steady state ~30 % of the human-steps end in linearProgram3 and the
+// serial per-thread solve leaves 1-2 lanes of a warp active for most of the kernel (profiles/).
+// Here the 32 lanes of a warp solve ONE human's LP at a time: the loops over "previous lines"
+// (linearProgram1's interval clipping, linearProgram3's projected-line construction) are split
+// across lanes and reduced with exact min / max / ballot, so the result is bit-identical to the
+// sequential RVO2 order:  tLeft only grows and tRight only shrinks, hence "some prefix has
+// tLeft > tRight" <=> "the final interval is empty", and a parallel-infeasible line fails the LP
+// wherever it sits.  Every function below is called by all lanes with warp-uniform arguments.
+
+template <class Lines>
+CN_HD bool cn_lp1_coop(const CnCoop& co, const Lines& lines, int lineNo, float radius, CnF2 optVelocity,
+                       bool directionOpt, CnF2& result) {
+  const CnLine ln = lines.get(lineNo);
+  const float dotProduct = f2dot(ln.point, ln.dir);
+  const float discriminant = dotProduct * dotProduct + radius * radius - f2abssq(ln.point);
+  if (discriminant < 0.0f) return false;
+  const float sqrtDiscriminant = sqrtf(discriminant);
+  float tLeft = -dotProduct - sqrtDiscriminant;
+  float tRight = -dotProduct + sqrtDiscriminant;
+  float tl = -INFINITY, tr = INFINITY;
+  bool bad = false;
+  for (int i = co.lane; i < lineNo; i += co.nlanes) {
+    const CnLine li = lines.get(i);
+    const float denominator = f2det(ln.dir, li.dir);
+    const float numerator = f2det(li.dir, f2sub(ln.point, li.point));
+    if (fabsf(denominator) <= CN_RVO_EPS) {
+      if (numerator < 0.0f) bad = true;
+      continue;
+    }
+    const float t = numerator / denominator;
+    if (denominator >= 0.0f) tr = cn_minf(tr, t);
+    else tl = cn_maxf(tl, t);
+  }
+  bad = cn_any(co, bad);
+  tr = cn_warp_min(co, tr);
+  tl = cn_warp_max(co, tl);
+  if (bad) return false;
+  tRight = cn_minf(tRight, tr);
+  tLeft = cn_maxf(tLeft, tl);
+  if (tLeft > tRight) return false;
+  if (directionOpt) {
+    if (f2dot(optVelocity, ln.dir) > 0.0f) result = f2add(ln.point, f2scale(tRight, ln.dir));
+    else result = f2add(ln.point, f2scale(tLeft, ln.dir));
+  } else {
+    const float t = f2dot(ln.dir, f2sub(optVelocity, ln.point));
+    if (t < tLeft) result = f2add(ln.point, f2scale(tLeft, ln.dir));
+    else if (t > tRight) result = f2add(ln.point, f2scale(tRight, ln.dir));
+    else result = f2add(ln.point, f2scale(t, ln.dir));
+  }
+  return true;
+}
+
+// linearProgram2 with a warp-uniform result (used on the projected lines inside linearProgram3)
+template <class Lines>
+CN_HD int cn_lp2_coop(const CnCoop& co, const Lines& lines, int numLines, float radius, CnF2 optVelocity,
+                      bool directionOpt, CnF2& result) {
+  if (directionOpt) result = f2scale(radius, optVelocity);
+  else if (f2abssq(optVelocity) > radius * radius) result = f2scale(radius, f2normalize(optVelocity));
+  else result = optVelocity;
+  for (int i = 0; i < numLines; ++i) {
+    const CnLine li = lines.get(i);
+    if (f2det(li.dir, f2sub(li.point, result)) > 0.0f) {
+      const CnF2 tempResult = result;
+      if (!cn_lp1_coop(co, lines, i, radius, optVelocity, directionOpt, result)) {
+        result = tempResult;
+        return i;
+      }
+    }
+  }
+  return numLines;
+}
+
+// linearProgram3: `proj` is a warp-shared scratch store for the projected lines
+template <class Lines>
+CN_HD void cn_lp3_coop(const CnCoop& co, const Lines& lines, int numLines, int beginLine, float radius, CnF2& result,
+                       CnLineStore proj) {
+  float distance = 0.0f;
+  for (int i = beginLine; i < numLines; ++i) {
+    const CnLine li = lines.get(i);
+    if (f2det(li.dir, f2sub(li.point, result)) > distance) {
+      int np = 0;
+      for (int base = 0; base < i; base += co.nlanes) {
+        const int j = base + co.lane;
+        bool keep = false;
+        CnLine line;
+        line.point = f2(0.0f, 0.0f); line.dir = f2(0.0f, 0.0f);
+        if (j < i) {
+          const CnLine lj = lines.get(j);
+          const float determinant = f2det(li.dir, lj.dir);
+          if (fabsf(determinant) <= CN_RVO_EPS) {
+            if (!(f2dot(li.dir, lj.dir) > 0.0f)) {
+              line.point = f2scale(0.5f, f2add(li.point, lj.point));
+              keep = true;
+            }
+          } else {
+            line.point = f2add(li.point, f2scale(f2det(lj.dir, f2sub(li.point, lj.point)) / determinant, li.dir));
+            keep = true;
+          }
+          if (keep) line.dir = f2normalize(f2sub(lj.dir, li.dir));
+        }
+        const uint32_t m = cn_ballot(co, keep);
+        if (keep) proj.set(np + cn_popc_below(co, m), line);       // order-preserving compaction
+        np += cn_popc(m);
+      }
+      cn_coop_sync(co);
+      const CnF2 tempResult = result;
+      if (cn_lp2_coop(co, proj, np, radius, f2(-li.dir.y, li.dir.x), true, result) < np) result = tempResult;
+      distance = f2det(li.dir, f2sub(li.point, result));
+      cn_coop_sync(co);
+    }
+  }
+}
+
+// The line stores of all lanes of a warp: lane L's lines start at smem0 + L (stride `stride`
+// float4 per line) and its overflow lines (k >= cap) at ovf0 + L * ovf_stride.
+struct CnWarpLines {
+  float4* smem0;
+  int stride, cap;
+  float4* ovf0;
+  int ovf_stride;
+  CN_HD CnLineStore of(int lane) const {
+    CnLineStore s; s.base = smem0 + lane; s.stride = stride; s.cap = cap; s.ovf = ovf0 + (size_t)lane * ovf_stride;
+    return s;
+  }
+};
+
+// Solve the LPs of all lanes of a warp.  In: per-lane line count / max speed / preferred velocity
+// (nl = 0 for idle lanes).  Out: per-lane new velocity and LP2 failure index (-1 = LP2 succeeded).
+CN_HD void cn_orca_solve_coop(const CnCoop& co, const CnWarpLines& W, int nl, float vmax, CnF2 pref, CnLineStore proj,
+                              CnF2& result, int& fail) {
+  const CnLineStore mine = W.of(co.lane);
+  // linearProgram2 initialisation (closest point, not direction)
+  if (f2abssq(pref) > vmax * vmax) result = f2scale(vmax, f2normalize(pref));
+  else result = pref;
+  fail = -1;
+  int i = 0;
+  int running = nl > 0 ? 1 : 0;
+  for (;;) {
+    if (running) {           // own scan up to the next violated constraint (no collectives inside)
+      while (i < nl) {
+        const CnLine li = mine.get(i);
+        if (f2det(li.dir, f2sub(li.point, result)) > 0.0f) break;
+        ++i;
+      }
+      if (i == nl) running = 0;
+    }
+    cn_coop_sync(co);
+    uint32_t req = cn_ballot(co, running != 0);
+    if (!req) break;
+    while (req) {
+      const int L = cn_ffs(req);
+      req &= req - 1;
+      const int iL = cn_bcast_i(co, i, L);
+      const float rL = cn_bcast_f(co, vmax, L);
+      const CnF2 oL = f2(cn_bcast_f(co, pref.x, L), cn_bcast_f(co, pref.y, L));
+      CnF2 r2 = f2(0.0f, 0.0f);
+      const bool ok = cn_lp1_coop(co, W.of(L), iL, rL, oL, false, r2);
+      if (co.lane == L) {
+        if (ok) { result = r2; ++i; }
+        else { fail = i; running = 0; }
+      }
+    }
+  }
+  // linearProgram3 for the lanes whose LP2 failed, one owner at a time
+  uint32_t req = cn_ballot(co, fail >= 0);
+  while (req) {
+    const int L = cn_ffs(req);
+    req &= req - 1;
+    const int nlL = cn_bcast_i(co, nl, L), fL = cn_bcast_i(co, fail, L);
+    const float rL = cn_bcast_f(co, vmax, L);
+    CnF2 resL = f2(cn_bcast_f(co, result.x, L), cn_bcast_f(co, result.y, L));
+    cn_lp3_coop(co, W.of(L), nlL, fL, rL, resL, proj);
+    if (co.lane == L) result = resL;
+  }
 }

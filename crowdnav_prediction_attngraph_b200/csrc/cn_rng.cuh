@@ -15,10 +15,9 @@ struct CnRng {
   int pos;
 };
 
-// Cooperative execution context.  The reset kernel runs ONE environment per warp with every lane
-// executing the same (replicated, warp-uniform) control flow; only the data-parallel inner loops
-// (MT19937 twist, rejection-sampling collision checks) are split across lanes.  {0, 1} = a single
-// thread (the step kernel's leader, the CPU test harness).
+// Cooperative execution context.  {lane, 32}: the 32 lanes of a warp execute the same (replicated,
+// warp-uniform) control flow and split data-parallel inner loops between them; {0, 1}: a single
+// thread (the CPU test harness, where every collective degenerates to the identity).
 struct CnCoop {
   int lane, nlanes;
 };
@@ -33,6 +32,67 @@ CN_HD void cn_coop_sync(const CnCoop& c) {
   if (c.nlanes > 1) __syncwarp();
 #endif
   (void)c;
+}
+CN_HD uint32_t cn_ballot(const CnCoop& c, bool pred) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) return __ballot_sync(0xffffffffu, pred);
+#endif
+  return pred ? 1u : 0u;
+}
+CN_HD float cn_bcast_f(const CnCoop& c, float v, int src) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) return __shfl_sync(0xffffffffu, v, src);
+#endif
+  (void)src;
+  return v;
+}
+CN_HD int cn_bcast_i(const CnCoop& c, int v, int src) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) return __shfl_sync(0xffffffffu, v, src);
+#endif
+  (void)src;
+  return v;
+}
+// warp-wide min / max with std::min / std::max comparison semantics (exact, order independent
+// for non-NaN inputs)
+CN_HD float cn_warp_min(const CnCoop& c, float v) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = (w < v) ? w : v; }
+  }
+#endif
+  return v;
+}
+CN_HD float cn_warp_max(const CnCoop& c, float v) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = (v < w) ? w : v; }
+  }
+#endif
+  return v;
+}
+CN_HD int cn_popc_below(const CnCoop& c, uint32_t mask) {   // set bits of `mask` at lane positions below this lane
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) return __popc(mask & ((1u << c.lane) - 1u));
+#endif
+  (void)mask;
+  return 0;
+}
+CN_HD int cn_popc(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  return __popc(m);
+#else
+  return __builtin_popcount(m);
+#endif
+}
+CN_HD int cn_ffs(uint32_t m) {    // index of the lowest set bit (m != 0)
+#if defined(__CUDA_ARCH__)
+  return __ffs(m) - 1;
+#else
+  return __builtin_ffs((int)m) - 1;
+#endif
 }
 
 CN_HD void cn_rng_seed(CnRng& r, uint32_t seed, const CnCoop& c) {

@@ -41,6 +41,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
   std::vector<uint8_t> u(H);
   std::vector<float4> lines((size_t)H * H);
   std::vector<float> rows((size_t)H * 16);
+  std::vector<float4> projbuf(MAXH);
   for (int e = 0; e < p.N; ++e) {
     CnEnvSh s;
     s.px = d.data(); s.py = s.px + H; s.gx = s.py + H; s.gy = s.gx + H; s.rad = s.gy + H; s.vpref = s.rad + H;
@@ -54,9 +55,14 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     } else {
       for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, action);
       for (int h = 0; h < H; ++h) {
-        CnLineStore ls; ls.base = lines.data() + (size_t)h * H; ls.stride = 1;
-        ls.cap = 3; ls.ovf = lines.data() + (size_t)h * H + 3;      // exercise both storage tiers
-        cn_phase_orca<MAXH>(p, g, s, e, h, ls);
+        // single-lane "warp": the cooperative solver degenerates to the sequential RVO2 order
+        CnWarpLines W; W.smem0 = lines.data() + (size_t)h * H; W.stride = 1; W.cap = 3;    // exercise both tiers
+        W.ovf0 = lines.data() + (size_t)h * H + 3; W.ovf_stride = 0;
+        CnLineStore proj; proj.base = projbuf.data(); proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
+        int nl = 0, fail = -1; float vmax = 0; CnF2 pref = f2(0, 0), result = f2(0, 0);
+        cn_orca_build<MAXH>(p, g, s, e, h, W.of(0), nl, vmax, pref);
+        cn_orca_solve_coop(co, W, nl, vmax, pref, proj, result, fail);
+        cn_orca_finish(p, g, s, e, h, result, nl, fail);
       }
       cn_phase_reward(p, g, s, e, out);
       for (int h = 0; h < H; ++h) cn_phase_integrate(p, s, h);
