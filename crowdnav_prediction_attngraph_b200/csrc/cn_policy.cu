@@ -51,7 +51,7 @@ struct cn_policy {
   bool profile;
   std::vector<cudaEvent_t> ev;
   // workspace
-  int *row_start, *mc;
+  int *row_start, *row_env, *mc;
   float *x16, *e1, *e2, *qkv, *ao, *sout, *xr, *rs, *t1, *u, *wv, *h0, *gi, *gh, *outb, *ac1, *a2, *c2;
 };
 
@@ -244,6 +244,8 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
     p->row_start = reinterpret_cast<int*>(q);
     if (!rc) rc = palloc(p, &q, 4);
     p->mc = reinterpret_cast<int*>(q);
+    if (!rc) rc = palloc(p, &q, M + 1);
+    p->row_env = reinterpret_cast<int*>(q);
   }
   WS(x16, M * 16); WS(e1, M * 128); WS(e2, M * 512); WS(qkv, M * 1536); WS(ao, M * 512); WS(sout, M * 256);
   WS(xr, N * 16); WS(rs, N * 256); WS(t1, N * 128); WS(u, N * 256); WS(wv, N * 256); WS(h0, N * 128);
@@ -432,7 +434,7 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   {
     cn_row_offsets_kernel<<<1, 1024, 0, st>>>(d->detected_human_num, N, H, p->row_start, p->mc);
     const int total = M * 16 > N * 128 ? M * 16 : N * 128;
-    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->x16,
+    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->row_env, p->x16,
                                                                d->temporal_edges, d->robot_node, d->h_in, d->masks, p->xr,
                                                                p->h0, tcm ? p->tH0.hi : nullptr, tcm ? p->tH0.lo : nullptr);
     p->launches += 2;
@@ -449,8 +451,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
   mark(p, st, 4);
   {
-    cn_hh_attention_kernel<<<N, 256, 0, st>>>(
-        p->qkv, p->row_start, H, tcm ? nullptr : p->ao, tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
+    cn_hh_attention_kernel<<<(M + 7) / 8, 256, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, tcm ? nullptr : p->ao,
+                                                        tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
     p->launches += 1;
   }
   mark(p, st, 5);

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(1024) cn_row_offsets_kernel(const float* __res
 // Input packing: x16[row_start[e] + j, 16] = spatial_edges[e, j] zero-padded to K=16 for j < n_e;
 // xr[N,16] = cat(temporal_edges(2), robot_node(7)) zero padded; h0 = h_in * mask.
 __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win, int H, int N,
-                                      const int* __restrict__ row_start, float* __restrict__ x16,
+                                      const int* __restrict__ row_start, int* __restrict__ row_env,
+                                      float* __restrict__ x16,
                                       const float* __restrict__ temporal, const float* __restrict__ robot,
                                       const float* __restrict__ h_in, const float* __restrict__ masks,
                                       float* __restrict__ xr, float* __restrict__ h0, __half* __restrict__ h0_hi,
@@ -206,7 +207,10 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
     const int r = idx >> 4, c = idx & 15;
     const int e = r / H, j = r - e * H;
     const int rs = row_start[e], n = row_start[e + 1] - rs;
-    if (j < n) x16[(size_t)(rs + j) * 16 + c] = c < Win ? spatial[(size_t)r * Win + c] : 0.0f;
+    if (j < n) {
+      x16[(size_t)(rs + j) * 16 + c] = c < Win ? spatial[(size_t)r * Win + c] : 0.0f;
+      if (c == 0) row_env[rs + j] = e;
+    }
   }
   if (idx < N * 16) {
     const int e = idx >> 4, c = idx & 15;
@@ -233,70 +237,85 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
 // Keys j >= n_e are padding (key_padding_mask); query rows >= n_e are never consumed
 // downstream (their robot-human attention weight is exactly 0), they are written as zeros.
 __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __restrict__ qkv,
-                                                              const int* __restrict__ row_start, int H,
+                                                              const int* __restrict__ row_start,
+                                                              const int* __restrict__ row_env,
+                                                              const int* __restrict__ mc_ptr,
                                                               float* __restrict__ out /* [Mc,512] or null */,
                                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  // One CTA per environment, one WARP per head.  An environment has only n <= H valid (compacted)
-  // humans (n ~ 4-8 on average), so K / V rows are read straight from global memory (L1/L2 resident,
-  // each row is re-read n times) instead of being staged: no shared memory, no block barrier, full
-  // occupancy.  Lanes own keys for the scores and output dims for P.V.
-  const int e = blockIdx.x;
-  const int hd = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // One WARP per valid (compacted) human row = one attention query, all 8 heads at once.
+  // Lane l owns elements [16 l, 16 l + 16) of the 512-wide q / k / v / o rows, i.e. a quarter of
+  // head l / 4: a key's score is a 16-FMA partial dot reduced over the 4 lanes of a head (2 shuffles),
+  // and soft-max is computed online (running max / sum) so nothing is staged: K and V rows are
+  // read straight from global memory with fully coalesced 2 KB warp loads.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= *mc_ptr) return;
+  const int e = row_env[r];
   const size_t row0 = (size_t)row_start[e];
   const int n = row_start[e + 1] - row_start[e];
-  const float scale = 0.125f;   // 1/sqrt(head_dim = 64)
-  const float* base = qkv + row0 * 1536 + hd * 64;
-  for (int i = 0; i < n; ++i) {
-    const float4* qv = reinterpret_cast<const float4*>(base + (size_t)i * 1536);   // broadcast loads
-    float sc[4];
-    float mx = -INFINITY;
+  const float scale = 0.125f;   // 1/sqrt(head_dim = 64); torch scales q before q k^T
+  float q[16], acc[16];
+  {
+    const float4* qv = reinterpret_cast<const float4*>(qkv + (size_t)r * 1536 + lane * 16);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int j = lane + 32 * t;
-      float s = -INFINITY;
-      if (j < n) {
-        const float4* kv = reinterpret_cast<const float4*>(base + (size_t)j * 1536 + 512);
-        s = 0.0f;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) {
-          const float4 a = __ldg(qv + d), b = __ldg(kv + d);
-          // torch scales q before q k^T
-          s = fmaf(a.x * scale, b.x, s); s = fmaf(a.y * scale, b.y, s);
-          s = fmaf(a.z * scale, b.z, s); s = fmaf(a.w * scale, b.w, s);
-        }
-      }
-      sc[t] = s;
-      mx = fmaxf(mx, s);
+      const float4 a = __ldg(qv + t);
+      q[4 * t] = a.x * scale; q[4 * t + 1] = a.y * scale; q[4 * t + 2] = a.z * scale; q[4 * t + 3] = a.w * scale;
     }
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.0f;
+  for (int t = 0; t < 16; ++t) acc[t] = 0.0f;
+  float m = -INFINITY, l = 0.0f;
+  for (int j = 0; j < n; ++j) {
+    const float4* kv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 512 + lane * 16);
+    const float4* vv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 1024 + lane * 16);
+    float s = 0.0f;
+    float4 vr[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int j = lane + 32 * t;
-      sc[t] = (j < n) ? expf(sc[t] - mx) : 0.0f;
-      sum += sc[t];
+      const float4 b = __ldg(kv + t);
+      vr[t] = __ldg(vv + t);
+      s = fmaf(q[4 * t], b.x, s); s = fmaf(q[4 * t + 1], b.y, s);
+      s = fmaf(q[4 * t + 2], b.z, s); s = fmaf(q[4 * t + 3], b.w, s);
     }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);          // all 4 lanes of the head hold the score
+    const float mn = fmaxf(m, s);
+    const float corr = expf(m - mn);                  // exp(-inf) = 0 on the first key
+    const float pj = expf(s - mn);
+    l = l * corr + pj;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-    // O = P V: lanes over the 64 output dims (2 per lane), coalesced V reads
-    float o0 = 0.0f, o1 = 0.0f;
-    for (int j = 0; j < n; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31) * inv;
-      const float* vr = base + (size_t)j * 1536 + 1024;
-      o0 = fmaf(pj, __ldg(vr + lane), o0);
-      o1 = fmaf(pj, __ldg(vr + lane + 32), o1);
+    for (int t = 0; t < 4; ++t) {
+      acc[4 * t] = fmaf(pj, vr[t].x, acc[4 * t] * corr);
+      acc[4 * t + 1] = fmaf(pj, vr[t].y, acc[4 * t + 1] * corr);
+      acc[4 * t + 2] = fmaf(pj, vr[t].z, acc[4 * t + 2] * corr);
+      acc[4 * t + 3] = fmaf(pj, vr[t].w, acc[4 * t + 3] * corr);
     }
-    const size_t off = (row0 + i) * 512 + hd * 64;
-    if (out) { out[off + lane] = o0; out[off + lane + 32] = o1; }
-    if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
-      const float c0 = fminf(fmaxf(o0, -65504.0f), 65504.0f), c1 = fminf(fmaxf(o1, -65504.0f), 65504.0f);
+    m = mn;
+  }
+  const float inv = 1.0f / l;
+  const size_t off = (size_t)r * 512 + lane * 16;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t] *= inv;
+  if (out) {
+    float4* dst = reinterpret_cast<float4*>(out + off);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dst[t] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
+  }
+  if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float c0 = fminf(fmaxf(acc[2 * t], -65504.0f), 65504.0f), c1 = fminf(fmaxf(acc[2 * t + 1], -65504.0f), 65504.0f);
       const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
-      out_hi[off + lane] = h0; out_hi[off + lane + 32] = h1;
-      out_lo[off + lane] = __float2half_rn(c0 - __half2float(h0));
-      out_lo[off + lane + 32] = __float2half_rn(c1 - __half2float(h1));
+      const __half l0 = __float2half_rn(c0 - __half2float(h0)), l1 = __float2half_rn(c1 - __half2float(h1));
+      ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
+    uint4* dh = reinterpret_cast<uint4*>(out_hi + off);
+    uint4* dl = reinterpret_cast<uint4*>(out_lo + off);
+    dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+    dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
   }
 }
 

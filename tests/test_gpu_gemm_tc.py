@@ -32,12 +32,12 @@ def test_gemm_tc_matches_fp64(M, N, K, act, bn):
     _capi.check(lib, lib.cn_internal_gemm_tc(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cout.data_ptr(), M, N, K, act, bn),
                 "cn_internal_gemm_tc")
     ref = A.double() @ W.double().T + b.double()
+    scale = ref.abs().max().item()                   # magnitude of the accumulated products
     if act == 1:
         ref = ref.clamp_min(0)
     if act == 2:
         ref = torch.tanh(ref)
     err = (Cout.double() - ref).abs().max().item()
-    scale = ref.abs().max().item()
     tol = 3e-6 * max(1.0, scale)
     assert err < tol, (err, scale)
 
