@@ -56,6 +56,7 @@ struct CnEnvSh {
   int done, info, reset_flag;
   int nvis;
   int goal_flag;         // some human is within its radius of its goal (respawn pending)
+  int lean;              // step kernel: gx / gy / rad / vpref point straight into HBM (read-only there)
 };
 
 CN_HD size_t cn_idx(const CnParams& p, int e, int h) { return (size_t)e * p.H + h; }
@@ -84,8 +85,8 @@ CN_HD bool cn_in_fov(double x1, double y1, double vx1, double vy1, double x2, do
 CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h,
                          const float* action /* [N,2] or null (reset) */) {
   const size_t i = cn_idx(p, e, h);
-  s.px[h] = g.hpx[i]; s.py[h] = g.hpy[i]; s.gx[h] = g.hgx[i]; s.gy[h] = g.hgy[i];
-  s.rad[h] = g.hrad[i]; s.vpref[h] = g.hvpref[i];
+  s.px[h] = g.hpx[i]; s.py[h] = g.hpy[i];
+  if (!s.lean) { s.gx[h] = g.hgx[i]; s.gy[h] = g.hgy[i]; s.rad[h] = g.hrad[i]; s.vpref[h] = g.hvpref[i]; }
   s.vx[h] = g.hvx[i]; s.vy[h] = g.hvy[i];
   s.fx[h] = (float)s.px[h]; s.fy[h] = (float)s.py[h];
   if (h == 0) {
@@ -145,9 +146,9 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   const float invTimeHorizon = 1.0f / p.orca_time_horizon;
   const float timeStep = (float)p.time_step;
 
-  // --- neighbour selection: dist^2 < neighborDist^2, ascending, ties in insertion (index) order.
-  // Pass 1 compresses the in-range neighbours; pass 2 ranks them among themselves (O(nv^2) instead
-  // of O(H^2)) and builds each ORCA line directly at its sorted position.
+  // --- neighbour selection: dist^2 < neighborDist^2 kept sorted ascending by insertion with a strict
+  // `<` (ties keep insertion = index order), exactly Agent::insertAgentNeighbor; ORCA lines are then
+  // built directly in sorted order.
   float vd[MAXH];
   uint8_t vj[MAXH];          // bit 7 = dummy (invisible) neighbour, bits 0..6 = human index
   int nl = 0;
@@ -156,19 +157,21 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
     const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
     const CnF2 op = v ? f2(s.fx[j], s.fy[j]) : f2(7.0f, 7.0f);     // dummy_human (crowd_sim.py:130-133)
     const float d = f2abssq(f2sub(pos, op));
-    if (d < rangeSq) { vd[nl] = d; vj[nl] = (uint8_t)(j | (v ? 0 : 0x80)); ++nl; }
+    if (d < rangeSq) {
+      int pos_i = nl;
+      while (pos_i > 0 && d < vd[pos_i - 1]) { vd[pos_i] = vd[pos_i - 1]; vj[pos_i] = vj[pos_i - 1]; --pos_i; }
+      vd[pos_i] = d; vj[pos_i] = (uint8_t)(j | (v ? 0 : 0x80));
+      ++nl;
+    }
   }
   for (int a = 0; a < nl; ++a) {
-    const float da = vd[a];
-    int rank = 0;
-    for (int b = 0; b < nl; ++b) rank += (vd[b] < da || (vd[b] == da && b < a)) ? 1 : 0;
     const int j = vj[a] & 0x7f;
     const bool dummy = (vj[a] & 0x80) != 0;
     const CnF2 op = dummy ? f2(7.0f, 7.0f) : f2(s.fx[j], s.fy[j]);
     const CnF2 ov = dummy ? f2(0.0f, 0.0f) : f2(s.vx[j], s.vy[j]);
     const float orad = p.randomize ? g.sim_rother[i * H + j]
                                    : (float)((dummy ? 0.3 : s.rad[j]) + pad + p.orca_safety_space);
-    lines.set(rank, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
+    lines.set(a, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
   }
   nl_out = nl; vmax_out = vmax; pref_out = pref;
 }
@@ -485,8 +488,8 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
 // Phase STORE: write the working set back to HBM.
 CN_HD void cn_phase_store(const CnParams& p, const CnState& g, const CnEnvSh& s, int e, int h) {
   const size_t i = cn_idx(p, e, h);
-  g.hpx[i] = s.px[h]; g.hpy[i] = s.py[h]; g.hgx[i] = s.gx[h]; g.hgy[i] = s.gy[h];
-  g.hrad[i] = s.rad[h]; g.hvpref[i] = s.vpref[h];
+  g.hpx[i] = s.px[h]; g.hpy[i] = s.py[h];
+  if (!s.lean) { g.hgx[i] = s.gx[h]; g.hgy[i] = s.gy[h]; g.hrad[i] = s.rad[h]; g.hvpref[i] = s.vpref[h]; }
   g.hvx[i] = s.vx[h]; g.hvy[i] = s.vy[h];
   if (h == 0) {
     g.rpx[e] = s.rpx; g.rpy[e] = s.rpy; g.rgx[e] = s.rgx; g.rgy[e] = s.rgy;

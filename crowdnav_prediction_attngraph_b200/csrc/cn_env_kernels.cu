@@ -29,22 +29,31 @@ struct EnvSmemLayout {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-__host__ __device__ inline EnvSmemLayout env_layout(int H) {
+// lean = step kernel: goals / radii / preferred speeds are read-only there and stay in HBM, only what
+// other threads read or what changes lives in shared memory (px, py, t0, t1 + 6 float arrays)
+__host__ __device__ inline EnvSmemLayout env_layout(int H, bool lean) {
   EnvSmemLayout L;
   size_t o = align16(sizeof(CnEnvSh));
-  L.off_dbl = o; o += (size_t)8 * H * sizeof(double);
+  L.off_dbl = o; o += (size_t)(lean ? 4 : 8) * H * sizeof(double);
   L.off_flt = o; o += (size_t)6 * H * sizeof(float);
   L.off_u8 = o; o += (size_t)H;
   L.per_env = align16(o);
   return L;
 }
 
-__device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L, int H) {
+__device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L, int H, bool lean, const CnState& g,
+                                    int e) {
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
   double* d = reinterpret_cast<double*>(base + L.off_dbl);
   float* f = reinterpret_cast<float*>(base + L.off_flt);
-  s->px = d; s->py = d + H; s->gx = d + 2 * H; s->gy = d + 3 * H; s->rad = d + 4 * H; s->vpref = d + 5 * H;
-  s->t0 = d + 6 * H; s->t1 = d + 7 * H;
+  s->px = d; s->py = d + H; s->t0 = d + 2 * H; s->t1 = d + 3 * H;
+  if (lean) {
+    const size_t o = (size_t)e * H;
+    s->gx = g.hgx + o; s->gy = g.hgy + o; s->rad = g.hrad + o; s->vpref = g.hvpref + o;
+  } else {
+    s->gx = d + 4 * H; s->gy = d + 5 * H; s->rad = d + 6 * H; s->vpref = d + 7 * H;
+  }
+  s->lean = lean ? 1 : 0;
   s->vx = f; s->vy = f + H; s->fx = f + 2 * H; s->fy = f + 3 * H; s->nvx = f + 4 * H; s->nvy = f + 5 * H;
   s->visr = base + L.off_u8;
   return s;
@@ -53,7 +62,7 @@ __device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L,
 // One rollout step of every environment (no reset inside: environments that finish are flagged in
 // out.done and re-initialised by cn_env_reset_kernel, launched right behind on the same stream).
 template <int MAXH, int MAXW>
-__global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
+__global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
                                                           CnObs ob, CnStepOut out, int epb, int line_cap) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.H;
@@ -61,11 +70,11 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
   const int h = threadIdx.x - le * H;
   const int e = blockIdx.x * epb + le;
   const bool active = (le < epb) && (e < p.N);
-  const EnvSmemLayout L = env_layout(H);
+  const EnvSmemLayout L = env_layout(H, true);
   CnEnvSh* s = nullptr;
   if (le < epb) {
     s = reinterpret_cast<CnEnvSh*>(smem + (size_t)le * L.per_env);
-    if (h == 0) env_view(smem + (size_t)le * L.per_env, L, H);
+    if (h == 0 && e < p.N) env_view(smem + (size_t)le * L.per_env, L, H, true, g, e);
   }
   __syncthreads();
   // ORCA line storage of this warp: first `line_cap` lines of every thread in shared memory
@@ -82,6 +91,10 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
   CnLineStore proj;
   proj.base = lines_smem + (size_t)line_cap * blockDim.x + (size_t)warp * MAXH;
   proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
+  // CTA-wide linearProgram3 task queue: {count, head, tasks[blockDim]} after the projection scratch
+  unsigned char* lp3_q = reinterpret_cast<unsigned char*>(lines_smem + (size_t)line_cap * blockDim.x +
+                                                          (size_t)(blockDim.x >> 5) * MAXH);
+  if (threadIdx.x == 0) { reinterpret_cast<int*>(lp3_q)[0] = 0; reinterpret_cast<int*>(lp3_q)[1] = 0; }
   const CnCoop co = {lane, 32};
 
   if (active) cn_phase_load(p, g, *s, e, h, action);
@@ -92,7 +105,39 @@ __global__ void __launch_bounds__(256) cn_env_step_kernel(CnParams p, CnState g,
     CnF2 pref = f2(0.0f, 0.0f), result = f2(0.0f, 0.0f);
     if (active) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref);
     __syncwarp();
-    cn_orca_solve_coop(co, W, nl, vmax, pref, proj, result, fail);    // all 32 lanes, idle ones with nl = 0
+    cn_orca_lp2_warp(co, W, nl, vmax, pref, result, fail);            // all 32 lanes, idle ones with nl = 0
+    // linearProgram3 (needed by ~30 % of the humans in steady state) is balanced across the whole
+    // CTA: failed humans are queued in shared memory and every warp pops tasks until the queue is dry.
+    int* lp3_count = reinterpret_cast<int*>(lp3_q);
+    int* lp3_head = lp3_count + 1;
+    unsigned short* lp3_tasks = reinterpret_cast<unsigned short*>(lp3_count + 2);
+    if (fail >= 0) {
+      s->nvx[h] = result.x; s->nvy[h] = result.y;                     // LP2 result at the failure point
+      reinterpret_cast<int*>(&s->t0[h])[0] = nl | (fail << 8);        // t0 is free until cn_orca_finish
+      reinterpret_cast<float*>(&s->t0[h])[1] = vmax;
+      lp3_tasks[atomicAdd(lp3_count, 1)] = (unsigned short)threadIdx.x;
+    }
+    __syncthreads();
+    const int ntask = *lp3_count;
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(lp3_head, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= ntask) break;
+      const int owner = lp3_tasks[t];
+      const int ole = owner / H, oh = owner - ole * H;
+      CnEnvSh* os = reinterpret_cast<CnEnvSh*>(smem + (size_t)ole * L.per_env);
+      const int packed = reinterpret_cast<const int*>(&os->t0[oh])[0];
+      const float ovmax = reinterpret_cast<const float*>(&os->t0[oh])[1];
+      CnF2 ores = f2(os->nvx[oh], os->nvy[oh]);
+      CnLineStore ol;
+      ol.base = lines_smem + owner; ol.stride = blockDim.x; ol.cap = line_cap;
+      ol.ovf = reinterpret_cast<float4*>(g.line_ovf) + ((size_t)blockIdx.x * blockDim.x + owner) * g.ovf_stride;
+      cn_lp3_coop(co, ol, packed & 0xff, packed >> 8, ovmax, ores, proj);
+      if (lane == 0) { os->nvx[oh] = ores.x; os->nvy[oh] = ores.y; }
+    }
+    __syncthreads();
+    if (fail >= 0) result = f2(s->nvx[h], s->nvy[h]);
     if (active) cn_orca_finish(p, g, *s, e, h, result, nl, fail);
   }
   __syncthreads();
@@ -129,10 +174,10 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
   const int evt = force ? 2 : g.evt[e];
   if (evt == 0) return;
   const int H = p.H;
-  const EnvSmemLayout L = env_layout(H);
+  const EnvSmemLayout L = env_layout(H, false);
   unsigned char* base = smem + (size_t)warp * per_warp_bytes;
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
-  if (lane == 0) env_view(base, L, H);
+  if (lane == 0) env_view(base, L, H, false, g, e);
   __syncwarp();
   uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
   float* rows = reinterpret_cast<float*>(base + L.per_env + 624 * sizeof(uint32_t));
@@ -332,38 +377,45 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   env->d_out.not_done = nullptr;
   if (rc) { cn_env_destroy(env); return rc; }
 
-  // launch geometry: EPB whole environments per CTA (<= 256 threads).  The first `line_cap` ORCA
-  // lines of every thread live in shared memory; the cap is lowered until the whole launch is
+  // launch geometry: EPB whole environments per CTA (<= 288 threads); the first `line_cap` ORCA lines
+  // of every thread live in shared memory.  Search (epb, cap) for the largest cap whose launch is
   // resident in ONE wave (shared memory is the occupancy limiter; a 1.16-wave launch costs 2x).
   env->maxh = p.H <= 32 ? 32 : (p.H <= 64 ? 64 : 128);
-  const EnvSmemLayout L = env_layout(p.H);
-  int epb = 256 / p.H;
-  if (epb < 1) epb = 1;
-  env->epb = epb;
-  env->threads = ((epb * p.H + 31) / 32) * 32;
-  if (env->threads > 256) { cn_env_destroy(env); return cn_set_error("internal: %d threads", env->threads); }
+  const EnvSmemLayout L = env_layout(p.H, true);
   int nsm = 0;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
-  const int grid = (p.N + epb - 1) / epb;
   KernelFn fn = pick_kernel(env->maxh);
-  int cap = p.H > 1 ? p.H - 1 : 1;
-  for (;;) {
-    const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * env->threads * sizeof(float4) +
-                        (size_t)(env->threads / 32) * env->maxh * sizeof(float4);   // + per-warp LP3 scratch
-    bool ok = need <= 227 * 1024;
-    if (ok) {
-      err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-      int per_sm = 0;
-      if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, env->threads, need);
-      if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("occupancy query: %s", cudaGetErrorString(err)); }
-      ok = (long long)per_sm * nsm >= grid || cap <= 4;
-    }
-    if (ok) { env->smem_bytes = need; env->line_cap = cap; break; }
-    if (cap <= 1) { cn_env_destroy(env); return cn_set_error("cn_env_create: human_num %d does not fit shared memory", p.H); }
-    --cap;
-  }
-  err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+  err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(err)); }
+  const int cap_max = p.H > 1 ? p.H - 1 : 1;
+  int best_epb = 0, best_cap = 0, best_threads = 0;
+  size_t best_need = 0;
+  bool best_single = false;
+  for (int epb = 288 / p.H > 0 ? 288 / p.H : 1; epb >= 1; --epb) {
+    const int threads = ((epb * p.H + 31) / 32) * 32;
+    if (threads > 288) continue;
+    const int grid_try = (p.N + epb - 1) / epb;
+    for (int cap = cap_max; cap >= 1; --cap) {
+      const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * threads * sizeof(float4) +
+                          (size_t)(threads / 32) * env->maxh * sizeof(float4) +   // + per-warp LP3 scratch
+                          align16(8 + 2 * (size_t)threads);                       // + CTA LP3 task queue
+      if (need > 227 * 1024) continue;
+      int per_sm = 0;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, need);
+      if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("occupancy query: %s", cudaGetErrorString(err)); }
+      const bool single = (long long)per_sm * nsm >= grid_try;
+      // preference: single wave first, then larger cap, then larger epb (fewer CTAs)
+      const bool better = !best_epb || (single && !best_single) ||
+                          (single == best_single && (cap > best_cap || (cap == best_cap && epb > best_epb)));
+      if (better && (single || !best_single)) {
+        best_epb = epb; best_cap = cap; best_threads = threads; best_need = need; best_single = single;
+      }
+      if (single) break;          // smaller caps of this epb cannot be better
+    }
+  }
+  if (!best_epb) { cn_env_destroy(env); return cn_set_error("cn_env_create: human_num %d does not fit shared memory", p.H); }
+  env->epb = best_epb; env->threads = best_threads; env->line_cap = best_cap; env->smem_bytes = best_need;
+  const int grid = (p.N + env->epb - 1) / env->epb;
   {
     // global scratch for the overflow lines (k >= line_cap) of every step-kernel thread
     float4* ovf = nullptr;
@@ -373,7 +425,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     env->g.line_ovf = ovf;
   }
   // reset kernel: per-warp working set + MT19937 state + observation rows
-  env->reset_warp_bytes = align16(L.per_env + 624 * sizeof(uint32_t) + (size_t)p.H * 16 * sizeof(float));
+  env->reset_warp_bytes = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t) + (size_t)p.H * 16 * sizeof(float));
   err = cudaFuncSetAttribute(cn_env_event_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(CN_EVENT_WARPS * env->reset_warp_bytes));
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }

@@ -121,35 +121,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 }  // namespace tc
 
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, blockIdx.x + grid, ...
+// (n fastest, so CTAs running at the same time share A rows in L2).  The row count may live on the
+// device (ep.m_ptr, compacted human rows): no CTA is ever launched for an empty tile.  Two TMEM
+// accumulators (2 x BN columns) let the epilogue of tile i overlap the mainloop of tile i + 1.
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                   const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, int M, int N,
                   int K, TcEpilogue ep) {
   if (ep.m_ptr) { const int mc = *ep.m_ptr; M = mc < M ? mc : M; }
-  if ((int)(blockIdx.y * TC_BM) >= M) return;       // uniform for the whole CTA: before any barrier / TMEM use
+  const int n_ntiles = N / BN;
+  const int n_tiles = ((M + TC_BM - 1) / TC_BM) * n_ntiles;
+  if ((int)blockIdx.x >= n_tiles) return;           // uniform for the whole CTA: before any barrier / TMEM use
   constexpr int TC_STAGES = TcCfg<BN>::kStages;
   constexpr int TC_B_TILE_BYTES = TcCfg<BN>::kBTile;
   constexpr int TC_STAGE_BYTES = TcCfg<BN>::kStageBytes;
   constexpr int TC_BN = BN;
+  constexpr uint32_t TMEM_COLS = 2 * TcCfg<BN>::kTmemCols;       // two accumulators
   extern __shared__ uint8_t tc_smem_raw[];
   const uint32_t raw = tc::smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* base_ptr = tc_smem_raw + (base - raw);
   const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;  // barriers after the operand ring
-  // full[s] = bar_base + 8 s ; empty[s] = bar_base + 32 + 8 s ; tmem_full = bar_base + 64 ; tmem ptr at +72
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 72);
+  // full[s] = +8 s ; empty[s] = +32 + 8 s ; tmem_full[b] = +64 + 8 b ; tmem_empty[b] = +80 + 8 b ; tmem ptr at +96
+  const uint32_t bar_full = bar_base, bar_empty = bar_base + 32, bar_tfull = bar_base + 64, bar_tempty = bar_base + 80;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int num_kb = K / TC_BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      tc::mbar_init(bar_base + 8 * s, 1);         // full: producer's arrive.expect_tx
-      tc::mbar_init(bar_base + 32 + 8 * s, 1);    // empty: one tcgen05.commit
+      tc::mbar_init(bar_full + 8 * s, 1);         // producer's arrive.expect_tx
+      tc::mbar_init(bar_empty + 8 * s, 1);        // one tcgen05.commit
     }
-    tc::mbar_init(bar_base + 64, 1);              // accumulator ready
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(bar_tfull + 8 * b, 1);        // accumulator b complete (tcgen05.commit)
+      tc::mbar_init(bar_tempty + 8 * b, 4);       // accumulator b drained (one arrive per epilogue warp)
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
@@ -157,113 +167,131 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
   }
   if (warp == 1) {
-    // allocate 256 TMEM columns (power of two >= 32); the same warp frees them at the end
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)TcCfg<BN>::kTmemCols) : "memory");
+                 "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
-  const uint32_t tmem_acc = *tmem_ptr_smem;
+  const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        tc::mbar_wait(bar_base + 32 + 8 * s, ph ^ 1u);            // slot free (first pass returns immediately)
-        const uint32_t full = bar_base + 8 * s;
-        tc::mbar_expect_tx(full, TC_STAGE_BYTES);
-        const uint32_t st = base + s * TC_STAGE_BYTES;
-        tc::tma_load_2d(st, &map_ahi, full, kb * TC_BK, m0);
-        tc::tma_load_2d(st + TC_A_TILE_BYTES, &map_alo, full, kb * TC_BK, m0);
-        tc::tma_load_2d(st + 2 * TC_A_TILE_BYTES, &map_bhi, full, kb * TC_BK, n0);
-        tc::tma_load_2d(st + 2 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &map_blo, full, kb * TC_BK, n0);
+      uint32_t it = 0;                                            // running k-block counter across tiles
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+          tc::mbar_wait(bar_empty + 8 * s, ph ^ 1u);              // slot free (first pass returns immediately)
+          const uint32_t full = bar_full + 8 * s;
+          tc::mbar_expect_tx(full, TC_STAGE_BYTES);
+          const uint32_t st = base + s * TC_STAGE_BYTES;
+          tc::tma_load_2d(st, &map_ahi, full, kb * TC_BK, m0);
+          tc::tma_load_2d(st + TC_A_TILE_BYTES, &map_alo, full, kb * TC_BK, m0);
+          tc::tma_load_2d(st + 2 * TC_A_TILE_BYTES, &map_bhi, full, kb * TC_BK, n0);
+          tc::tma_load_2d(st + 2 * TC_A_TILE_BYTES + TC_B_TILE_BYTES, &map_blo, full, kb * TC_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        tc::mbar_wait(bar_base + 8 * s, ph);                      // TMA bytes landed
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
+        tc::mbar_wait(bar_tempty + 8 * ab, aph ^ 1u);             // epilogue drained this accumulator
         tc::tcgen05_fence_after();
-        const uint32_t st = base + s * TC_STAGE_BYTES;
-        const uint32_t a_hi = st, a_lo = st + TC_A_TILE_BYTES, b_hi = st + 2 * TC_A_TILE_BYTES,
-                       b_lo = st + 2 * TC_A_TILE_BYTES + TC_B_TILE_BYTES;
+        const uint32_t tmem_acc = tmem_base + ab * TcCfg<BN>::kTmemCols;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
+          tc::mbar_wait(bar_full + 8 * s, ph);                    // TMA bytes landed
+          tc::tcgen05_fence_after();
+          const uint32_t st = base + s * TC_STAGE_BYTES;
+          const uint32_t a_hi = st, a_lo = st + TC_A_TILE_BYTES, b_hi = st + 2 * TC_A_TILE_BYTES,
+                         b_lo = st + 2 * TC_A_TILE_BYTES + TC_B_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint32_t koff = k * 32;                           // 16 fp16 = 32 bytes inside the swizzle atom
-          const uint64_t dah = tc::make_desc(a_hi + koff), dal = tc::make_desc(a_lo + koff);
-          const uint64_t dbh = tc::make_desc(b_hi + koff), dbl = tc::make_desc(b_lo + koff);
-          tc::mma_f16(tmem_acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc::mma_f16(tmem_acc, dah, dbl, idesc, 1u);
-          tc::mma_f16(tmem_acc, dal, dbh, idesc, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint32_t koff = k * 32;                         // 16 fp16 = 32 bytes inside the swizzle atom
+            const uint64_t dah = tc::make_desc(a_hi + koff), dal = tc::make_desc(a_lo + koff);
+            const uint64_t dbh = tc::make_desc(b_hi + koff), dbl = tc::make_desc(b_lo + koff);
+            tc::mma_f16(tmem_acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::mma_f16(tmem_acc, dah, dbl, idesc, 1u);
+            tc::mma_f16(tmem_acc, dal, dbh, idesc, 1u);
+          }
+          tc::mma_commit(bar_empty + 8 * s);                      // frees the smem slot when the MMAs retire
         }
-        tc::mma_commit(bar_base + 32 + 8 * s);                    // frees the smem slot when the MMAs retire
+        tc::mma_commit(bar_tfull + 8 * ab);                       // accumulator complete
       }
-      tc::mma_commit(bar_base + 64);                              // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                       // TMEM lane quadrant this warp may access
-    tc::mbar_wait(bar_base + 64, 0);
-    tc::tcgen05_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
+      const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
+      tc::mbar_wait(bar_tfull + 8 * ab, aph);
+      tc::tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + ab * TcCfg<BN>::kTmemCols;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
 #pragma unroll 1
-    for (int c = 0; c < TC_BN / 32; ++c) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      const int nb = n0 + c * 32;
-      float v[32];
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        const int nb = n0 + c * 32;
+        float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * ep.inv_scale;
-        if (ep.bias) x += __ldg(ep.bias + nb + j);
-        if (nb + j >= ep.act_lo && nb + j < ep.act_hi) {
-          if (ep.act == 1) x = x > 0.0f ? x : 0.0f;
-          else if (ep.act == 2) x = tc::fast_tanh(x);
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]) * ep.inv_scale;
+          if (ep.bias) x += __ldg(ep.bias + nb + j);
+          if (nb + j >= ep.act_lo && nb + j < ep.act_hi) {
+            if (ep.act == 1) x = x > 0.0f ? x : 0.0f;
+            else if (ep.act == 2) x = tc::fast_tanh(x);
+          }
+          v[j] = x;
         }
-        v[j] = x;
-      }
-      if (row_ok) {
-        if (ep.c32) {
-          float4* dst = reinterpret_cast<float4*>(ep.c32 + (size_t)row * ep.ldc + nb);
+        if (row_ok) {
+          if (ep.c32) {
+            float4* dst = reinterpret_cast<float4*>(ep.c32 + (size_t)row * ep.ldc + nb);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (ep.out_hi) {
-          uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + (size_t)row * ep.ldh + nb);
-          uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + (size_t)row * ep.ldh + nb);
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (ep.out_hi) {
+            uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + (size_t)row * ep.ldh + nb);
+            uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + (size_t)row * ep.ldh + nb);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t ph[4], pl[4];
+            for (int j = 0; j < 4; ++j) {
+              uint32_t ph[4], pl[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float x0 = fminf(fmaxf(v[8 * j + 2 * t], -65504.0f), 65504.0f);
-              const float x1 = fminf(fmaxf(v[8 * j + 2 * t + 1], -65504.0f), 65504.0f);
-              const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-              const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-              ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-              pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              for (int t = 0; t < 4; ++t) {
+                const float x0 = fminf(fmaxf(v[8 * j + 2 * t], -65504.0f), 65504.0f);
+                const float x1 = fminf(fmaxf(v[8 * j + 2 * t + 1], -65504.0f), 65504.0f);
+                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+                ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              }
+              dh[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              dl[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
-            dh[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            dl[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
           }
         }
       }
+      // this warp is done reading the accumulator: hand it back to the MMA issuer
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8 * ab) : "memory");
     }
   }
   tc::tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc::tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)TcCfg<BN>::kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 

@@ -342,10 +342,11 @@ struct CnWarpLines {
   }
 };
 
-// Solve the LPs of all lanes of a warp.  In: per-lane line count / max speed / preferred velocity
-// (nl = 0 for idle lanes).  Out: per-lane new velocity and LP2 failure index (-1 = LP2 succeeded).
-CN_HD void cn_orca_solve_coop(const CnCoop& co, const CnWarpLines& W, int nl, float vmax, CnF2 pref, CnLineStore proj,
-                              CnF2& result, int& fail) {
+// linearProgram2 of all lanes of a warp (cooperative linearProgram1 servicing).  In: per-lane line
+// count / max speed / preferred velocity (nl = 0 for idle lanes).  Out: per-lane velocity and LP2
+// failure index (-1 = LP2 succeeded; otherwise linearProgram3 must follow from that line).
+CN_HD void cn_orca_lp2_warp(const CnCoop& co, const CnWarpLines& W, int nl, float vmax, CnF2 pref, CnF2& result,
+                            int& fail) {
   const CnLineStore mine = W.of(co.lane);
   // linearProgram2 initialisation (closest point, not direction)
   if (f2abssq(pref) > vmax * vmax) result = f2scale(vmax, f2normalize(pref));
@@ -379,7 +380,12 @@ CN_HD void cn_orca_solve_coop(const CnCoop& co, const CnWarpLines& W, int nl, fl
       }
     }
   }
-  // linearProgram3 for the lanes whose LP2 failed, one owner at a time
+}
+
+// linearProgram3 for the lanes whose LP2 failed, serviced within the warp one owner at a time
+// (CPU harness / fallback; the step kernel balances these tasks across the whole CTA instead).
+CN_HD void cn_orca_lp3_warp(const CnCoop& co, const CnWarpLines& W, int nl, float vmax, CnLineStore proj, CnF2& result,
+                            int fail) {
   uint32_t req = cn_ballot(co, fail >= 0);
   while (req) {
     const int L = cn_ffs(req);

@@ -34,6 +34,7 @@ struct cn_policy {
   int N, H, Win, M;
   int64_t launches;
   int attn_hpc;        // heads per CTA of the HH attention kernel
+  int num_sms;
   bool finalized;
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> allocs;
@@ -155,7 +156,9 @@ void gemm_tc(cn_policy* p, cudaStream_t st, const TcMat& A, const TcMat& B, int 
   TcEpilogue ep;
   ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.act_lo = act_lo; ep.act_hi = act_hi;
   ep.c32 = o.c32; ep.ldc = o.ldc; ep.out_hi = o.oh; ep.out_lo = o.ol; ep.ldh = o.ldh; ep.m_ptr = m_ptr;
-  dim3 grid(N / bn, (M + TC_BM - 1) / TC_BM);
+  // persistent: one CTA per SM at most; tiles beyond the device-side row count are never touched
+  const int tiles = (N / bn) * ((M + TC_BM - 1) / TC_BM);
+  dim3 grid(tiles < p->num_sms ? tiles : p->num_sms);
   if (bn == 256)
     cn_gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, M, N, K, ep);
   else
@@ -234,6 +237,8 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   p->cfg = *cfg;
   p->N = cfg->num_envs; p->H = cfg->human_num; p->Win = cfg->input_size; p->M = p->N * p->H;
   p->launches = 0; p->finalized = false; p->profile = false;
+  p->num_sms = 148;
+  cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   const size_t M = (size_t)p->M, N = (size_t)p->N;
   const int Mi = p->M, Ni = p->N;
   int rc = 0;
@@ -451,7 +456,7 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
   mark(p, st, 4);
   {
-    cn_hh_attention_kernel<<<(M + 7) / 8, 256, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, tcm ? nullptr : p->ao,
+    cn_hh_attention_kernel<<<p->num_sms * 8, 256, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, tcm ? nullptr : p->ao,
                                                         tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
     p->launches += 1;
   }
@@ -529,6 +534,8 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
     return cn_set_error("cn_internal_gemm_tc: need bn in {64,256}, N %% bn == 0 and K %% 64 == 0");
   cn_policy tmp;
   tmp.launches = 0;
+  tmp.num_sms = 148;
+  cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, 0);
   TcMat A, B;
   int rc = tc_alloc(&tmp, A, M, K, TC_BM);
   if (!rc) rc = tc_alloc(&tmp, B, N, K, bn);

@@ -248,8 +248,10 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
   // and soft-max is computed online (running max / sum) so nothing is staged: K and V rows are
   // read straight from global memory with fully coalesced 2 KB warp loads.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (r >= *mc_ptr) return;
+  const int mc = *mc_ptr;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  // grid-stride over the compacted rows: the launch is sized to the machine, not to the worst case
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < mc; r += nwarps) {
   const int e = row_env[r];
   const size_t row0 = (size_t)row_start[e];
   const int n = row_start[e + 1] - row_start[e];
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
     dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
     dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
   }
+  }   // row loop
 }
 
 // ------------------------------------------------------------------------------------------

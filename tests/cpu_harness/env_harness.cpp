@@ -48,6 +48,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     s.t0 = s.vpref + H; s.t1 = s.t0 + H;
     s.vx = f.data(); s.vy = s.vx + H; s.fx = s.vy + H; s.fy = s.fx + H; s.nvx = s.fy + H; s.nvy = s.nvx + H;
     s.visr = u.data();
+    s.lean = 0;
     const CnCoop co = {0, 1};
     if (mode == 1) {
       s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
@@ -61,7 +62,8 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
         CnLineStore proj; proj.base = projbuf.data(); proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
         int nl = 0, fail = -1; float vmax = 0; CnF2 pref = f2(0, 0), result = f2(0, 0);
         cn_orca_build<MAXH>(p, g, s, e, h, W.of(0), nl, vmax, pref);
-        cn_orca_solve_coop(co, W, nl, vmax, pref, proj, result, fail);
+        cn_orca_lp2_warp(co, W, nl, vmax, pref, result, fail);
+        cn_orca_lp3_warp(co, W, nl, vmax, proj, result, fail);
         cn_orca_finish(p, g, s, e, h, result, nl, fail);
       }
       cn_phase_reward(p, g, s, e, out);
