@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("CN_GEMM_MODE", "0")))
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("CN_GEMM_MODE", "1")),
+                    help="1 = tcgen05 3xFP16 GEMMs (default), 0 = fp32 CUDA-core GEMMs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -76,6 +76,7 @@ struct CnState {
   // per-step event flags written by the step kernel, consumed by the event kernel:
   // 0 = nothing, 1 = goal dynamics (respawn / goal change) pending, 2 = episode finished (reset)
   uint8_t *evt;                      // [N]
+  uint8_t *spawn_overflow;           // [N] set when a rejection-sampling loop hit CN_MAX_SPAWN_TRIES
   // overflow ORCA lines (k >= line_cap) of every step-kernel thread: [grid * block][ovf_stride] float4
   void *line_ovf;
   int ovf_stride;

@@ -26,6 +26,7 @@
 #include "cn_orca.cuh"
 
 #define CN_PI 3.141592653589793
+#define CN_MAX_SPAWN_TRIES 20000
 
 CN_HD double cn_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
@@ -273,7 +274,10 @@ CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, cons
                                        CnRng& rng, const CnCoop& co, int n_present) {
   CnSpawn sp;
   cn_new_human_attrs(p, g, e, rng, co, sp.vpref, sp.rad);
-  for (;;) {
+  // The reference loops until a free spot is found and never terminates when the circle is full
+  // (it cannot place more than ~76 humans of radius 0.3-0.5); a kernel must not hang the GPU, so after
+  // CN_MAX_SPAWN_TRIES rejected candidates the last one is accepted and the environment is flagged.
+  for (int tries = 0;; ++tries) {
     const double angle = cn_rng_double(rng, co) * CN_PI * 2;
     const double px_noise = cn_rng_uniform(rng, co, 0, 1) * 2;
     const double py_noise = cn_rng_uniform(rng, co, 0, 1) * 2;
@@ -289,7 +293,11 @@ CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, cons
         collide = true; break;
       }
     }
-    if (!cn_any(co, collide)) { sp.px = px; sp.py = py; break; }
+    if (!cn_any(co, collide) || tries >= CN_MAX_SPAWN_TRIES) {
+      sp.px = px; sp.py = py;
+      if (tries >= CN_MAX_SPAWN_TRIES && co.lane == 0) g.spawn_overflow[e] = 1;
+      break;
+    }
   }
   return sp;
 }
@@ -442,7 +450,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
       if (s.vpref[i] == 0) continue;
       if (cn_rng_double(rng, co) <= p.goal_change_chance) {
         double gx, gy;
-        for (;;) {
+        for (int tries = 0;; ++tries) {
           const double angle = cn_rng_double(rng, co) * CN_PI * 2;
           const double vp = (s.vpref[i] == 0) ? 1.0 : s.vpref[i];
           const double gx_noise = (cn_rng_double(rng, co) - 0.5) * vp;
@@ -461,6 +469,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
             }
           }
           if (!cn_any(co, collide)) break;
+          if (tries >= CN_MAX_SPAWN_TRIES) { if (co.lane == 0) g.spawn_overflow[e] = 1; break; }
         }
         cn_coop_sync(co);
         if (co.lane == 0) { s.gx[i] = gx; s.gy[i] = gy; }

@@ -89,7 +89,7 @@ def make_reference_like_state_dict(input_size=12, seed=0):
 class CudaPolicy(object):
     """Thin handle on cn_policy: upload a reference state_dict, run the rollout forward."""
 
-    def __init__(self, num_envs, human_num, input_size=12, device="cuda:0", gemm_mode=0):
+    def __init__(self, num_envs, human_num, input_size=12, device="cuda:0", gemm_mode=1):
         self.lib = _capi.load_library()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -196,7 +196,7 @@ class Policy(nn.Module):
     def _engine(self, N, device):
         if self._cuda is None or self._cuda.N != N or self._cuda.device != device:
             self._cuda = CudaPolicy(N, self.human_num, self.input_size, device=device,
-                                    gemm_mode=int(os.environ.get("CN_GEMM_MODE", "0")))
+                                    gemm_mode=int(os.environ.get("CN_GEMM_MODE", "1")))
             self._cuda_version = -1
         ver = sum(int(p._version) for p in self.parameters())
         if ver != self._cuda_version:                       # parameters changed (optimizer step / load_state_dict)

@@ -112,7 +112,7 @@ void* harness_create(const cn_config* cfg) {
   A(bpx, NH); A(bpy, NH); A(bvx, NH); A(bvy, NH); A(brad, NH); A(vis, NH);
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH); A(sim_rother, NH * p.H);
   A(mt, N * 624); A(mt_pos, N);
-  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
 #undef A
   for (size_t e = 0; e < N; ++e) g.nd_global[e] = cfg->orca_neighbor_dist;
   return hn;

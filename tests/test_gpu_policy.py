@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
-def _cuda_policy(N, H, sd, gemm_mode=0):
+def _cuda_policy(N, H, sd, gemm_mode=0):   # fp32 CUDA-core path here; tensor-core path in test_gpu_gemm_tc.py
     from crowdnav_prediction_attngraph_b200.policy import CudaPolicy
     pol = CudaPolicy(N, H, 12, device="cuda:0", gemm_mode=gemm_mode)
     pol.load_state_dict(sd)
