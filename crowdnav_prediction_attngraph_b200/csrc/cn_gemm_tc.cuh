@@ -32,7 +32,7 @@ struct TcCfg {
   static constexpr int kStages = (BN >= 256) ? 2 : 4;
   static constexpr int kBTile = BN * TC_BK * 2;
   static constexpr int kStageBytes = 2 * TC_A_TILE_BYTES + 2 * kBTile;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -238,21 +238,38 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       const uint32_t tmem_acc = tmem_base + ab * TcCfg<BN>::kTmemCols;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
+      // stage this tile's bias slice in shared memory once (epilogue warps only: named barrier 1)
+      float* bias_s = reinterpret_cast<float*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 256);
+      {
+        const int et = threadIdx.x - 64;                          // 0..127 within the epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");            // previous tile's readers are done
+        for (int c = et; c < TC_BN; c += 128) bias_s[c] = ep.bias ? __ldg(ep.bias + n0 + c) : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      // activation is uniform over the tile unless the [act_lo, act_hi) window cuts through it
+      const bool act_full = ep.act_lo <= n0 && ep.act_hi >= n0 + TC_BN;
+      const bool act_none = ep.act == 0 || ep.act_hi <= n0 || ep.act_lo >= n0 + TC_BN;
+      const int act_mode = act_none ? 0 : (act_full ? ep.act : 3);
 #pragma unroll 1
       for (int c = 0; c < TC_BN / 32; ++c) {
         uint32_t r[32];
         tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         const int nb = n0 + c * 32;
+        const float* bs = bias_s + c * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) * ep.inv_scale;
-          if (ep.bias) x += __ldg(ep.bias + nb + j);
-          if (nb + j >= ep.act_lo && nb + j < ep.act_hi) {
-            if (ep.act == 1) x = x > 0.0f ? x : 0.0f;
-            else if (ep.act == 2) x = tc::fast_tanh(x);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), ep.inv_scale, bs[j]);
+        if (act_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (act_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tc::fast_tanh(v[j]);
+        } else if (act_mode == 3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nb + j >= ep.act_lo && nb + j < ep.act_hi) v[j] = (ep.act == 1) ? fmaxf(v[j], 0.0f) : tc::fast_tanh(v[j]);
           }
-          v[j] = x;
         }
         if (row_ok) {
           if (ep.c32) {

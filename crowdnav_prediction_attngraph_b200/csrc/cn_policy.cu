@@ -48,6 +48,10 @@ struct cn_policy {
   // tcgen05 path: split activations (A operands)
   TcMat tE1, tE2, tAo;                                  // per human rows
   TcMat tRs, tT1, tTe, tWv, tH0, tH1, tOut, tAc1, tA1, tC1;   // per environment rows (tTe / tA1 / tC1 = column views)
+  // second stream: the robot branch / gh / critic.2 are independent of the per-human chain and run
+  // concurrently with it (fork / join with events; capturable in a CUDA graph)
+  cudaStream_t st2;
+  cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
   // optional per-stage profiling
   bool profile;
   std::vector<cudaEvent_t> ev;
@@ -187,7 +191,7 @@ void gemm(cn_policy* p, cudaStream_t st, const float* A, int lda, const float* W
 }
 
 const char* kStageNames[] = {"pack_inputs", "embed1_gemm", "embed2_gemm", "qkv_gemm", "hh_attention",
-                             "outproj_spatial_gemm", "robot_branch", "hr_attention", "gru", "actor_critic_heads"};
+                             "outproj_spatial_gemm", "robot_branch_join", "hr_attention", "gru", "actor_critic_heads"};
 const int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
 inline void mark(cn_policy* p, cudaStream_t st, int i) {
@@ -239,6 +243,11 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   p->launches = 0; p->finalized = false; p->profile = false;
   p->num_sms = 148;
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming);
   const size_t M = (size_t)p->M, N = (size_t)p->N;
   const int Mi = p->M, Ni = p->N;
   int rc = 0;
@@ -285,6 +294,10 @@ int cn_policy_destroy(cn_policy* p) {
   cudaSetDevice(p->cfg.device);
   for (void* q : p->allocs) cudaFree(q);
   for (auto& e : p->ev) cudaEventDestroy(e);
+  if (p->st2) {
+    cudaStreamDestroy(p->st2);
+    cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); cudaEventDestroy(p->ev_fork2); cudaEventDestroy(p->ev_join2);
+  }
   delete p;
   return 0;
 }
@@ -444,6 +457,22 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
                                                                p->h0, tcm ? p->tH0.hi : nullptr, tcm ? p->tH0.lo : nullptr);
     p->launches += 2;
   }
+  // fork: the robot branch (rs, [enc|te], u) and gh only depend on the packed inputs
+  cudaStream_t s2 = p->st2;
+  cudaEventRecord(p->ev_fork, st);
+  cudaStreamWaitEvent(s2, p->ev_fork, 0);
+  if (tcm) {
+    gemm(p, s2, p->xr, 16, p->Wr, 16, p->br, nullptr, 256, N, 256, 16, CN_ACT_RELU, 0, ALL, nullptr, p->tRs.hi, p->tRs.lo);
+    gemm_tc(p, s2, p->tRs, p->tWet, N, 128, 256, 64, p->bet, CN_ACT_RELU, out_both(p->t1, 128, p->tT1), nullptr, 0, 64);
+    gemm_tc(p, s2, p->tTe, p->tWsT, N, 256, 64, 64, nullptr, CN_ACT_NONE, out32(p->u, 256));
+    gemm_tc(p, s2, p->tH0, p->tWhh, N, 384, 128, 64, p->bhh, CN_ACT_NONE, out32(p->gh, 384));
+  } else {
+    gemm(p, s2, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
+    gemm(p, s2, p->rs, 256, p->Wet, 256, p->bet, p->t1, 128, N, 128, 256, CN_ACT_RELU, 0, 64);   // [enc | te]
+    gemm(p, s2, p->t1 + 64, 128, p->WsT, 64, nullptr, p->u, 256, N, 256, 64, CN_ACT_NONE);        // u = W_s^T te
+    gemm(p, s2, p->h0, 128, p->Whh, 128, p->bhh, p->gh, 384, N, 384, 128, CN_ACT_NONE);
+  }
+  cudaEventRecord(p->ev_join, s2);
   // 1. human-human branch over the Mc = sum_e n_e valid rows (device-side count p->mc)
   mark(p, st, 1);
   if (tcm) gemm(p, st, p->x16, 16, p->W1, 16, p->b1, nullptr, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc, p->tE1.hi, p->tE1.lo);
@@ -457,55 +486,52 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   mark(p, st, 4);
   {
     cn_hh_attention_kernel<<<p->num_sms * 8, 256, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, tcm ? nullptr : p->ao,
-                                                        tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
+                                                           tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
     p->launches += 1;
   }
   mark(p, st, 5);
   if (tcm) gemm_tc(p, st, p->tAo, p->tWos, M, 256, 512, 256, p->bos, CN_ACT_RELU, out32(p->sout, 256), mc);
   else gemm(p, st, p->ao, 512, p->Wos, 512, p->bos, p->sout, 256, M, 256, 512, CN_ACT_RELU, 0, ALL, mc);
-  // 2. robot branch:  rs = ReLU(W_r [te, rn]);  t1 = [ReLU(enc) | te];  u = W_s^T te
+  // 2. join the robot branch
   mark(p, st, 6);
-  if (tcm) {
-    gemm(p, st, p->xr, 16, p->Wr, 16, p->br, nullptr, 256, N, 256, 16, CN_ACT_RELU, 0, ALL, nullptr, p->tRs.hi, p->tRs.lo);
-    gemm_tc(p, st, p->tRs, p->tWet, N, 128, 256, 64, p->bet, CN_ACT_RELU, out_both(p->t1, 128, p->tT1), nullptr, 0, 64);
-    gemm_tc(p, st, p->tTe, p->tWsT, N, 256, 64, 64, nullptr, CN_ACT_NONE, out32(p->u, 256));
-  } else {
-    gemm(p, st, p->xr, 16, p->Wr, 16, p->br, p->rs, 256, N, 256, 16, CN_ACT_RELU);
-    gemm(p, st, p->rs, 256, p->Wet, 256, p->bet, p->t1, 128, N, 128, 256, CN_ACT_RELU, 0, 64);   // [enc | te]
-    gemm(p, st, p->t1 + 64, 128, p->WsT, 64, nullptr, p->u, 256, N, 256, 64, CN_ACT_NONE);        // u = W_s^T te
-  }
+  cudaStreamWaitEvent(st, p->ev_join, 0);
   mark(p, st, 7);
   cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, p->row_start, N, H, p->wv,
                                                       tcm ? p->tWv.hi : nullptr, tcm ? p->tWv.lo : nullptr);
   p->launches += 1;
-  // 3. GRU: emb overwrites the te half of t1 -> t1 = [enc | emb] = GRU input
+  // 3. GRU: emb overwrites the te half of t1 -> t1 = [enc | emb] = GRU input (gh came from the side stream)
   mark(p, st, 8);
   if (tcm) {
     TcOut o; o.oh = p->tT1.hi + 64; o.ol = p->tT1.lo + 64; o.ldh = 128;
     gemm_tc(p, st, p->tWv, p->tWa, N, 64, 256, 64, p->ba, CN_ACT_RELU, o);
     gemm_tc(p, st, p->tT1, p->tWih, N, 384, 128, 64, p->bih, CN_ACT_NONE, out32(p->gi, 384));
-    gemm_tc(p, st, p->tH0, p->tWhh, N, 384, 128, 64, p->bhh, CN_ACT_NONE, out32(p->gh, 384));
   } else {
     gemm(p, st, p->wv, 256, p->Wa, 256, p->ba, p->t1 + 64, 128, N, 64, 256, CN_ACT_RELU);
     gemm(p, st, p->t1, 128, p->Wih, 128, p->bih, p->gi, 384, N, 384, 128, CN_ACT_NONE);
-    gemm(p, st, p->h0, 128, p->Whh, 128, p->bhh, p->gh, 384, N, 384, 128, CN_ACT_NONE);
   }
   cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out, tcm ? p->tH1.hi : nullptr,
                                                             tcm ? p->tH1.lo : nullptr);
   p->launches += 1;
-  // 4. output_linear, actor / critic MLPs, heads
+  // 4. output_linear, actor / critic MLPs (critic.2 on the side stream), heads
   mark(p, st, 9);
   if (tcm) {
     gemm_tc(p, st, p->tH1, p->tWo, N, 256, 128, 64, p->bo, CN_ACT_NONE, out16(p->tOut));
     gemm_tc(p, st, p->tOut, p->tWac1, N, 512, 256, 64, p->bac1, CN_ACT_TANH, out16(p->tAc1));    // [actor.0 | critic.0]
+    cudaEventRecord(p->ev_fork2, st);
+    cudaStreamWaitEvent(s2, p->ev_fork2, 0);
+    gemm_tc(p, s2, p->tC1, p->tWc2, N, 256, 256, 64, p->bc2, CN_ACT_TANH, out32(p->c2, 256));
+    cudaEventRecord(p->ev_join2, s2);
     gemm_tc(p, st, p->tA1, p->tWa2, N, 256, 256, 64, p->ba2, CN_ACT_TANH, out32(p->a2, 256));
-    gemm_tc(p, st, p->tC1, p->tWc2, N, 256, 256, 64, p->bc2, CN_ACT_TANH, out32(p->c2, 256));
   } else {
     gemm(p, st, d->h_out, 128, p->Wo, 128, p->bo, p->outb, 256, N, 256, 128, CN_ACT_NONE);
     gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);
+    cudaEventRecord(p->ev_fork2, st);
+    cudaStreamWaitEvent(s2, p->ev_fork2, 0);
+    gemm(p, s2, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
+    cudaEventRecord(p->ev_join2, s2);
     gemm(p, st, p->ac1, 512, p->Wa2, 256, p->ba2, p->a2, 256, N, 256, 256, CN_ACT_TANH);
-    gemm(p, st, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
   }
+  cudaStreamWaitEvent(st, p->ev_join2, 0);
   cn_heads_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->a2, 256, p->c2, 256, p->wv_, p->bv, p->Wm, p->bm, p->logstd, d->noise, N,
                                                d->value, d->action, d->log_prob, d->action_mean);
   p->launches += 1;
@@ -534,6 +560,7 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
     return cn_set_error("cn_internal_gemm_tc: need bn in {64,256}, N %% bn == 0 and K %% 64 == 0");
   cn_policy tmp;
   tmp.launches = 0;
+  tmp.st2 = nullptr;
   tmp.num_sms = 148;
   cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, 0);
   TcMat A, B;

@@ -243,82 +243,83 @@ __global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __res
                                                               float* __restrict__ out /* [Mc,512] or null */,
                                                               __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   // One WARP per valid (compacted) human row = one attention query, all 8 heads at once.
-  // Lane l owns elements [16 l, 16 l + 16) of the 512-wide q / k / v / o rows, i.e. a quarter of
-  // head l / 4: a key's score is a 16-FMA partial dot reduced over the 4 lanes of a head (2 shuffles),
-  // and soft-max is computed online (running max / sum) so nothing is staged: K and V rows are
-  // read straight from global memory with fully coalesced 2 KB warp loads.
+  // Every 512-float q / k / v / o row is touched with four fully coalesced LDG.128 per warp: lane l
+  // owns float4 #(l + 32 k), k = 0..3, i.e. elements 128 k + 4 l .. + 3, which belong to head
+  // 2 k + (l >= 16).  A key's score for head (2k + half) is the 4-FMA partial reduced over the 16 lanes
+  // of the half (4 xor-shuffles); soft-max runs online (running max / sum per head), nothing is staged.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mc = *mc_ptr;
   const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const float scale = 0.125f;   // 1/sqrt(head_dim = 64); torch scales q before q k^T
   // grid-stride over the compacted rows: the launch is sized to the machine, not to the worst case
   for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < mc; r += nwarps) {
-  const int e = row_env[r];
-  const size_t row0 = (size_t)row_start[e];
-  const int n = row_start[e + 1] - row_start[e];
-  const float scale = 0.125f;   // 1/sqrt(head_dim = 64); torch scales q before q k^T
-  float q[16], acc[16];
-  {
-    const float4* qv = reinterpret_cast<const float4*>(qkv + (size_t)r * 1536 + lane * 16);
+    const int e = row_env[r];
+    const size_t row0 = (size_t)row_start[e];
+    const int n = row_start[e + 1] - row_start[e];
+    float4 q[4], acc[4];
+    float m[4], l[4];
+    {
+      const float4* qv = reinterpret_cast<const float4*>(qkv + (size_t)r * 1536) + lane;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float4 a = __ldg(qv + t);
-      q[4 * t] = a.x * scale; q[4 * t + 1] = a.y * scale; q[4 * t + 2] = a.z * scale; q[4 * t + 3] = a.w * scale;
+      for (int k = 0; k < 4; ++k) {
+        const float4 a = __ldg(qv + 32 * k);
+        q[k] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+        acc[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        m[k] = -INFINITY; l[k] = 0.0f;
+      }
     }
-  }
+    for (int j = 0; j < n; ++j) {
+      const float4* kv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 512) + lane;
+      const float4* vv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 1024) + lane;
+      float4 kr[4], vr[4];
 #pragma unroll
-  for (int t = 0; t < 16; ++t) acc[t] = 0.0f;
-  float m = -INFINITY, l = 0.0f;
-  for (int j = 0; j < n; ++j) {
-    const float4* kv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 512 + lane * 16);
-    const float4* vv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 1024 + lane * 16);
-    float s = 0.0f;
-    float4 vr[4];
+      for (int k = 0; k < 4; ++k) { kr[k] = __ldg(kv + 32 * k); vr[k] = __ldg(vv + 32 * k); }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float4 b = __ldg(kv + t);
-      vr[t] = __ldg(vv + t);
-      s = fmaf(q[4 * t], b.x, s); s = fmaf(q[4 * t + 1], b.y, s);
-      s = fmaf(q[4 * t + 2], b.z, s); s = fmaf(q[4 * t + 3], b.w, s);
+      for (int k = 0; k < 4; ++k) {
+        float s = q[k].x * kr[k].x;
+        s = fmaf(q[k].y, kr[k].y, s); s = fmaf(q[k].z, kr[k].z, s); s = fmaf(q[k].w, kr[k].w, s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);        // all 16 lanes of the half hold the head's score
+        const float mn = fmaxf(m[k], s);
+        const float corr = expf(m[k] - mn);              // exp(-inf) = 0 on the first key
+        const float pj = expf(s - mn);
+        l[k] = l[k] * corr + pj;
+        acc[k].x = fmaf(pj, vr[k].x, acc[k].x * corr); acc[k].y = fmaf(pj, vr[k].y, acc[k].y * corr);
+        acc[k].z = fmaf(pj, vr[k].z, acc[k].z * corr); acc[k].w = fmaf(pj, vr[k].w, acc[k].w * corr);
+        m[k] = mn;
+      }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);          // all 4 lanes of the head hold the score
-    const float mn = fmaxf(m, s);
-    const float corr = expf(m - mn);                  // exp(-inf) = 0 on the first key
-    const float pj = expf(s - mn);
-    l = l * corr + pj;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      acc[4 * t] = fmaf(pj, vr[t].x, acc[4 * t] * corr);
-      acc[4 * t + 1] = fmaf(pj, vr[t].y, acc[4 * t + 1] * corr);
-      acc[4 * t + 2] = fmaf(pj, vr[t].z, acc[4 * t + 2] * corr);
-      acc[4 * t + 3] = fmaf(pj, vr[t].w, acc[4 * t + 3] * corr);
+    for (int k = 0; k < 4; ++k) {
+      const float inv = 1.0f / l[k];
+      acc[k].x *= inv; acc[k].y *= inv; acc[k].z *= inv; acc[k].w *= inv;
     }
-    m = mn;
-  }
-  const float inv = 1.0f / l;
-  const size_t off = (size_t)r * 512 + lane * 16;
+    if (out) {
+      float4* dst = reinterpret_cast<float4*>(out + (size_t)r * 512) + lane;
 #pragma unroll
-  for (int t = 0; t < 16; ++t) acc[t] *= inv;
-  if (out) {
-    float4* dst = reinterpret_cast<float4*>(out + off);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) dst[t] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
-  }
-  if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
-    uint32_t ph[8], pl[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float c0 = fminf(fmaxf(acc[2 * t], -65504.0f), 65504.0f), c1 = fminf(fmaxf(acc[2 * t + 1], -65504.0f), 65504.0f);
-      const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
-      const __half l0 = __float2half_rn(c0 - __half2float(h0)), l1 = __float2half_rn(c1 - __half2float(h1));
-      ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      for (int k = 0; k < 4; ++k) dst[32 * k] = acc[k];
     }
-    uint4* dh = reinterpret_cast<uint4*>(out_hi + off);
-    uint4* dl = reinterpret_cast<uint4*>(out_lo + off);
-    dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-    dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-  }
+    if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
+      uint2* dh = reinterpret_cast<uint2*>(out_hi + (size_t)r * 512) + lane;
+      uint2* dl = reinterpret_cast<uint2*>(out_lo + (size_t)r * 512) + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float c[4] = {fminf(fmaxf(acc[k].x, -65504.0f), 65504.0f), fminf(fmaxf(acc[k].y, -65504.0f), 65504.0f),
+                            fminf(fmaxf(acc[k].z, -65504.0f), 65504.0f), fminf(fmaxf(acc[k].w, -65504.0f), 65504.0f)};
+        uint32_t ph[2], pl[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const __half h0 = __float2half_rn(c[2 * t]), h1 = __float2half_rn(c[2 * t + 1]);
+          const __half l0 = __float2half_rn(c[2 * t] - __half2float(h0)), l1 = __float2half_rn(c[2 * t + 1] - __half2float(h1));
+          ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        dh[32 * k] = make_uint2(ph[0], ph[1]);
+        dl[32 * k] = make_uint2(pl[0], pl[1]);
+      }
+    }
   }   // row loop
 }
 
