@@ -147,9 +147,10 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   const float invTimeHorizon = 1.0f / p.orca_time_horizon;
   const float timeStep = (float)p.time_step;
 
-  // --- neighbour selection: dist^2 < neighborDist^2 kept sorted ascending by insertion with a strict
-  // `<` (ties keep insertion = index order), exactly Agent::insertAgentNeighbor; ORCA lines are then
-  // built directly in sorted order.
+  // --- neighbour selection: dist^2 < neighborDist^2, ascending, ties in insertion (index) order
+  // (Agent::insertAgentNeighbor).  Pass 1 compresses the in-range neighbours; pass 2 ranks them by
+  // counting (independent loads, no serial insertion chain through local memory) and builds each
+  // ORCA line directly at its sorted position.
   float vd[MAXH];
   uint8_t vj[MAXH];          // bit 7 = dummy (invisible) neighbour, bits 0..6 = human index
   int nl = 0;
@@ -158,21 +159,19 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
     const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
     const CnF2 op = v ? f2(s.fx[j], s.fy[j]) : f2(7.0f, 7.0f);     // dummy_human (crowd_sim.py:130-133)
     const float d = f2abssq(f2sub(pos, op));
-    if (d < rangeSq) {
-      int pos_i = nl;
-      while (pos_i > 0 && d < vd[pos_i - 1]) { vd[pos_i] = vd[pos_i - 1]; vj[pos_i] = vj[pos_i - 1]; --pos_i; }
-      vd[pos_i] = d; vj[pos_i] = (uint8_t)(j | (v ? 0 : 0x80));
-      ++nl;
-    }
+    if (d < rangeSq) { vd[nl] = d; vj[nl] = (uint8_t)(j | (v ? 0 : 0x80)); ++nl; }
   }
   for (int a = 0; a < nl; ++a) {
+    const float da = vd[a];
+    int rank = 0;
+    for (int b = 0; b < nl; ++b) rank += (vd[b] < da || (vd[b] == da && b < a)) ? 1 : 0;
     const int j = vj[a] & 0x7f;
     const bool dummy = (vj[a] & 0x80) != 0;
     const CnF2 op = dummy ? f2(7.0f, 7.0f) : f2(s.fx[j], s.fy[j]);
     const CnF2 ov = dummy ? f2(0.0f, 0.0f) : f2(s.vx[j], s.vy[j]);
     const float orad = p.randomize ? g.sim_rother[i * H + j]
                                    : (float)((dummy ? 0.3 : s.rad[j]) + pad + p.orca_safety_space);
-    lines.set(a, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
+    lines.set(rank, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
   }
   nl_out = nl; vmax_out = vmax; pref_out = pref;
 }

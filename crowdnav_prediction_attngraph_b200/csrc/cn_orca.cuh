@@ -50,12 +50,12 @@ struct CnLineStore {
   int cap;
   float4* ovf;     // per-thread overflow storage for k >= cap
   CN_HD CnLine get(int k) const {
-    const float4 v = (k < cap) ? base[(size_t)k * stride] : ovf[k - cap];
+    const float4 v = (k < cap) ? base[k * stride] : ovf[k - cap];
     CnLine l; l.point = f2(v.x, v.y); l.dir = f2(v.z, v.w); return l;
   }
   CN_HD void set(int k, const CnLine& l) {
     float4 v; v.x = l.point.x; v.y = l.point.y; v.z = l.dir.x; v.w = l.dir.y;
-    if (k < cap) base[(size_t)k * stride] = v; else ovf[k - cap] = v;
+    if (k < cap) base[k * stride] = v; else ovf[k - cap] = v;
   }
 };
 

@@ -53,24 +53,24 @@ CN_HD int cn_bcast_i(const CnCoop& c, int v, int src) {
   (void)src;
   return v;
 }
-// warp-wide min / max with std::min / std::max comparison semantics (exact, order independent
-// for non-NaN inputs)
+// warp-wide min / max (exact, order independent for non-NaN inputs).  On the device the float is
+// mapped to a monotonically ordered int32 and reduced with one REDUX instruction.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ int cn_f2ord(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float cn_ord2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
+#endif
 CN_HD float cn_warp_min(const CnCoop& c, float v) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = (w < v) ? w : v; }
-  }
+  if (c.nlanes > 1) return cn_ord2f(__reduce_min_sync(0xffffffffu, cn_f2ord(v)));
 #endif
+  (void)c;
   return v;
 }
 CN_HD float cn_warp_max(const CnCoop& c, float v) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = (v < w) ? w : v; }
-  }
+  if (c.nlanes > 1) return cn_ord2f(__reduce_max_sync(0xffffffffu, cn_f2ord(v)));
 #endif
+  (void)c;
   return v;
 }
 CN_HD int cn_popc_below(const CnCoop& c, uint32_t mask) {   // set bits of `mask` at lane positions below this lane
