@@ -112,14 +112,28 @@ __global__ void __launch_bounds__(256) cn_gemm_f32_kernel(const float* __restric
         v[j] = x;
       }
       if (out_hi) {    // (hi, lo) fp16 split for the tensor-core consumer; same leading dimension
+        if (nb + 3 < N && ((ldc & 3) == 0)) {
+          uint32_t ph[2], pl[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (nb + j < N) {
-            const float c = fminf(fmaxf(v[j], -65504.0f), 65504.0f);
-            const __half hh = __float2half_rn(c);
-            out_hi[(size_t)m * ldc + nb + j] = hh;
-            out_lo[(size_t)m * ldc + nb + j] = __float2half_rn(c - __half2float(hh));
+          for (int t = 0; t < 2; ++t) {
+            const float c0 = fminf(fmaxf(v[2 * t], -65504.0f), 65504.0f), c1 = fminf(fmaxf(v[2 * t + 1], -65504.0f), 65504.0f);
+            const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
+            const __half l0 = __float2half_rn(c0 - __half2float(h0)), l1 = __float2half_rn(c1 - __half2float(h1));
+            ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
+          *reinterpret_cast<uint2*>(out_hi + (size_t)m * ldc + nb) = make_uint2(ph[0], ph[1]);
+          *reinterpret_cast<uint2*>(out_lo + (size_t)m * ldc + nb) = make_uint2(pl[0], pl[1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (nb + j < N) {
+              const float c = fminf(fmaxf(v[j], -65504.0f), 65504.0f);
+              const __half hh = __float2half_rn(c);
+              out_hi[(size_t)m * ldc + nb + j] = hh;
+              out_lo[(size_t)m * ldc + nb + j] = __float2half_rn(c - __half2float(hh));
+            }
+        }
         if (!Cout) continue;
       }
       float* dst = Cout + (size_t)m * ldc + nb;
