@@ -128,7 +128,7 @@ class ClockSampler(object):
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -219,8 +219,10 @@ def run_ours(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_env, t_pol = [], []
     e0.record()
+    c0 = time.perf_counter()
     for _ in range(a.steps):
         device_step()
+    cpu_enqueue_ms = (time.perf_counter() - c0) * 1000.0 / a.steps      # host time to enqueue one step
     e1.record()
     barrier()
     ms_value = e0.elapsed_time(e1)
@@ -253,7 +255,16 @@ def run_ours(a):
     barrier()
     wall_e2e = (time.perf_counter() - w0) * 1000.0
     ms_e2e = max(f0.elapsed_time(f1), 0.0)
+    # the timed regions last tens of milliseconds, shorter than nvidia-smi's sampling period: keep the
+    # SAME device step running (untimed) until the sampler has seen >= 1 s of load, then read it
+    t_load = time.perf_counter()
+    while time.perf_counter() - t_load < 1.2:
+        for _ in range(50):
+            device_step()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed regions + 1.2 s of the same device step (sampling period 50 ms)"
 
     # ---------------------------------------------------------------- per-kernel timing (outside the timed regions)
     lib = eng.lib
@@ -335,7 +346,7 @@ def run_ours(a):
                 "h2d_bytes_per_step": N * 4 * 3,                 # masks + bad_masks + reward into the storage
                 "d2h_bytes_per_step": N * (4 + 1 + 4 + 4 + 8 + 4),   # reward, done, info, aux, ep_ret, ep_len
                 "ms_per_step": e2e_ms / a.steps, "ms_per_step_cuda_events": ms_e2e / a.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "cpu_enqueue_ms_per_step": cpu_enqueue_ms,
         "roofline": roof_env if dominant_is_env else roof_gemm,
         "roofline_other": roof_gemm if dominant_is_env else roof_env,
         "valid_human_rows": rows_valid, "mean_detected_humans": rows_valid / float(N),

@@ -70,6 +70,13 @@ struct CnState {
   // legacy numpy MT19937 per environment
   uint32_t *mt;                      // [N][624]
   int *mt_pos;                       // [N]
+  // PREPARED next episode (an episode's initial state is a pure function of (seed, case_counter), so
+  // it is computed off the critical path and merely installed when the current episode ends)
+  double *prep_robot;                // [N][4] px, py, gx, gy
+  double *prep_hpx, *prep_hpy, *prep_hrad, *prep_hvpref;   // [N][H]
+  double *prep_nd;                   // [N] config.orca.neighbor_dist after the spawn draws
+  uint32_t *prep_mt;                 // [N][624] generator state after the reset draws
+  int *prep_mt_pos;                  // [N]
   // diagnostics of the last step (parity tests)
   float *last_hvx, *last_hvy;        // ORCA output velocities [N][H]
   int *orca_nlines, *orca_fail;      // [N][H]

@@ -256,12 +256,11 @@ CN_HD int cn_event_flag(const CnParams& p, const CnState& g, const CnEnvSh& s, i
 // RNG-consuming pieces (leader thread only, serial — they share one MT19937 stream).
 struct CnSpawn { double px, py, vpref, rad; };
 
-CN_HD void cn_new_human_attrs(const CnParams& p, const CnState& g, int e, CnRng& rng, const CnCoop& co,
-                              double& vpref, double& rad) {
+CN_HD void cn_new_human_attrs(const CnParams& p, CnRng& rng, const CnCoop& co, double& nd_global, double& vpref,
+                              double& rad) {
   vpref = p.human_vpref; rad = p.human_radius;
   if (p.randomize) {                      // agent.py:20-23 then agent.py:44-50
-    const double nd = cn_rng_uniform(rng, co, 5, 10);
-    if (co.lane == 0) g.nd_global[e] = nd;
+    nd_global = cn_rng_uniform(rng, co, 5, 10);
     vpref = cn_rng_uniform(rng, co, 0.5, 1.5);
     rad = cn_rng_uniform(rng, co, 0.3, 0.5);
   }
@@ -269,10 +268,10 @@ CN_HD void cn_new_human_attrs(const CnParams& p, const CnState& g, int e, CnRng&
 
 // generate_circle_crossing_human (crowd_sim_var_num.py:116-146) against robot + humans[0..n_present).
 // Replicated execution: every lane draws the same numbers; the collision scan is lane-strided.
-CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, const CnEnvSh& s, int e,
-                                       CnRng& rng, const CnCoop& co, int n_present) {
+CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnEnvSh& s, CnRng& rng, const CnCoop& co, int n_present,
+                                       double& nd_global, uint8_t* overflow) {
   CnSpawn sp;
-  cn_new_human_attrs(p, g, e, rng, co, sp.vpref, sp.rad);
+  cn_new_human_attrs(p, rng, co, nd_global, sp.vpref, sp.rad);
   // The reference loops until a free spot is found and never terminates when the circle is full
   // (it cannot place more than ~76 humans of radius 0.3-0.5); a kernel must not hang the GPU, so after
   // CN_MAX_SPAWN_TRIES rejected candidates the last one is accepted and the environment is flagged.
@@ -294,16 +293,18 @@ CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnState& g, cons
     }
     if (!cn_any(co, collide) || tries >= CN_MAX_SPAWN_TRIES) {
       sp.px = px; sp.py = py;
-      if (tries >= CN_MAX_SPAWN_TRIES && co.lane == 0) g.spawn_overflow[e] = 1;
+      if (tries >= CN_MAX_SPAWN_TRIES && co.lane == 0) *overflow = 1;
       break;
     }
   }
   return sp;
 }
 
-// reset (crowd_sim_var_num.py:303-363).  `key` = 624-word MT19937 scratch (shared memory in the
-// reset kernel); every lane of `co` runs this function (replicated), lane 0 owns the writes.
-CN_HD void cn_reset_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
+// PREPARE the next episode of environment e (crowd_sim_var_num.py:303-363 up to generate_ob): seed the
+// legacy MT19937 with the CURRENT case_counter, sample robot + humans into the scratch working set `s`
+// and publish the result in g.prep_*.  Pure function of (seed, case_counter): it runs off the critical
+// path.  `key` = 624-word scratch; every lane of `co` runs this function (replicated), lane 0 writes.
+CN_HD void cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
   const int H = p.H;
   CnRng rng; rng.key = key; rng.pos = 624;
   const uint32_t cc = g.case_counter[e];
@@ -315,34 +316,57 @@ CN_HD void cn_reset_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, 
     const double gx = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
     const double gy = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
     if (cn_norm_dot(px - gx, py - gy) >= 8) {
-      if (co.lane == 0) { s.rpx = px; s.rpy = py; s.rgx = gx; s.rgy = gy; s.rvx = 0.0f; s.rvy = 0.0f; }
+      if (co.lane == 0) { s.rpx = px; s.rpy = py; s.rgx = gx; s.rgy = gy; }
       break;
     }
   }
   cn_coop_sync(co);
+  double nd = g.nd_global[e];
   for (int i = 0; i < H; ++i) {
-    const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, co, i);
+    const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, i, nd, g.spawn_overflow + e);
     if (co.lane == 0) {
-      s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
-      s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
-      s.fx[i] = (float)sp.px; s.fy[i] = (float)sp.py;
-      const size_t gi = cn_idx(p, e, i);
-      g.sim_exists[gi] = 0;
-      g.bpx[gi] = 0; g.bpy[gi] = 0; g.bvx[gi] = 0; g.bvy[gi] = 0; g.brad[gi] = 0;   // last_human_states = zeros
+      s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
     }
     cn_coop_sync(co);
   }
+  for (int i = co.lane; i < H; i += co.nlanes) {
+    const size_t gi = cn_idx(p, e, i);
+    g.prep_hpx[gi] = s.px[i]; g.prep_hpy[gi] = s.py[i]; g.prep_hrad[gi] = s.rad[i]; g.prep_hvpref[gi] = s.vpref[i];
+  }
   if (co.lane == 0) {
+    double* r = g.prep_robot + (size_t)e * 4;
+    r[0] = s.rpx; r[1] = s.rpy; r[2] = s.rgx; r[3] = s.rgy;
+    g.prep_nd[e] = nd;
+    g.prep_mt_pos[e] = rng.pos;
+  }
+  cn_coop_sync(co);
+}
+
+// INSTALL the prepared episode (per human thread; the leader also installs the per-env scalars).
+// Called for finished episodes right after the reward, and for every environment on a full reset.
+CN_HD void cn_install_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h) {
+  const int H = p.H;
+  const size_t i = cn_idx(p, e, h);
+  const double px = g.prep_hpx[i], py = g.prep_hpy[i];
+  s.px[h] = px; s.py[h] = py; s.gx[h] = -px; s.gy[h] = -py;        // lean: gx / gy / rad / vpref alias HBM
+  s.rad[h] = g.prep_hrad[i]; s.vpref[h] = g.prep_hvpref[i];
+  s.vx[h] = 0.0f; s.vy[h] = 0.0f; s.fx[h] = (float)px; s.fy[h] = (float)py;
+  g.sim_exists[i] = 0;
+  g.bpx[i] = 0; g.bpy[i] = 0; g.bvx[i] = 0; g.bvy[i] = 0; g.brad[i] = 0;   // last_human_states = zeros
+  for (int w = h; w < 624; w += H) g.mt[(size_t)e * 624 + w] = g.prep_mt[(size_t)e * 624 + w];
+  if (h == 0) {
+    const double* r = g.prep_robot + (size_t)e * 4;
+    s.rpx = r[0]; s.rpy = r[1]; s.rgx = r[2]; s.rgy = r[3]; s.rvx = 0.0f; s.rvy = 0.0f;
     // case_counter = (case_counter + nenv) % case_size['train'] with case_size = UINT32_MAX - 2000
     const uint64_t case_size = 4294967295ull - 2000ull;
-    g.case_counter[e] = (uint32_t)(((uint64_t)cc + (uint64_t)p.nenv_total) % case_size);
+    g.case_counter[e] = (uint32_t)(((uint64_t)g.case_counter[e] + (uint64_t)p.nenv_total) % case_size);
     g.potential[e] = -fabs(cn_norm_dot(s.rgx - s.rpx, s.rgy - s.rpy));
     g.step_count[e] = 0;
     g.ep_ret[e] = 0.0; g.ep_len[e] = 0;
-    g.mt_pos[e] = rng.pos;
-    s.reset_flag = 1; s.done = 0; s.nvis = 0;
+    g.mt_pos[e] = g.prep_mt_pos[e];
+    if (p.randomize) g.nd_global[e] = g.prep_nd[e];
+    s.reset_flag = 1; s.nvis = 0; s.goal_flag = 0;
   }
-  cn_coop_sync(co);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -441,6 +465,7 @@ CN_HD void cn_phase_obs_c(const CnParams& p, CnEnvSh& s, int e, int h, const CnO
 CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
   const int H = p.H;
   CnRng rng; rng.key = key; rng.pos = g.mt_pos[e];
+  double nd = g.nd_global[e];
   const int step = g.step_count[e];
   // global_time % 5 == 0 with global_time = step * 0.25 accumulated exactly
   const double gt = step * p.time_step;
@@ -479,7 +504,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   if (p.end_goal_changing) {
     for (int i = 0; i < H; ++i) {
       if (cn_norm_dot(s.gx[i] - s.px[i], s.gy[i] - s.py[i]) < s.rad[i]) {
-        const CnSpawn sp = cn_circle_crossing_human(p, g, s, e, rng, co, H);
+        const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, H, nd, g.spawn_overflow + e);
         cn_coop_sync(co);
         if (co.lane == 0) {
           s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
@@ -490,7 +515,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
       }
     }
   }
-  if (co.lane == 0) g.mt_pos[e] = rng.pos;
+  if (co.lane == 0) { g.mt_pos[e] = rng.pos; if (p.randomize) g.nd_global[e] = nd; }
 }
 
 // Phase STORE: write the working set back to HBM.

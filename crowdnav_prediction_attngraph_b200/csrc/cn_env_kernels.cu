@@ -59,11 +59,12 @@ __device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L,
   return s;
 }
 
-// One rollout step of every environment (no reset inside: environments that finish are flagged in
-// out.done and re-initialised by cn_env_reset_kernel, launched right behind on the same stream).
+// One rollout step of every environment.  Episodes that finish INSTALL their prepared successor
+// (g.prep_*, computed off the critical path by cn_env_event_kernel) and emit its first observation in
+// the same launch.  mode 1 = reset of the whole vector env: no step, every environment installs.
 template <int MAXH, int MAXW>
 __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
-                                                          CnObs ob, CnStepOut out, int epb, int line_cap) {
+                                                          CnObs ob, CnStepOut out, int epb, int line_cap, int mode) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.H;
   const int le = threadIdx.x / H;
@@ -97,9 +98,13 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   if (threadIdx.x == 0) { reinterpret_cast<int*>(lp3_q)[0] = 0; reinterpret_cast<int*>(lp3_q)[1] = 0; }
   const CnCoop co = {lane, 32};
 
-  if (active) cn_phase_load(p, g, *s, e, h, action);
+  if (mode == 1) {
+    if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; }
+  } else if (active) {
+    cn_phase_load(p, g, *s, e, h, action);
+  }
   __syncthreads();
-  {
+  if (mode != 1) {
     int nl = 0, fail = -1;
     float vmax = 0.0f;
     CnF2 pref = f2(0.0f, 0.0f), result = f2(0.0f, 0.0f);
@@ -141,17 +146,19 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
     if (active) cn_orca_finish(p, g, *s, e, h, result, nl, fail);
   }
   __syncthreads();
-  if (active && h == 0) cn_phase_reward(p, g, *s, e, out);
+  if (mode != 1 && active && h == 0) cn_phase_reward(p, g, *s, e, out);
   __syncthreads();
-  if (active) cn_phase_integrate(p, *s, h);
+  if (active) {
+    if (s->done) cn_install_env(p, g, *s, e, h);      // finished: the prepared next episode takes over
+    else cn_phase_integrate(p, *s, h);
+  }
   __syncthreads();
-  const bool live = active && !s->done;      // finished episodes: observation comes from the reset kernel
   float row[MAXW];
-  if (live) cn_phase_obs_a<MAXW>(p, g, *s, e, h, row);
+  if (active) cn_phase_obs_a<MAXW>(p, g, *s, e, h, row);
   __syncthreads();
-  if (live) cn_phase_obs_b(p, g, *s, e, h, row, ob);
+  if (active) cn_phase_obs_b(p, g, *s, e, h, row, ob);
   __syncthreads();
-  if (live) {
+  if (active) {
     cn_phase_obs_c(p, *s, e, h, ob);
     cn_phase_store(p, g, *s, e, h);
   }
@@ -159,13 +166,14 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
 }
 
 // Event kernel: ONE WARP per environment, for everything that consumes the legacy numpy MT19937
-// stream (624-word state per environment): episode reset (CrowdSimVarNum.reset), end-goal respawns
-// and random goal changes.  The state is staged in shared memory (lane-parallel twist), rejection
-// sampling collision checks are lane-strided, and after a reset the first observation is generated
-// with lanes over humans.  Warps whose environment has no event (g.evt == 0) exit immediately.
+// stream (624-word state per environment): PREPARATION of the next episode (CrowdSimVarNum.reset up
+// to generate_ob, evt 2), end-goal respawns and random goal changes (evt 1).  The generator state is
+// staged in shared memory (lane-parallel twist) and the rejection-sampling collision scans are
+// lane-strided.  Nothing here touches observation buffers, so the kernel runs on the engine's side
+// stream, overlapped with the policy; the next step kernel waits for it.  Warps whose environment has
+// no event (g.evt == 0) exit immediately.
 #define CN_EVENT_WARPS 4
-template <int MAXW>
-__global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnParams p, CnState g, CnObs ob, int force,
+__global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnParams p, CnState g, int force,
                                                                            size_t per_warp_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,20 +188,10 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
   if (lane == 0) env_view(base, L, H, false, g, e);
   __syncwarp();
   uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
-  float* rows = reinterpret_cast<float*>(base + L.per_env + 624 * sizeof(uint32_t));
   const CnCoop co = {lane, 32};
   if (evt == 2) {
-    if (lane == 0) { s->done = 0; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; }
-    __syncwarp();
-    cn_reset_env(p, g, *s, e, key, co);
-    for (int h = lane; h < H; h += 32) cn_phase_obs_a<MAXW>(p, g, *s, e, h, rows + (size_t)h * MAXW);
-    __syncwarp();
-    for (int h = lane; h < H; h += 32) cn_phase_obs_b(p, g, *s, e, h, rows + (size_t)h * MAXW, ob);
-    __syncwarp();
-    for (int h = lane; h < H; h += 32) {
-      cn_phase_obs_c(p, *s, e, h, ob);
-      cn_phase_store(p, g, *s, e, h);
-    }
+    cn_prepare_env(p, g, *s, e, key, co);
+    for (int i = lane; i < 624; i += 32) g.prep_mt[(size_t)e * 624 + i] = key[i];
   } else {
     // goal dynamics on the state the step kernel just stored
     for (int h = lane; h < H; h += 32) cn_phase_load(p, g, *s, e, h, nullptr);
@@ -202,8 +200,8 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
     cn_phase_goals(p, g, *s, e, key, co);
     __syncwarp();
     for (int h = lane; h < H; h += 32) cn_phase_store(p, g, *s, e, h);
+    for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
   }
-  for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
 }
 
 struct Field {
@@ -227,6 +225,11 @@ struct cn_env {
   int64_t launches;
   std::map<std::string, Field> fields;
   std::vector<void*> allocs;
+  // side stream of the event kernel (overlaps the caller's policy work between two steps)
+  cudaStream_t side;
+  cudaEvent_t ev_step, ev_side;
+  bool side_pending;      // an event kernel is in flight: the next launch on the caller's stream waits for it
+  bool prep_dirty;        // a state upload may have invalidated the prepared episodes
   // staging for the host-buffer entry point
   float* d_action;
   cn_obs_ptrs d_obs;
@@ -249,7 +252,7 @@ int dev_alloc(cn_env* env, const char* name, T** ptr, size_t count) {
   return 0;
 }
 
-typedef void (*KernelFn)(CnParams, CnState, const float*, CnObs, CnStepOut, int, int);
+typedef void (*KernelFn)(CnParams, CnState, const float*, CnObs, CnStepOut, int, int, int);
 
 KernelFn pick_kernel(int maxh) {
   if (maxh <= 32) return cn_env_step_kernel<32, 16>;
@@ -264,27 +267,59 @@ CnObs to_obs(const cn_obs_ptrs* o) {
   return ob;
 }
 
-int launch_events(cn_env* env, const cn_obs_ptrs* o, int force, cudaStream_t stream) {
+int event_kernel(cn_env* env, int force, cudaStream_t stream) {
   const int grid = (env->p.N + CN_EVENT_WARPS - 1) / CN_EVENT_WARPS;
-  cn_env_event_kernel<16><<<grid, CN_EVENT_WARPS * 32, CN_EVENT_WARPS * env->reset_warp_bytes, stream>>>(
-      env->p, env->g, to_obs(o), force, env->reset_warp_bytes);
+  cn_env_event_kernel<<<grid, CN_EVENT_WARPS * 32, CN_EVENT_WARPS * env->reset_warp_bytes, stream>>>(
+      env->p, env->g, force, env->reset_warp_bytes);
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_event_kernel launch: %s", cudaGetErrorString(err));
   return 0;
 }
 
-int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const cn_step_ptrs* r, cudaStream_t stream) {
+// make `stream` wait for the event kernel in flight on the side stream (if any)
+int join_side(cn_env* env, cudaStream_t stream) {
+  if (!env->side_pending) return 0;
+  cudaError_t err = cudaStreamWaitEvent(stream, env->ev_side, 0);
+  if (err != cudaSuccess) return cn_set_error("cudaStreamWaitEvent(side): %s", cudaGetErrorString(err));
+  env->side_pending = false;
+  return 0;
+}
+
+// step (or mode 1: install-everything) kernel on the caller's stream, then the event kernel behind it
+// on the side stream
+int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const cn_step_ptrs* r, int mode,
+                cudaStream_t stream) {
   CnStepOut out;
-  out.reward = r->reward; out.done = r->done; out.info = r->info; out.info_aux = r->info_aux;
-  out.ep_ret = r->ep_ret; out.ep_len = r->ep_len; out.not_done = r->not_done;
+  memset(&out, 0, sizeof(out));
+  if (r) {
+    out.reward = r->reward; out.done = r->done; out.info = r->info; out.info_aux = r->info_aux;
+    out.ep_ret = r->ep_ret; out.ep_len = r->ep_len; out.not_done = r->not_done;
+  }
+  int rc = join_side(env, stream);
+  if (rc) return rc;
+  if (mode == 1 || env->prep_dirty) {
+    // (re)compute every prepared episode first: a pure function of (seed, case_counter)
+    rc = event_kernel(env, 1, stream);
+    if (rc) return rc;
+    env->prep_dirty = false;
+  }
   const int grid = (env->p.N + env->epb - 1) / env->epb;
   KernelFn fn = pick_kernel(env->maxh);
-  fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, to_obs(o), out, env->epb, env->line_cap);
+  fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, to_obs(o), out, env->epb, env->line_cap,
+                                                      mode);
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel launch: %s", cudaGetErrorString(err));
-  return launch_events(env, o, 0, stream);
+  err = cudaEventRecord(env->ev_step, stream);
+  if (err == cudaSuccess) err = cudaStreamWaitEvent(env->side, env->ev_step, 0);
+  if (err != cudaSuccess) return cn_set_error("fork to side stream: %s", cudaGetErrorString(err));
+  rc = event_kernel(env, 0, env->side);
+  if (rc) return rc;
+  err = cudaEventRecord(env->ev_side, env->side);
+  if (err != cudaSuccess) return cn_set_error("cudaEventRecord(side): %s", cudaGetErrorString(err));
+  env->side_pending = true;
+  return 0;
 }
 
 }  // namespace
@@ -314,6 +349,12 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   env->cfg = *cfg;
   env->device = cfg->device;
   env->launches = 0;
+  env->side = nullptr; env->ev_step = nullptr; env->ev_side = nullptr;
+  env->side_pending = false; env->prep_dirty = true;
+  err = cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->ev_step, cudaEventDisableTiming);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->ev_side, cudaEventDisableTiming);
+  if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("side stream: %s", cudaGetErrorString(err)); }
   CnParams& p = env->p;
   memset(&p, 0, sizeof(p));
   p.N = cfg->num_envs; p.H = cfg->human_num; p.P = cfg->predict_steps;
@@ -351,6 +392,8 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH);
   A(sim_rother, p.randomize ? NH * p.H : (size_t)4);
   A(mt, N * 624); A(mt_pos, N);
+  A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
+  A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
 #undef A
   if (!rc) {
@@ -424,9 +467,9 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     if (rc2) { cn_env_destroy(env); return rc2; }
     env->g.line_ovf = ovf;
   }
-  // reset kernel: per-warp working set + MT19937 state + observation rows
-  env->reset_warp_bytes = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t) + (size_t)p.H * 16 * sizeof(float));
-  err = cudaFuncSetAttribute(cn_env_event_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // event kernel: per-warp working set + MT19937 state
+  env->reset_warp_bytes = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t));
+  err = cudaFuncSetAttribute(cn_env_event_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(CN_EVENT_WARPS * env->reset_warp_bytes));
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }
   *out = env;
@@ -436,6 +479,10 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
 int cn_env_destroy(cn_env* env) {
   if (!env) return 0;
   cudaSetDevice(env->device);
+  cudaDeviceSynchronize();
+  if (env->side) cudaStreamDestroy(env->side);
+  if (env->ev_step) cudaEventDestroy(env->ev_step);
+  if (env->ev_side) cudaEventDestroy(env->ev_side);
   for (void* q : env->allocs) cudaFree(q);
   delete env;
   return 0;
@@ -445,7 +492,7 @@ int cn_env_reset(cn_env* env, const cn_obs_ptrs* d_obs, void* stream) {
   if (!env || !d_obs) return cn_set_error("cn_env_reset: null argument");
   cudaSetDevice(env->device);
   // a reset of the whole vec env restarts Monitor bookkeeping but NOT case_counter (it keeps advancing)
-  return launch_events(env, d_obs, 1, (cudaStream_t)stream);
+  return launch_step(env, nullptr, d_obs, nullptr, 1, (cudaStream_t)stream);
 }
 
 int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, const cn_step_ptrs* d_out,
@@ -454,7 +501,7 @@ int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, co
   if (!d_out->reward || !d_out->done || !d_out->info || !d_out->info_aux || !d_out->ep_ret || !d_out->ep_len)
     return cn_set_error("cn_env_step: every cn_step_ptrs field must be set");
   cudaSetDevice(env->device);
-  return launch_step(env, d_action, d_obs, d_out, (cudaStream_t)stream);
+  return launch_step(env, d_action, d_obs, d_out, 0, (cudaStream_t)stream);
 }
 
 int cn_env_step_host(cn_env* env, const float* h_action, const cn_obs_ptrs* h_obs, const cn_step_ptrs* h_out) {
@@ -464,7 +511,7 @@ int cn_env_step_host(cn_env* env, const float* h_action, const cn_obs_ptrs* h_ob
   cudaStream_t st = 0;
   cudaError_t err = cudaMemcpyAsync(env->d_action, h_action, N * 2 * sizeof(float), cudaMemcpyHostToDevice, st);
   if (err != cudaSuccess) return cn_set_error("H2D action: %s", cudaGetErrorString(err));
-  int rc = launch_step(env, env->d_action, &env->d_obs, &env->d_out, st);
+  int rc = launch_step(env, env->d_action, &env->d_obs, &env->d_out, 0, st);
   if (rc) return rc;
 #define D2H(dst, src, bytes) if (dst) { err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st); \
     if (err != cudaSuccess) return cn_set_error("D2H " #dst ": %s", cudaGetErrorString(err)); }
@@ -503,6 +550,7 @@ int cn_env_state_copy(cn_env* env, const char* name, void* h_buf, size_t bytes, 
     err = dir ? cudaMemcpy(it->second.ptr, h_buf, bytes, cudaMemcpyHostToDevice)
               : cudaMemcpy(h_buf, it->second.ptr, bytes, cudaMemcpyDeviceToHost);
   if (err != cudaSuccess) return cn_set_error("cn_env_state_copy(%s): %s", name, cudaGetErrorString(err));
+  if (dir) env->prep_dirty = true;
   return 0;
 }
 

@@ -50,9 +50,12 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     s.visr = u.data();
     s.lean = 0;
     const CnCoop co = {0, 1};
+    uint32_t* prep_key = g.prep_mt + (size_t)e * 624;
     if (mode == 1) {
-      s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
-      cn_reset_env(p, g, s, e, g.mt + (size_t)e * 624, co);
+      // full reset = prepare (event kernel, forced) -> install + first observation (step kernel, mode 1)
+      cn_prepare_env(p, g, s, e, prep_key, co);
+      s.done = 1; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
+      for (int h = H - 1; h >= 0; --h) cn_install_env(p, g, s, e, h);
     } else {
       for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, action);
       for (int h = 0; h < H; ++h) {
@@ -67,15 +70,17 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
         cn_orca_finish(p, g, s, e, h, result, nl, fail);
       }
       cn_phase_reward(p, g, s, e, out);
-      for (int h = 0; h < H; ++h) cn_phase_integrate(p, s, h);
-      if (s.done) cn_reset_env(p, g, s, e, g.mt + (size_t)e * 624, co);   // = cn_env_reset_kernel for this env
+      if (s.done) { for (int h = H - 1; h >= 0; --h) cn_install_env(p, g, s, e, h); }   // prepared next episode
+      else { for (int h = 0; h < H; ++h) cn_phase_integrate(p, s, h); }
     }
     for (int h = 0; h < H; ++h) cn_phase_obs_a<16>(p, g, s, e, h, rows.data() + (size_t)h * 16);
     for (int h = 0; h < H; ++h) cn_phase_obs_b(p, g, s, e, h, rows.data() + (size_t)h * 16, ob);
     for (int h = 0; h < H; ++h) cn_phase_obs_c(p, s, e, h, ob);
-    // event kernel, goal-dynamics branch (runs only when the step kernel flagged it)
-    if (mode == 0 && !s.reset_flag && cn_event_flag(p, g, s, e) == 1) cn_phase_goals(p, g, s, e, g.mt + (size_t)e * 624, co);
+    const int evt = cn_event_flag(p, g, s, e);
+    // event kernel: goal dynamics (evt 1) or preparation of the next episode (evt 2)
+    if (evt == 1) cn_phase_goals(p, g, s, e, g.mt + (size_t)e * 624, co);
     for (int h = 0; h < H; ++h) cn_phase_store(p, g, s, e, h);
+    if (evt == 2) cn_prepare_env(p, g, s, e, prep_key, co);
   }
 }
 
@@ -112,6 +117,8 @@ void* harness_create(const cn_config* cfg) {
   A(bpx, NH); A(bpy, NH); A(bvx, NH); A(bvy, NH); A(brad, NH); A(vis, NH);
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH); A(sim_rother, NH * p.H);
   A(mt, N * 624); A(mt_pos, N);
+  A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
+  A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
 #undef A
   for (size_t e = 0; e < N; ++e) g.nd_global[e] = cfg->orca_neighbor_dist;

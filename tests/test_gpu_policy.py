@@ -92,3 +92,29 @@ def test_policy_module_drop_in_act_and_evaluate():
         v2, lp2, ent, _ = pol.evaluate_actions(obs, hx, masks, action)
     assert (value - v2).abs().max() < 1e-4 and (logp - lp2).abs().max() < 1e-4
     assert hx2['human_human_edge_rnn'].shape == (N, H + 1, 256)
+
+
+def test_cuda_policy_varnum_input_size_2_both_gemm_modes():
+    """CrowdSimVarNum-v0 policy (BASELINE config 1 shape: 5 humans, spatial_edges width 2)."""
+    from oracle.policy_ref import PolicyRef
+    from crowdnav_prediction_attngraph_b200.policy import CudaPolicy, make_reference_like_state_dict
+    N, H = 70, 5
+    sd = make_reference_like_state_dict(2, seed=9)
+    ref = PolicyRef(2)
+    ref.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(1)
+    n = torch.randint(1, H + 1, (N, 1), generator=gen).float()
+    sp = torch.randn(N, H, 2, generator=gen) * 3
+    sp[torch.arange(H)[None, :] >= n] = 15.0
+    obs = dict(robot_node=torch.randn(N, 1, 7, generator=gen) * 3, temporal_edges=torch.randn(N, 1, 2, generator=gen),
+               spatial_edges=sp, detected_human_num=n)
+    h = torch.randn(N, 1, 128, generator=gen)
+    masks = torch.ones(N, 1)
+    with torch.no_grad():
+        rv, rm, rh = ref(obs, h, masks)
+    for mode in (0, 1):
+        pol = CudaPolicy(N, H, 2, device="cuda:0", gemm_mode=mode)
+        pol.load_state_dict(sd)
+        value, action, logp, h1, mean = pol.act({k: v.cuda() for k, v in obs.items()}, h.cuda(), masks.cuda(),
+                                                deterministic=True, return_mean=True)
+        assert (value.cpu() - rv).abs().max() < TOL and (mean.cpu() - rm).abs().max() < TOL and (h1.cpu() - rh).abs().max() < TOL
