@@ -26,7 +26,7 @@
 #include "cn_orca.cuh"
 
 #define CN_PI 3.141592653589793
-#define CN_MAX_SPAWN_TRIES 20000
+#define CN_MAX_SPAWN_TRIES 4096
 
 CN_HD double cn_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
@@ -266,37 +266,89 @@ CN_HD void cn_new_human_attrs(const CnParams& p, CnRng& rng, const CnCoop& co, d
   }
 }
 
+// Rejection sampling of a point near the circle that keeps `rad_i + r_k + discomfort_dist` clear of the
+// position AND the goal of the robot and of humans [0, n) except `skip`
+// (crowd_sim_var_num.py:116-146 spawn: noise = U[0,1)*2; crowd_sim.py:415-450 goal change: noise =
+// (U[0,1) - 0.5) * v_pref).  Every try consumes exactly three random_sample() = six MT19937 words, so a
+// warp evaluates up to 32 CONSECUTIVE tries at once (lane j peeks at words [pos + 6j, pos + 6j + 6),
+// checks its candidate against every agent) and accepts the first free one: same result and same
+// stream position as the sequential loop.  Near the 624-word twist boundary (and in the single-thread
+// host build) it falls back to one try at a time with a lane-strided scan.
+// The reference loops forever when no free spot exists (it cannot place more than ~76 humans); a
+// kernel must not hang, so try number CN_MAX_SPAWN_TRIES is accepted as is and the environment flagged.
+struct CnCand { double x, y; };
+CN_HD bool cn_cand_collides(const CnParams& p, const CnEnvSh& s, double x, double y, double rad_i, int k) {
+  double ax, ay, agx, agy, ar;
+  if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
+  else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
+  const double min_dist = rad_i + ar + p.discomfort_dist;
+  // exact predicate: np.linalg.norm(d) < min_dist.  Squared distances decide every case that is not within
+  // 1e-14 (relative) of the boundary without the fp64 square root; the boundary band takes the exact path.
+  const double m2 = min_dist * min_dist, lo = m2 * (1.0 - 1e-14), hi = m2 * (1.0 + 1e-14);
+  const double dx = x - ax, dy = y - ay, ex = x - agx, ey = y - agy;
+  const double d2 = dx * dx + dy * dy, e2 = ex * ex + ey * ey;
+  if (d2 < lo || e2 < lo) return true;
+  if (d2 > hi && e2 > hi) return false;
+  return cn_norm_dot(dx, dy) < min_dist || cn_norm_dot(ex, ey) < min_dist;
+}
+CN_HD CnCand cn_cand_point(const CnParams& p, double u0, double u1, double u2, int goal_kind, double vp) {
+  const double angle = u0 * CN_PI * 2;
+  const double nx = goal_kind ? (u1 - 0.5) * vp : u1 * 2;
+  const double ny = goal_kind ? (u2 - 0.5) * vp : u2 * 2;
+  CnCand c;
+  c.x = p.circle_radius * cos(angle) + nx;
+  c.y = p.circle_radius * sin(angle) + ny;
+  return c;
+}
+CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng, const CnCoop& co, int goal_kind, int n,
+                                 int skip, double rad_i, double vp, uint8_t* overflow) {
+  CnCand c; c.x = 0; c.y = 0;
+  for (int tries = 0;;) {
+    int nb = (624 - rng.pos) / 6;                              // whole tries left before the next twist
+    if (nb > co.nlanes) nb = co.nlanes;
+    if (nb > CN_MAX_SPAWN_TRIES - tries + 1) nb = CN_MAX_SPAWN_TRIES - tries + 1;
+    if (co.nlanes > 1 && nb >= 1) {
+      bool collide = true;
+      if (co.lane < nb) {
+        const int off = 6 * co.lane;
+        c = cn_cand_point(p, cn_rng_peek_double(rng, off), cn_rng_peek_double(rng, off + 2),
+                          cn_rng_peek_double(rng, off + 4), goal_kind, vp);
+        collide = false;
+        for (int k = -1; k < n && !collide; ++k)
+          if (k != skip) collide = cn_cand_collides(p, s, c.x, c.y, rad_i, k);
+      }
+      const uint32_t free_mask = cn_ballot(co, !collide);
+      const bool last = (tries + nb - 1 >= CN_MAX_SPAWN_TRIES);
+      if (free_mask || last) {
+        const int j = free_mask ? cn_ffs(free_mask) : nb - 1;
+        c.x = cn_bcast_d(co, c.x, j); c.y = cn_bcast_d(co, c.y, j);
+        rng.pos += 6 * (j + 1);
+        if (!free_mask && co.lane == 0) *overflow = 1;
+        return c;
+      }
+      rng.pos += 6 * nb; tries += nb;
+    } else {
+      const double u0 = cn_rng_double(rng, co), u1 = cn_rng_double(rng, co), u2 = cn_rng_double(rng, co);
+      c = cn_cand_point(p, u0, u1, u2, goal_kind, vp);
+      bool collide = false;
+      for (int k = -1 + co.lane; k < n; k += co.nlanes) {
+        if (k == skip) continue;
+        if (cn_cand_collides(p, s, c.x, c.y, rad_i, k)) { collide = true; break; }
+      }
+      if (!cn_any(co, collide)) return c;
+      if (tries >= CN_MAX_SPAWN_TRIES) { if (co.lane == 0) *overflow = 1; return c; }
+      ++tries;
+    }
+  }
+}
+
 // generate_circle_crossing_human (crowd_sim_var_num.py:116-146) against robot + humans[0..n_present).
-// Replicated execution: every lane draws the same numbers; the collision scan is lane-strided.
 CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnEnvSh& s, CnRng& rng, const CnCoop& co, int n_present,
                                        double& nd_global, uint8_t* overflow) {
   CnSpawn sp;
   cn_new_human_attrs(p, rng, co, nd_global, sp.vpref, sp.rad);
-  // The reference loops until a free spot is found and never terminates when the circle is full
-  // (it cannot place more than ~76 humans of radius 0.3-0.5); a kernel must not hang the GPU, so after
-  // CN_MAX_SPAWN_TRIES rejected candidates the last one is accepted and the environment is flagged.
-  for (int tries = 0;; ++tries) {
-    const double angle = cn_rng_double(rng, co) * CN_PI * 2;
-    const double px_noise = cn_rng_uniform(rng, co, 0, 1) * 2;
-    const double py_noise = cn_rng_uniform(rng, co, 0, 1) * 2;
-    const double px = p.circle_radius * cos(angle) + px_noise;
-    const double py = p.circle_radius * sin(angle) + py_noise;
-    bool collide = false;
-    for (int k = -1 + co.lane; k < n_present; k += co.nlanes) {
-      double ax, ay, agx, agy, ar;
-      if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
-      else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
-      const double min_dist = sp.rad + ar + p.discomfort_dist;
-      if (cn_norm_dot(px - ax, py - ay) < min_dist || cn_norm_dot(px - agx, py - agy) < min_dist) {
-        collide = true; break;
-      }
-    }
-    if (!cn_any(co, collide) || tries >= CN_MAX_SPAWN_TRIES) {
-      sp.px = px; sp.py = py;
-      if (tries >= CN_MAX_SPAWN_TRIES && co.lane == 0) *overflow = 1;
-      break;
-    }
-  }
+  const CnCand c = cn_rejection_sample(p, s, rng, co, 0, n_present, -2, sp.rad, 0.0, overflow);
+  sp.px = c.x; sp.py = c.y;
   return sp;
 }
 
@@ -473,28 +525,9 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
     for (int i = 0; i < H; ++i) {
       if (s.vpref[i] == 0) continue;
       if (cn_rng_double(rng, co) <= p.goal_change_chance) {
-        double gx, gy;
-        for (int tries = 0;; ++tries) {
-          const double angle = cn_rng_double(rng, co) * CN_PI * 2;
-          const double vp = (s.vpref[i] == 0) ? 1.0 : s.vpref[i];
-          const double gx_noise = (cn_rng_double(rng, co) - 0.5) * vp;
-          const double gy_noise = (cn_rng_double(rng, co) - 0.5) * vp;
-          gx = p.circle_radius * cos(angle) + gx_noise;
-          gy = p.circle_radius * sin(angle) + gy_noise;
-          bool collide = false;
-          for (int k = -1 + co.lane; k < H; k += co.nlanes) {
-            if (k == i) continue;
-            double ax, ay, agx, agy, ar;
-            if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
-            else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
-            const double min_dist = s.rad[i] + ar + p.discomfort_dist;
-            if (cn_norm_dot(gx - ax, gy - ay) < min_dist || cn_norm_dot(gx - agx, gy - agy) < min_dist) {
-              collide = true; break;
-            }
-          }
-          if (!cn_any(co, collide)) break;
-          if (tries >= CN_MAX_SPAWN_TRIES) { if (co.lane == 0) g.spawn_overflow[e] = 1; break; }
-        }
+        const double vp = (s.vpref[i] == 0) ? 1.0 : s.vpref[i];
+        const CnCand c = cn_rejection_sample(p, s, rng, co, 1, H, i, s.rad[i], vp, g.spawn_overflow + e);
+        const double gx = c.x, gy = c.y;
         cn_coop_sync(co);
         if (co.lane == 0) { s.gx[i] = gx; s.gy[i] = gy; }
         cn_coop_sync(co);

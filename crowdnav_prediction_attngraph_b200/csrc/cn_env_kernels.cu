@@ -8,6 +8,7 @@
 // fp32 ORCA sequence and the fp64 reward/visibility tests must round exactly like the oracle).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -229,6 +230,7 @@ struct cn_env {
   cudaStream_t side;
   cudaEvent_t ev_step, ev_side;
   bool side_pending;      // an event kernel is in flight: the next launch on the caller's stream waits for it
+  bool use_side;
   bool prep_dirty;        // a state upload may have invalidated the prepared episodes
   // staging for the host-buffer entry point
   float* d_action;
@@ -311,6 +313,7 @@ int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const 
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel launch: %s", cudaGetErrorString(err));
+  if (!env->use_side) return event_kernel(env, 0, stream);      // CN_NO_SIDE_STREAM=1: everything in stream order
   err = cudaEventRecord(env->ev_step, stream);
   if (err == cudaSuccess) err = cudaStreamWaitEvent(env->side, env->ev_step, 0);
   if (err != cudaSuccess) return cn_set_error("fork to side stream: %s", cudaGetErrorString(err));
@@ -351,6 +354,10 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   env->launches = 0;
   env->side = nullptr; env->ev_step = nullptr; env->ev_side = nullptr;
   env->side_pending = false; env->prep_dirty = true;
+  {
+    const char* ns = getenv("CN_NO_SIDE_STREAM");       // debugging / profiling aid
+    env->use_side = !(ns && ns[0] == '1');
+  }
   err = cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->ev_step, cudaEventDisableTiming);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->ev_side, cudaEventDisableTiming);

@@ -143,6 +143,28 @@ CN_HD uint32_t cn_rng_u32(CnRng& r, const CnCoop& c) {
   return y;
 }
 
+// tempered output / random_sample() at a word offset AHEAD of the stream position, without consuming
+// (caller guarantees pos + off + 1 < 624: no twist inside the window)
+CN_HD uint32_t cn_rng_peek_u32(const CnRng& r, int off) {
+  uint32_t y = r.key[r.pos + off];
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+CN_HD double cn_rng_peek_double(const CnRng& r, int off) {
+  const uint32_t a = cn_rng_peek_u32(r, off) >> 5, b = cn_rng_peek_u32(r, off + 1) >> 6;
+  return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+}
+CN_HD double cn_bcast_d(const CnCoop& c, double v, int src) {
+#if defined(__CUDA_ARCH__)
+  if (c.nlanes > 1) return __shfl_sync(0xffffffffu, v, src);
+#endif
+  (void)src;
+  return v;
+}
+
 CN_HD double cn_rng_double(CnRng& r, const CnCoop& c) {
   const uint32_t a = cn_rng_u32(r, c) >> 5, b = cn_rng_u32(r, c) >> 6;
   return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;

@@ -162,16 +162,22 @@ class CudaCrowdVecEnv(object):
         # double-buffered observation tensors so a returned dict stays valid for one more step
         self._obs_bufs = [self._alloc_obs(dev) for _ in range(2)]
         self._flip = 0
-        self._out = dict(reward=torch.zeros(N, dtype=torch.float32, device=dev),
-                         done=torch.zeros(N, dtype=torch.uint8, device=dev),
-                         info=torch.zeros(N, dtype=torch.int32, device=dev),
-                         info_aux=torch.zeros(N, dtype=torch.float32, device=dev),
-                         ep_ret=torch.zeros(N, dtype=torch.float64, device=dev),
-                         ep_len=torch.zeros(N, dtype=torch.int32, device=dev))
+        # per-step results live in ONE packed device buffer (and one pinned host mirror) so that the
+        # reference-facing step() needs a single D2H copy: [ep_ret f64 | reward f32 | info i32 | info_aux f32 |
+        # ep_len i32 | done u8]
+        layout = [("ep_ret", torch.float64), ("reward", torch.float32), ("info", torch.int32),
+                  ("info_aux", torch.float32), ("ep_len", torch.int32), ("done", torch.uint8)]
+        total = sum(N * torch.empty(0, dtype=dt).element_size() for _, dt in layout)
+        self._out_packed = torch.zeros(total, dtype=torch.uint8, device=dev)
+        self._host_packed = torch.zeros(total, dtype=torch.uint8).pin_memory()
+        self._out, self._host, off = {}, {}, 0
+        for k, dt in layout:
+            nb = N * torch.empty(0, dtype=dt).element_size()
+            self._out[k] = self._out_packed[off:off + nb].view(dt)
+            self._host[k] = self._host_packed[off:off + nb].view(dt)
+            off += nb
         self._outp = _capi.CnStepPtrs(*[self._out[k].data_ptr() if k in self._out else None
                                         for k, _ in _capi.CnStepPtrs._fields_])
-        # one packed pinned host buffer for the per-step D2H of (reward, done, info, aux, ep_ret, ep_len)
-        self._host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in self._out.items()}
         self.closed = False
 
     def _alloc_obs(self, dev):
@@ -233,8 +239,7 @@ class CudaCrowdVecEnv(object):
 
     def step_wait(self):
         obs, _, _, _ = self._pending
-        for k, v in self._out.items():
-            self._host[k].copy_(v, non_blocking=True)
+        self._host_packed.copy_(self._out_packed, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         h = self._host
         reward = h["reward"].clone().unsqueeze(1)

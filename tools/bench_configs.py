@@ -1,0 +1,80 @@
+"""Informational device-rollout timings of BASELINE configs other than the bench line (bench.py times
+configs[1]).  Same zero-copy rollout step as bench.py `value`; CUDA events; one JSON line per config.
+
+    python tools/bench_configs.py [--steps 60] [--warmup 20] [--configs c2,c4]
+"""
+import argparse
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+CONFIGS = {
+    # name: (env kwargs, envs per GPU)
+    "c2": (dict(human_num=20), 4096),
+    "c4": (dict(human_num=50, randomize_attributes=1, random_goal_changing=1, goal_change_chance=0.5), 2048),
+    "c2_h50": (dict(human_num=50), 4096),
+    "c1_varnum": (dict(human_num=5, const_vel=0), 4096),
+}
+
+
+def run(name, steps, warmup):
+    import torch
+    from crowdnav_prediction_attngraph_b200.vec_env import CudaCrowdVecEnv
+    from crowdnav_prediction_attngraph_b200.policy import Policy
+    from crowdnav_prediction_attngraph_b200.storage import RolloutStorage
+    kw, N = CONFIGS[name]
+    dev = torch.device("cuda", 0)
+    env = CudaCrowdVecEnv(num_envs=N, nenv_total=N, rank_offset=0, seed=425, device=dev, **kw)
+
+    class Args(object):
+        num_processes, seq_length, num_mini_batch = N, 30, 2
+    torch.manual_seed(425)
+    policy = Policy(env.observation_space.spaces, env.action_space, base_kwargs=Args(), base='selfAttn_merge_srnn').to(dev)
+    rollouts = RolloutStorage(30, N, env.observation_space.spaces, env.action_space, 128, 256, device=dev)
+    obs = env.reset()
+    for k in rollouts.obs:
+        rollouts.obs[k][0].copy_(obs[k])
+    eng = policy._engine(N, dev)
+
+    def device_step():
+        rollouts.rollout_step_zero_copy(eng, env)
+        if rollouts.step == 0:
+            rollouts.after_update()
+
+    for _ in range(warmup):
+        device_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        device_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # env-only share: time the env step alone with the last actions
+    act = rollouts.actions[rollouts.step - 1 if rollouts.step else 0]
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        env.step_device(act)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_env = f0.elapsed_time(f1) / steps
+    overflow = int(env.get_state("spawn_overflow").sum())
+    print(json.dumps({"config": name, "env_kwargs": kw, "envs": N, "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3,
+                      "env_only_ms_per_step": ms_env, "valid_human_rows": int(eng.lib.cn_policy_last_rows(eng._h)),
+                      "spawn_overflow_envs": overflow}))
+    del eng, policy, env
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--configs", default="c2,c4")
+    a = ap.parse_args()
+    for c in a.configs.split(","):
+        run(c, a.steps, a.warmup)
