@@ -328,8 +328,13 @@ def run_ours(a):
                  "mma_flops_issued_per_launch": qkv_flops * (3 if a.gemm_mode == 1 else 1), "dense_rows": N * HUMANS}
     # environment step: algorithmic bytes per launch = B_env * N / CUDA-event time
     env_gbs = B_ENV * N / (env_ms / 1000.0) / 1e9 if env_ms > 0 else 0.0
-    roof_env = {"kernel": "cn_env_step_kernel + cn_env_reset_kernel (one rollout step of %d envs)" % N, "bound": "hbm",
-                "achieved": env_gbs, "peak": hbm, "unit": "GB/s", "frac": env_gbs / hbm, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch at N=4096, H=20 (ncu --set full,
+    # profiles/r1_env_step_kernel_summary.md, capture r1_env_step_v6): 11.24 MB + 0.45 MB
+    env_traffic = 11.69e6 * N / 4096.0 if HUMANS == 20 else None
+    roof_env = {"kernel": "cn_env_step_kernel (one rollout step of %d envs; cn_env_event_kernel runs on a side stream)" % N,
+                "bound": "hbm",
+                "achieved": env_gbs, "peak": hbm, "unit": "GB/s", "frac": env_gbs / hbm, "traffic": env_traffic,
+                "traffic_source": "ncu capture profiles/r1_env_step_kernel_summary.md (v6), scaled by N/4096",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", "launch_ms": env_ms,
                 "algorithmic_bytes_per_launch": B_ENV * N,
                 "note": "latency/divergence bound by construction (per-human ORCA LP), see DESIGN.md"}
@@ -341,7 +346,7 @@ def run_ours(a):
         "config": {"workload": "CrowdSimPred-v0 const_vel, 20 humans, HH+HR attention, %d envs per GPU (BASELINE configs[1])" % N,
                    "global_envs": total_envs, "rollout_T": ROLLOUT_T, "parallelism": "env-sharded dp%d" % world,
                    "weights": "random init (orthogonal), seed 425", "gemm_mode": a.gemm_mode,
-                   "l2": "per-step working set (policy activations ~1.2 GB at N=4096) exceeds the 126 MB L2; no flush needed"},
+                   "l2": "no flush: every step touches a different rollout-storage slot (30 slots x 4.3 MB of observations) plus ~170 MB of policy activations and 19 MB of env state, > the 126 MB L2"},
         "e2e": {"value": e2e, "unit": UNIT,
                 "h2d_bytes_per_step": N * 4 * 3,                 # masks + bad_masks + reward into the storage
                 "d2h_bytes_per_step": N * (4 + 1 + 4 + 4 + 8 + 4),   # reward, done, info, aux, ep_ret, ep_len

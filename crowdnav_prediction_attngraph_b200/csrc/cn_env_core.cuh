@@ -26,7 +26,7 @@
 #include "cn_orca.cuh"
 
 #define CN_PI 3.141592653589793
-#define CN_MAX_SPAWN_TRIES 4096
+#define CN_MAX_SPAWN_TRIES 20000
 
 CN_HD double cn_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
