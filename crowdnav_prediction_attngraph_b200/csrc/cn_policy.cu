@@ -12,6 +12,7 @@
 //              travel between layers as (hi, lo) fp16 pairs written by the producing kernel's epilogue.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -35,6 +36,7 @@ struct cn_policy {
   int64_t launches;
   int attn_hpc;        // heads per CTA of the HH attention kernel
   int num_sms;
+  int attn_qb;        // query rows per warp in the HH attention (CN_ATTN_QB, default 1)
   bool finalized;
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> allocs;
@@ -42,9 +44,10 @@ struct cn_policy {
   // device parameters (fp32 kernel layouts)
   float *W1, *b1, *W2, *b2, *Wqkv, *bqkv, *Wos, *bos;
   float *Wr, *br, *Wet, *bet, *WsT, *bs, *Wa, *ba, *Wih, *bih, *Whh, *bhh, *Wo, *bo;
+  float *Woac, *boac;      // (actor.0 | critic.0) o output_linear folded: 128 -> 512
   float *Wac1, *bac1, *Wa2, *ba2, *Wc2, *bc2, *wv_, *bv, *Wm, *bm, *logstd;
   // tcgen05 path: split weights (B operands; tile rows = 256 for per-human layers, 64 for per-env layers)
-  TcMat tW2, tWqkv, tWos, tWet, tWsT, tWa, tWih, tWhh, tWo, tWac1, tWa2, tWc2;
+  TcMat tW2, tWqkv, tWos, tWet, tWsT, tWa, tWih, tWhh, tWo, tWac1, tWoac, tWa2, tWc2;
   // tcgen05 path: split activations (A operands)
   TcMat tE1, tE2, tAo;                                  // per human rows
   TcMat tRs, tT1, tTe, tWv, tH0, tH1, tOut, tAc1, tA1, tC1;   // per environment rows (tTe / tA1 / tC1 = column views)
@@ -243,6 +246,10 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   p->launches = 0; p->finalized = false; p->profile = false;
   p->num_sms = 148;
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  {
+    const char* qb = getenv("CN_ATTN_QB");
+    p->attn_qb = (qb && qb[0] >= '1' && qb[0] <= '4') ? qb[0] - '0' : 1;
+  }
   cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
@@ -405,6 +412,8 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
   if (!rc) rc = palloc(p, &p->bqkv, 1536);
   if (!rc) rc = palloc(p, &p->Wos, (size_t)256 * 512);
   if (!rc) rc = palloc(p, &p->bos, 256);
+  if (!rc) rc = palloc(p, &p->Woac, (size_t)512 * 128);
+  if (!rc) rc = palloc(p, &p->boac, 512);
   if (rc) return rc;
   for (int i = 0; i < 3; ++i) {
     // Wf_i = Win_i (512x512) @ Wl_i (512x512);  bf_i = Win_i @ bl_i + bin_i
@@ -415,10 +424,15 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
   // Wos = Wsl (256x512) @ Wout (512x512);  bos = Wsl @ bout + bsl
   cn_fold_mm_kernel<<<dim3(4, 256), 128, 0, st>>>(d_wsl, d_wout, p->Wos, 256, 512, 512);
   cn_fold_mv_kernel<<<2, 128, 0, st>>>(d_wsl, d_bout, d_bsl, p->bos, 256, 512);
+  // Woac = [actor.0 ; critic.0] (512x256) @ output_linear (256x128);  boac = [actor.0 ; critic.0] @ bo + bac1
+  // (output_linear has no activation and feeds only the two MLPs, selfAttn_srnn_temp_node.py:438-447)
+  cn_fold_mm_kernel<<<dim3(1, 512), 128, 0, st>>>(p->Wac1, p->Wo, p->Woac, 512, 128, 256);
+  cn_fold_mv_kernel<<<4, 128, 0, st>>>(p->Wac1, p->bo, p->bac1, p->boac, 512, 256);
   if (p->cfg.gemm_mode == 1) {
     // fp16 (hi, lo) split of the tensor-core weights, pre-scaled by 2^6 (exact) so lo stays normal.
     // B-tile rows: 256 for the per-human layers (large M), 64 for the per-environment layers.
-    struct { float* src; TcMat* t; int rows, k, bn; } tw[12] = {
+    struct { float* src; TcMat* t; int rows, k, bn; } tw[13] = {
+        {p->Woac, &p->tWoac, 512, 128, 64},
         {p->W2, &p->tW2, 512, 128, 256},    {p->Wqkv, &p->tWqkv, 1536, 512, 256}, {p->Wos, &p->tWos, 256, 512, 256},
         {p->Wet, &p->tWet, 128, 256, 64},   {p->WsT, &p->tWsT, 256, 64, 64},      {p->Wa, &p->tWa, 64, 256, 64},
         {p->Wih, &p->tWih, 384, 128, 64},   {p->Whh, &p->tWhh, 384, 128, 64},     {p->Wo, &p->tWo, 256, 128, 64},
@@ -451,8 +465,9 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   // 0. compaction offsets, pack / pad inputs, h0 = h * mask
   {
     cn_row_offsets_kernel<<<1, 1024, 0, st>>>(d->detected_human_num, N, H, p->row_start, p->mc);
-    const int total = M * 16 > N * 128 ? M * 16 : N * 128;
-    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->row_env, p->x16,
+    const int total = (!tcm && M * 16 > N * 128) ? M * 16 : N * 128;
+    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->row_env,
+                                                               tcm ? nullptr : p->x16,
                                                                d->temporal_edges, d->robot_node, d->h_in, d->masks, p->xr,
                                                                p->h0, tcm ? p->tH0.hi : nullptr, tcm ? p->tH0.lo : nullptr);
     p->launches += 2;
@@ -475,8 +490,11 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   cudaEventRecord(p->ev_join, s2);
   // 1. human-human branch over the Mc = sum_e n_e valid rows (device-side count p->mc)
   mark(p, st, 1);
-  if (tcm) gemm(p, st, p->x16, 16, p->W1, 16, p->b1, nullptr, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc, p->tE1.hi, p->tE1.lo);
-  else gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc);
+  if (tcm) {
+    cn_embed1_kernel<<<p->num_sms * 6, 256, 0, st>>>(d->spatial_edges, p->Win, H, p->row_start, p->row_env, p->mc, p->W1, p->b1,
+                                                     p->tE1.hi, p->tE1.lo);
+    p->launches += 1;
+  } else gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc);
   mark(p, st, 2);
   if (tcm) gemm_tc(p, st, p->tE1, p->tW2, M, 512, 128, 256, p->b2, CN_ACT_RELU, out16(p->tE2), mc);
   else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU, 0, ALL, mc);
@@ -485,8 +503,10 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
   mark(p, st, 4);
   {
-    cn_hh_attention_kernel<<<p->num_sms * 8, 256, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, tcm ? nullptr : p->ao,
-                                                           tcm ? p->tAo.hi : nullptr, tcm ? p->tAo.lo : nullptr);
+    float* ao = tcm ? nullptr : p->ao;
+    __half* ah = tcm ? p->tAo.hi : nullptr;
+    __half* al = tcm ? p->tAo.lo : nullptr;
+    cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, ao, ah, al);
     p->launches += 1;
   }
   mark(p, st, 5);
@@ -515,16 +535,14 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   // 4. output_linear, actor / critic MLPs (critic.2 on the side stream), heads
   mark(p, st, 9);
   if (tcm) {
-    gemm_tc(p, st, p->tH1, p->tWo, N, 256, 128, 64, p->bo, CN_ACT_NONE, out16(p->tOut));
-    gemm_tc(p, st, p->tOut, p->tWac1, N, 512, 256, 64, p->bac1, CN_ACT_TANH, out16(p->tAc1));    // [actor.0 | critic.0]
+    gemm_tc(p, st, p->tH1, p->tWoac, N, 512, 128, 64, p->boac, CN_ACT_TANH, out16(p->tAc1));     // [actor.0 | critic.0]
     cudaEventRecord(p->ev_fork2, st);
     cudaStreamWaitEvent(s2, p->ev_fork2, 0);
     gemm_tc(p, s2, p->tC1, p->tWc2, N, 256, 256, 64, p->bc2, CN_ACT_TANH, out32(p->c2, 256));
     cudaEventRecord(p->ev_join2, s2);
     gemm_tc(p, st, p->tA1, p->tWa2, N, 256, 256, 64, p->ba2, CN_ACT_TANH, out32(p->a2, 256));
   } else {
-    gemm(p, st, d->h_out, 128, p->Wo, 128, p->bo, p->outb, 256, N, 256, 128, CN_ACT_NONE);
-    gemm(p, st, p->outb, 256, p->Wac1, 256, p->bac1, p->ac1, 512, N, 512, 256, CN_ACT_TANH);
+    gemm(p, st, d->h_out, 128, p->Woac, 128, p->boac, p->ac1, 512, N, 512, 128, CN_ACT_TANH);
     cudaEventRecord(p->ev_fork2, st);
     cudaStreamWaitEvent(s2, p->ev_fork2, 0);
     gemm(p, s2, p->ac1 + 256, 512, p->Wc2, 256, p->bc2, p->c2, 256, N, 256, 256, CN_ACT_TANH);
@@ -561,7 +579,7 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
   cn_policy tmp;
   tmp.launches = 0;
   tmp.st2 = nullptr;
-  tmp.num_sms = 148;
+  tmp.num_sms = 148; tmp.attn_qb = 1;
   cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, 0);
   TcMat A, B;
   int rc = tc_alloc(&tmp, A, M, K, TC_BM);

@@ -217,7 +217,7 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
                                       float* __restrict__ xr, float* __restrict__ h0, __half* __restrict__ h0_hi,
                                       __half* __restrict__ h0_lo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < N * H * 16) {
+  if (x16 && idx < N * H * 16) {
     const int r = idx >> 4, c = idx & 15;
     const int e = r / H, j = r - e * H;
     const int rs = row_start[e], n = row_start[e + 1] - rs;
@@ -225,6 +225,10 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
       x16[(size_t)(rs + j) * 16 + c] = c < Win ? spatial[(size_t)r * Win + c] : 0.0f;
       if (c == 0) row_env[rs + j] = e;
     }
+  }
+  if (!x16 && idx < N) {                  // tensor-core mode: row -> environment map of the compacted rows
+    const int rs = row_start[idx], n = row_start[idx + 1] - rs;
+    for (int j = 0; j < n; ++j) row_env[rs + j] = idx;
   }
   if (idx < N * 16) {
     const int e = idx >> 4, c = idx & 15;
@@ -246,92 +250,198 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
 }
 
 // ------------------------------------------------------------------------------------------
-// Human-human multi-head self attention for one (environment, head) per CTA.
-// qkv: [N*H, 1536] rows = (q | k | v), head hd uses columns hd*64..hd*64+63 of each third.
-// Keys j >= n_e are padding (key_padding_mask); query rows >= n_e are never consumed
-// downstream (their robot-human attention weight is exactly 0), they are written as zeros.
-__global__ void __launch_bounds__(256) cn_hh_attention_kernel(const float* __restrict__ qkv,
-                                                              const int* __restrict__ row_start,
-                                                              const int* __restrict__ row_env,
-                                                              const int* __restrict__ mc_ptr,
-                                                              float* __restrict__ out /* [Mc,512] or null */,
-                                                              __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  // One WARP per valid (compacted) human row = one attention query, all 8 heads at once.
-  // Every 512-float q / k / v / o row is touched with four fully coalesced LDG.128 per warp: lane l
-  // owns float4 #(l + 32 k), k = 0..3, i.e. elements 128 k + 4 l .. + 3, which belong to head
-  // 2 k + (l >= 16).  A key's score for head (2k + half) is the 4-FMA partial reduced over the 16 lanes
-  // of the half (4 xor-shuffles); soft-max runs online (running max / sum per head), nothing is staged.
+// First embedding layer of the human-human branch fused with the row compaction gather (tensor-core
+// mode): e1[row_start[e] + j] = relu(W1 spatial_edges[e, j] + b1) for j < n_e, written directly as the
+// fp16 (hi, lo) A operand of the next tcgen05 GEMM.  K = input width (12 or 2) is far too small for a
+// tensor-core tile: one warp per compacted human row, lane l owns outputs 4l..4l+3, the 128 x 16 weights sit
+// transposed in shared memory (conflict-free LDS.128), the input row is broadcast by shuffles, and each lane
+// issues one 8-byte store per half (256 B coalesced per warp).  Latency bound: sized for many resident warps.
+__global__ void __launch_bounds__(256) cn_embed1_kernel(const float* __restrict__ spatial, int Win, int H,
+                                                        const int* __restrict__ row_start, const int* __restrict__ row_env,
+                                                        const int* __restrict__ mc_ptr,
+                                                        const float* __restrict__ W1 /* [128][16], zero padded */,
+                                                        const float* __restrict__ b1, __half* __restrict__ e_hi,
+                                                        __half* __restrict__ e_lo /* [Mc,128] */) {
+  __shared__ __align__(16) float ws[16][128];        // transposed weights: ws[c][out]
+  for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) ws[i & 15][i >> 4] = W1[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + lane);
+  const int mc = *mc_ptr;
+  for (int r = gw; r < mc; r += nw) {
+    const int e = row_env[r];
+    const int j = r - row_start[e];
+    const float x = lane < Win ? __ldg(spatial + ((size_t)e * H + j) * Win + lane) : 0.0f;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float xc = __shfl_sync(0xffffffffu, x, c);
+      const float4 w = *reinterpret_cast<const float4*>(&ws[c][4 * lane]);
+      acc[0] = fmaf(xc, w.x, acc[0]); acc[1] = fmaf(xc, w.y, acc[1]);
+      acc[2] = fmaf(xc, w.z, acc[2]); acc[3] = fmaf(xc, w.w, acc[3]);
+    }
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ph[2], pl[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float c0 = acc[2 * t] + bb[2 * t], c1 = acc[2 * t + 1] + bb[2 * t + 1];
+      c0 = fminf(fmaxf(c0, 0.0f), 65504.0f); c1 = fminf(fmaxf(c1, 0.0f), 65504.0f);       // ReLU + fp16 range
+      const __half h0 = __float2half_rn(c0), h1 = __float2half_rn(c1);
+      const __half l0 = __float2half_rn(c0 - __half2float(h0)), l1 = __float2half_rn(c1 - __half2float(h1));
+      ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const size_t o = (size_t)r * 128 + 4 * lane;
+    *reinterpret_cast<uint2*>(e_hi + o) = make_uint2(ph[0], ph[1]);
+    *reinterpret_cast<uint2*>(e_lo + o) = make_uint2(pl[0], pl[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Human-human multi-head self attention over the compacted rows.
+// qkv: [Mc, 1536] rows = (q | k | v), head hd uses columns hd*64..hd*64+63 of each third.
+// Only valid humans have rows (keys j >= n_e of the reference's key_padding_mask do not exist here).
+//
+// One WARP per query row, all 8 heads at once.  Every 512-float q / k / v / o row is touched with four
+// fully coalesced LDG.128 per warp: lane l owns float4 #(l + 32 c), c = 0..3, i.e. elements
+// 128 c + 4 l .. + 3, which belong to head 2 c + (l >= 16).  The kernel was instruction-issue bound
+// (ncu: 3 200 warp instructions per query, 59 % issue active) on redundant work: every lane reduced and
+// exponentiated all four of its heads.  Now
+//  * the four per-lane partial dot products are reduced over the 16 lanes of a half with a PACKED
+//    butterfly (2 + 1 + 2 shuffles instead of 16): afterwards lane l holds the complete score of ONE
+//    head chunk own = 2 (l & 1) + ((l >> 1) & 1), so each lane exponentiates one head, not four;
+//  * soft-max is two-pass (pass 1: scores -> shared memory + running max; pass 2: p = exp(s - max),
+//    P V): one exp per (key, head) and no rescaling of the accumulators;
+//  * the p of the other three chunks come from the neighbouring lanes of the aligned 4-lane group.
+// K (pass 1) and V (pass 2) rows are software-pipelined one key ahead.
+#define CN_ATTN_WARPS 4
+#define CN_ATTN_MAXKEYS 128
+__global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(const float* __restrict__ qkv,
+                                                                             const int* __restrict__ row_start,
+                                                                             const int* __restrict__ row_env,
+                                                                             const int* __restrict__ mc_ptr,
+                                                                             float* __restrict__ out /* [Mc,512] or null */,
+                                                                             __half* __restrict__ out_hi,
+                                                                             __half* __restrict__ out_lo) {
+  __shared__ float sc[CN_ATTN_WARPS][CN_ATTN_MAXKEYS][8];       // scores [key][half * 4 + chunk]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mc = *mc_ptr;
-  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int nwarps = gridDim.x * CN_ATTN_WARPS;
   const float scale = 0.125f;   // 1/sqrt(head_dim = 64); torch scales q before q k^T
+  const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+  const int own = (b0 ? 2 : 0) + (b1 ? 1 : 0);                  // head chunk this lane finishes
+  const int col = ((lane >> 4) << 2) + own;                     // its column in sc[][][8]
+  const int grp = lane & ~3;
+  float (*myc)[8] = sc[warp];
   // grid-stride over the compacted rows: the launch is sized to the machine, not to the worst case
-  for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < mc; r += nwarps) {
+  for (int r = blockIdx.x * CN_ATTN_WARPS + warp; r < mc; r += nwarps) {
     const int e = row_env[r];
-    const size_t row0 = (size_t)row_start[e];
-    const int n = row_start[e + 1] - row_start[e];
-    float4 q[4], acc[4];
-    float m[4], l[4];
+    const int row0 = row_start[e];
+    const int n = row_start[e + 1] - row0;
+    float4 q[4];
     {
       const float4* qv = reinterpret_cast<const float4*>(qkv + (size_t)r * 1536) + lane;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 a = __ldg(qv + 32 * k);
-        q[k] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
-        acc[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        m[k] = -INFINITY; l[k] = 0.0f;
+      for (int c = 0; c < 4; ++c) {
+        const float4 a = __ldg(qv + 32 * c);
+        q[c] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
       }
+    }
+    // ---- pass 1: scores
+    float m = -INFINITY;
+    float4 nx[4];
+    {
+      const float4* kv = reinterpret_cast<const float4*>(qkv + (size_t)row0 * 1536 + 512) + lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) nx[c] = __ldg(kv + 32 * c);
     }
     for (int j = 0; j < n; ++j) {
-      const float4* kv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 512) + lane;
-      const float4* vv = reinterpret_cast<const float4*>(qkv + (row0 + j) * 1536 + 1024) + lane;
-      float4 kr[4], vr[4];
+      float4 kr[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { kr[k] = __ldg(kv + 32 * k); vr[k] = __ldg(vv + 32 * k); }
+      for (int c = 0; c < 4; ++c) kr[c] = nx[c];
+      if (j + 1 < n) {
+        const float4* kv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j + 1) * 1536 + 512) + lane;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float s = q[k].x * kr[k].x;
-        s = fmaf(q[k].y, kr[k].y, s); s = fmaf(q[k].z, kr[k].z, s); s = fmaf(q[k].w, kr[k].w, s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);        // all 16 lanes of the half hold the head's score
-        const float mn = fmaxf(m[k], s);
-        const float corr = expf(m[k] - mn);              // exp(-inf) = 0 on the first key
-        const float pj = expf(s - mn);
-        l[k] = l[k] * corr + pj;
-        acc[k].x = fmaf(pj, vr[k].x, acc[k].x * corr); acc[k].y = fmaf(pj, vr[k].y, acc[k].y * corr);
-        acc[k].z = fmaf(pj, vr[k].z, acc[k].z * corr); acc[k].w = fmaf(pj, vr[k].w, acc[k].w * corr);
-        m[k] = mn;
+        for (int c = 0; c < 4; ++c) nx[c] = __ldg(kv + 32 * c);
+      }
+      float s[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t = q[c].x * kr[c].x;
+        t = fmaf(q[c].y, kr[c].y, t); t = fmaf(q[c].z, kr[c].z, t); t = fmaf(q[c].w, kr[c].w, t);
+        s[c] = t;
+      }
+      // packed butterfly over the 16 lanes of the half: 4 values -> 1 per lane
+      const float x0 = b0 ? s[0] : s[2], x1 = b0 ? s[1] : s[3];                 // what the xor-1 partner keeps
+      const float r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
+      const float u0 = (b0 ? s[2] : s[0]) + r0, u1 = (b0 ? s[3] : s[1]) + r1;   // chunks (2 b0, 2 b0 + 1) over 2 lanes
+      const float y = b1 ? u0 : u1;
+      float v = (b1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, y, 2);            // chunk `own` over 4 lanes
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);                                  // ... over the 16 lanes of the half
+      m = fmaxf(m, v);
+      if ((lane & 12) == 0) myc[j][col] = v;                                    // lanes 0-3 and 16-19
+    }
+    __syncwarp();
+    // ---- pass 2: p = exp(s - max), accumulate P V
+    float4 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float l = 0.0f;
+    {
+      const float4* vv = reinterpret_cast<const float4*>(qkv + (size_t)row0 * 1536 + 1024) + lane;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) nx[c] = __ldg(vv + 32 * c);
+    }
+    for (int j = 0; j < n; ++j) {
+      float4 vr[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vr[c] = nx[c];
+      if (j + 1 < n) {
+        const float4* vv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j + 1) * 1536 + 1024) + lane;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) nx[c] = __ldg(vv + 32 * c);
+      }
+      const float p = expf(myc[j][col] - m);
+      l += p;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // chunk c was finished by the lane of this 4-lane group with (b0, b1) = (c >> 1, c & 1)
+        const float pc = __shfl_sync(0xffffffffu, p, grp | (c >> 1) | ((c & 1) << 1));
+        acc[c].x = fmaf(pc, vr[c].x, acc[c].x); acc[c].y = fmaf(pc, vr[c].y, acc[c].y);
+        acc[c].z = fmaf(pc, vr[c].z, acc[c].z); acc[c].w = fmaf(pc, vr[c].w, acc[c].w);
       }
     }
+    __syncwarp();                                      // sc is reused by this warp's next row
+    const float linv = 1.0f / l;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float inv = 1.0f / l[k];
-      acc[k].x *= inv; acc[k].y *= inv; acc[k].z *= inv; acc[k].w *= inv;
+    for (int c = 0; c < 4; ++c) {
+      const float inv = __shfl_sync(0xffffffffu, linv, grp | (c >> 1) | ((c & 1) << 1));
+      acc[c].x *= inv; acc[c].y *= inv; acc[c].z *= inv; acc[c].w *= inv;
     }
     if (out) {
       float4* dst = reinterpret_cast<float4*>(out + (size_t)r * 512) + lane;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) dst[32 * k] = acc[k];
+      for (int c = 0; c < 4; ++c) dst[32 * c] = acc[c];
     }
     if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
       uint2* dh = reinterpret_cast<uint2*>(out_hi + (size_t)r * 512) + lane;
       uint2* dl = reinterpret_cast<uint2*>(out_lo + (size_t)r * 512) + lane;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float c[4] = {fminf(fmaxf(acc[k].x, -65504.0f), 65504.0f), fminf(fmaxf(acc[k].y, -65504.0f), 65504.0f),
-                            fminf(fmaxf(acc[k].z, -65504.0f), 65504.0f), fminf(fmaxf(acc[k].w, -65504.0f), 65504.0f)};
+      for (int c = 0; c < 4; ++c) {
+        const float cv[4] = {fminf(fmaxf(acc[c].x, -65504.0f), 65504.0f), fminf(fmaxf(acc[c].y, -65504.0f), 65504.0f),
+                             fminf(fmaxf(acc[c].z, -65504.0f), 65504.0f), fminf(fmaxf(acc[c].w, -65504.0f), 65504.0f)};
         uint32_t ph[2], pl[2];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const __half h0 = __float2half_rn(c[2 * t]), h1 = __float2half_rn(c[2 * t + 1]);
-          const __half l0 = __float2half_rn(c[2 * t] - __half2float(h0)), l1 = __float2half_rn(c[2 * t + 1] - __half2float(h1));
-          ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int u = 0; u < 2; ++u) {
+          const __half h0 = __float2half_rn(cv[2 * u]), h1 = __float2half_rn(cv[2 * u + 1]);
+          const __half l0 = __float2half_rn(cv[2 * u] - __half2float(h0)), l1 = __float2half_rn(cv[2 * u + 1] - __half2float(h1));
+          ph[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          pl[u] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
-        dh[32 * k] = make_uint2(ph[0], ph[1]);
-        dl[32 * k] = make_uint2(pl[0], pl[1]);
+        dh[32 * c] = make_uint2(ph[0], ph[1]);
+        dl[32 * c] = make_uint2(pl[0], pl[1]);
       }
     }
   }   // row loop
