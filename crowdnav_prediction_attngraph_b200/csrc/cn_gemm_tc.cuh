@@ -25,14 +25,17 @@
 #define TC_BM 128
 #define TC_BK 64
 #define TC_A_TILE_BYTES (TC_BM * TC_BK * 2)           // 16 KB
-#define TC_THREADS 192
+#define TC_EPI_WARPS 8          // two per TMEM lane quadrant, each draining half of the tile's columns
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)
 
 template <int BN>
 struct TcCfg {
   static constexpr int kStages = (BN >= 256) ? 2 : 4;
   static constexpr int kBTile = BN * TC_BK * 2;
   static constexpr int kStageBytes = 2 * TC_A_TILE_BYTES + 2 * kBTile;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  // + per-epilogue-warp 4 KB staging slab for the TMA stores (fp32 32x32 box, or fp16 hi + lo 32x32 boxes)
+  static constexpr int kStageOutOff = kStages * kStageBytes + 2048;       // barriers (256) + bias (1024), 1024-aligned
+  static constexpr int kSmemBytes = kStageOutOff + TC_EPI_WARPS * 4096 + 1024 /*align slack*/;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -47,6 +50,8 @@ struct TcEpilogue {
   __half* out_lo;
   int ldh;
   const int* m_ptr;      // optional device-side row count (compacted rows); tiles past it exit
+  int dbg_nostore;       // diagnostic: run the epilogue arithmetic but skip the global stores
+  const int* m0_ptr;     // optional device-side first row: the launch covers rows [*m0_ptr, *m_ptr) (row chunks)
 };
 
 namespace tc {
@@ -74,6 +79,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// TMA store of a shared-memory box to global memory (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -128,11 +145,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
-                  const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, int M, int N,
-                  int K, TcEpilogue ep) {
+                  const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                  const __grid_constant__ CUtensorMap map_c32, const __grid_constant__ CUtensorMap map_ohi,
+                  const __grid_constant__ CUtensorMap map_olo, int M, int N, int K, TcEpilogue ep) {
   if (ep.m_ptr) { const int mc = *ep.m_ptr; M = mc < M ? mc : M; }
+  int m_lo = ep.m0_ptr ? *ep.m0_ptr : 0;
+  if (m_lo > M) m_lo = M;
   const int n_ntiles = N / BN;
-  const int n_tiles = ((M + TC_BM - 1) / TC_BM) * n_ntiles;
+  const int n_tiles = ((M - m_lo + TC_BM - 1) / TC_BM) * n_ntiles;
   if ((int)blockIdx.x >= n_tiles) return;           // uniform for the whole CTA: before any barrier / TMEM use
   constexpr int TC_STAGES = TcCfg<BN>::kStages;
   constexpr int TC_B_TILE_BYTES = TcCfg<BN>::kBTile;
@@ -158,13 +178,18 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(bar_tfull + 8 * b, 1);        // accumulator b complete (tcgen05.commit)
-      tc::mbar_init(bar_tempty + 8 * b, 4);       // accumulator b drained (one arrive per epilogue warp)
+      tc::mbar_init(bar_tempty + 8 * b, TC_EPI_WARPS);   // accumulator b drained (one arrive per epilogue warp)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ahi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_alo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+    if (ep.c32) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c32) : "memory");
+    if (ep.out_hi) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ohi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_olo) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_ptr_smem)),
@@ -181,7 +206,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
     if (lane == 0) {
       uint32_t it = 0;                                            // running k-block counter across tiles
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
+        const int m0 = m_lo + (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
           tc::mbar_wait(bar_empty + 8 * s, ph ^ 1u);              // slot free (first pass returns immediately)
@@ -229,29 +254,30 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                                       // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;                            // which half of the tile's 32-column chunks
+    constexpr int kChunks = TC_BN / 32 / (TC_EPI_WARPS / 4);
+    const uint32_t stage_out = base + TcCfg<BN>::kStageOutOff + (uint32_t)(warp - 2) * 4096u;   // 1024-byte aligned
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
+      const int m0 = m_lo + (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
       const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
       tc::mbar_wait(bar_tfull + 8 * ab, aph);
       tc::tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + ab * TcCfg<BN>::kTmemCols;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
       // stage this tile's bias slice in shared memory once (epilogue warps only: named barrier 1)
       float* bias_s = reinterpret_cast<float*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + 256);
       {
-        const int et = threadIdx.x - 64;                          // 0..127 within the epilogue warps
-        asm volatile("bar.sync 1, 128;" ::: "memory");            // previous tile's readers are done
-        for (int c = et; c < TC_BN; c += 128) bias_s[c] = ep.bias ? __ldg(ep.bias + n0 + c) : 0.0f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = threadIdx.x - 64;                          // index within the epilogue warps
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // previous tile's readers are done
+        for (int c = et; c < TC_BN; c += 32 * TC_EPI_WARPS) bias_s[c] = ep.bias ? __ldg(ep.bias + n0 + c) : 0.0f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
       // activation is uniform over the tile unless the [act_lo, act_hi) window cuts through it
       const bool act_full = ep.act_lo <= n0 && ep.act_hi >= n0 + TC_BN;
       const bool act_none = ep.act == 0 || ep.act_hi <= n0 || ep.act_lo >= n0 + TC_BN;
       const int act_mode = act_none ? 0 : (act_full ? ep.act : 3);
 #pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
+      for (int c = chalf * kChunks; c < (chalf + 1) * kChunks; ++c) {
         uint32_t r[32];
         tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
         const int nb = n0 + c * 32;
@@ -271,15 +297,28 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
             if (nb + j >= ep.act_lo && nb + j < ep.act_hi) v[j] = (ep.act == 1) ? fmaxf(v[j], 0.0f) : tc::fast_tanh(v[j]);
           }
         }
-        if (row_ok) {
+        // Results leave through shared memory and the TMA store engine: the thread = row layout of
+        // tcgen05.ld would make every direct STG.128 touch 32 different cache lines (measured: the stores
+        // were ~1/3 of the QKV kernel).  Each warp stages its 32 x 32 slab in a private swizzled buffer
+        // (conflict-free 16-byte st.shared) and one lane issues the bulk tensor store; rows past the
+        // tensor's extent are clipped by the TMA unit.
+        if (!ep.dbg_nostore) {
           if (ep.c32) {
-            float4* dst = reinterpret_cast<float4*>(ep.c32 + (size_t)row * ep.ldc + nb);
+            if (lane == 0) tc::tma_store_wait_read();            // previous slab has left the staging buffer
+            __syncwarp();
+            const uint32_t rowb = stage_out + (uint32_t)lane * 128u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)                          // SWIZZLE_128B: 16-byte chunk j of row r sits at j ^ (r & 7)
+              tc::st_shared_v4(rowb + (uint32_t)((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]),
+                               __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { tc::tma_store_2d(&map_c32, stage_out, nb, m0 + q * 32); tc::tma_store_commit(); }
           }
           if (ep.out_hi) {
-            uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + (size_t)row * ep.ldh + nb);
-            uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + (size_t)row * ep.ldh + nb);
+            if (lane == 0) tc::tma_store_wait_read();
+            __syncwarp();
+            const uint32_t rowh = stage_out + (uint32_t)lane * 64u, rowl = rowh + 2048u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t ph[4], pl[4];
@@ -292,8 +331,16 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
                 ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
                 pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
               }
-              dh[j] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              dl[j] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              const uint32_t sw = (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);   // SWIZZLE_64B: chunk j of row r at j ^ ((r >> 1) & 3)
+              tc::st_shared_v4(rowh + sw, ph[0], ph[1], ph[2], ph[3]);
+              tc::st_shared_v4(rowl + sw, pl[0], pl[1], pl[2], pl[3]);
+            }
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tc::tma_store_2d(&map_ohi, stage_out, nb, m0 + q * 32);
+              tc::tma_store_2d(&map_olo, stage_out + 2048u, nb, m0 + q * 32);
+              tc::tma_store_commit();
             }
           }
         }
@@ -303,6 +350,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8 * ab) : "memory");
     }
+    if (lane == 0) tc::tma_store_wait_all();                    // bulk stores of this thread are complete before exit
   }
   tc::tcgen05_fence_before();
   __syncthreads();

@@ -36,7 +36,8 @@ struct cn_policy {
   int64_t launches;
   int attn_hpc;        // heads per CTA of the HH attention kernel
   int num_sms;
-  int attn_qb;        // query rows per warp in the HH attention (CN_ATTN_QB, default 1)
+  bool launch_error;  // a GEMM output map could not be built (cn_last_error has the reason)
+  int qkv_chunks;     // 1 (default): single pass; 2 (CN_QKV_CHUNKS=2): QKV + attention in two row chunks with overlap
   bool finalized;
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> allocs;
@@ -53,11 +54,14 @@ struct cn_policy {
   TcMat tRs, tT1, tTe, tWv, tH0, tH1, tOut, tAc1, tA1, tC1;   // per environment rows (tTe / tA1 / tC1 = column views)
   // second stream: the robot branch / gh / critic.2 are independent of the per-human chain and run
   // concurrently with it (fork / join with events; capturable in a CUDA graph)
-  cudaStream_t st2;
-  cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
+  cudaStream_t st2, st3;
+  cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2, ev_fork3, ev_join3;
   // optional per-stage profiling
   bool profile;
   std::vector<cudaEvent_t> ev;
+  // cached TMA store maps of GEMM outputs: key = (pointer, element size, columns, rows, leading dimension)
+  struct OutMap { const void* ptr; int esize, cols, rows, ld; CUtensorMap map; };
+  std::vector<OutMap*> omaps;
   // workspace
   int *row_start, *row_env, *mc;
   float *x16, *e1, *e2, *qkv, *ao, *sout, *xr, *rs, *t1, *u, *wv, *h0, *gi, *gh, *outb, *ac1, *a2, *c2;
@@ -124,6 +128,32 @@ int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows,
   return 0;
 }
 
+// TMA store map of a row-major output [rows, cols] (leading dimension ld elements): box 32 x 32, swizzle
+// matching the epilogue's staging layout (fp32: 128-byte rows -> SWIZZLE_128B; fp16: 64-byte rows -> SWIZZLE_64B)
+const CUtensorMap* out_map(cn_policy* p, const void* ptr, int esize, int cols, int rows, int ld) {
+  for (auto* m : p->omaps)
+    if (m->ptr == ptr && m->esize == esize && m->cols == cols && m->rows == rows && m->ld == ld) return &m->map;
+  EncodeFn enc = get_encode();
+  if (!enc) { cn_set_error("cuTensorMapEncodeTiled entry point not available"); return nullptr; }
+  auto* m = new cn_policy::OutMap();
+  m->ptr = ptr; m->esize = esize; m->cols = cols; m->rows = rows; m->ld = ld;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * (cuuint64_t)esize};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&m->map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   esize == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cn_set_error("cuTensorMapEncodeTiled(out) failed (%d) cols=%d rows=%d ld=%d esize=%d", (int)r, cols, rows, ld, esize);
+    delete m;
+    return nullptr;
+  }
+  p->omaps.push_back(m);
+  return &m->map;
+}
+
 int halloc16(cn_policy* p, __half** ptr, size_t count) {
   float* q = nullptr;
   int rc = palloc(p, &q, (count + 1) / 2);
@@ -159,17 +189,29 @@ struct TcOut {
   __half *oh = nullptr, *ol = nullptr; int ldh = 0;
 };
 void gemm_tc(cn_policy* p, cudaStream_t st, const TcMat& A, const TcMat& B, int M, int N, int K, int bn, const float* bias,
-             int act, const TcOut& o, const int* m_ptr = nullptr, int act_lo = 0, int act_hi = 1 << 30) {
+             int act, const TcOut& o, const int* m_ptr = nullptr, int act_lo = 0, int act_hi = 1 << 30,
+             const int* m0_ptr = nullptr) {
   TcEpilogue ep;
   ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.act_lo = act_lo; ep.act_hi = act_hi;
-  ep.c32 = o.c32; ep.ldc = o.ldc; ep.out_hi = o.oh; ep.out_lo = o.ol; ep.ldh = o.ldh; ep.m_ptr = m_ptr;
+  ep.c32 = o.c32; ep.ldc = o.ldc; ep.out_hi = o.oh; ep.out_lo = o.ol; ep.ldh = o.ldh; ep.m_ptr = m_ptr; ep.m0_ptr = m0_ptr;
+  {
+    static const int nostore = (getenv("CN_DBG_NOSTORE") && getenv("CN_DBG_NOSTORE")[0] == '1') ? 1 : 0;
+    ep.dbg_nostore = nostore;
+  }
   // persistent: one CTA per SM at most; tiles beyond the device-side row count are never touched
   const int tiles = (N / bn) * ((M + TC_BM - 1) / TC_BM);
   dim3 grid(tiles < p->num_sms ? tiles : p->num_sms);
+  // TMA store maps of the outputs (cached; unused ones alias an operand map and are never dereferenced)
+  const CUtensorMap* mc32 = o.c32 ? out_map(p, o.c32, 4, N, M, o.ldc) : &A.mh;
+  const CUtensorMap* mhi = o.oh ? out_map(p, o.oh, 2, N, M, o.ldh) : &A.mh;
+  const CUtensorMap* mlo = o.ol ? out_map(p, o.ol, 2, N, M, o.ldh) : &A.mh;
+  if (!mc32 || !mhi || !mlo) { p->launch_error = true; return; }
   if (bn == 256)
-    cn_gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, M, N, K, ep);
+    cn_gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, *mc32, *mhi, *mlo, M, N,
+                                                                             K, ep);
   else
-    cn_gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, M, N, K, ep);
+    cn_gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, *mc32, *mhi, *mlo, M, N, K,
+                                                                           ep);
   p->launches += 1;
 }
 TcOut out32(float* c, int ldc) { TcOut o; o.c32 = c; o.ldc = ldc; return o; }
@@ -243,14 +285,17 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   cn_policy* p = new cn_policy();
   p->cfg = *cfg;
   p->N = cfg->num_envs; p->H = cfg->human_num; p->Win = cfg->input_size; p->M = p->N * p->H;
-  p->launches = 0; p->finalized = false; p->profile = false;
+  p->launches = 0; p->finalized = false; p->profile = false; p->launch_error = false;
   p->num_sms = 148;
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   {
-    const char* qb = getenv("CN_ATTN_QB");
-    p->attn_qb = (qb && qb[0] >= '1' && qb[0] <= '4') ? qb[0] - '0' : 1;
+    const char* qc = getenv("CN_QKV_CHUNKS");
+    p->qkv_chunks = (qc && qc[0] == '2') ? 2 : 1;
   }
   cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&p->st3, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&p->ev_fork3, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&p->ev_join3, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming);
@@ -300,9 +345,11 @@ int cn_policy_destroy(cn_policy* p) {
   if (!p) return 0;
   cudaSetDevice(p->cfg.device);
   for (void* q : p->allocs) cudaFree(q);
+  for (auto* m : p->omaps) delete m;
   for (auto& e : p->ev) cudaEventDestroy(e);
   if (p->st2) {
     cudaStreamDestroy(p->st2);
+    cudaStreamDestroy(p->st3); cudaEventDestroy(p->ev_fork3); cudaEventDestroy(p->ev_join3);
     cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); cudaEventDestroy(p->ev_fork2); cudaEventDestroy(p->ev_join2);
   }
   delete p;
@@ -499,14 +546,38 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   if (tcm) gemm_tc(p, st, p->tE1, p->tW2, M, 512, 128, 256, p->b2, CN_ACT_RELU, out16(p->tE2), mc);
   else gemm(p, st, p->e1, 128, p->W2, 128, p->b2, p->e2, 512, M, 512, 128, CN_ACT_RELU, 0, ALL, mc);
   mark(p, st, 3);
-  if (tcm) gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc);
-  else gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
-  mark(p, st, 4);
-  {
-    float* ao = tcm ? nullptr : p->ao;
-    __half* ah = tcm ? p->tAo.hi : nullptr;
-    __half* al = tcm ? p->tAo.lo : nullptr;
-    cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, ao, ah, al);
+  if (tcm) {
+    // Optional experiment (CN_QKV_CHUNKS=2): QKV projection + attention in two row chunks split at an environment
+    // boundary so that chunk 0's attention (side stream) overlaps chunk 1's GEMM.  Measured on B200: no gain
+    // (0.516 vs 0.505 ms/step) -- the attention is load-latency bound, not L2-capacity bound -- so it is off.
+    const int* mid = p->row_start + N / 2;
+    __half* ah = p->tAo.hi;
+    __half* al = p->tAo.lo;
+    if (p->qkv_chunks == 1) {
+      gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc);
+      mark(p, st, 4);
+      cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, mc, nullptr,
+                                                                             nullptr, ah, al);
+      p->launches += 1;
+    } else {
+    gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mid);
+    cudaEventRecord(p->ev_fork3, st);
+    cudaStreamWaitEvent(p->st3, p->ev_fork3, 0);
+    cn_hh_attention_kernel<<<p->num_sms * 8, CN_ATTN_WARPS * 32, 0, p->st3>>>(p->qkv, p->row_start, p->row_env, mid, nullptr,
+                                                                              nullptr, ah, al);
+    cudaEventRecord(p->ev_join3, p->st3);
+    gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc, 0, 1 << 30, mid);
+    mark(p, st, 4);
+    cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, mc, mid, nullptr,
+                                                                           ah, al);
+    cudaStreamWaitEvent(st, p->ev_join3, 0);
+    p->launches += 2;
+    }
+  } else {
+    gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
+    mark(p, st, 4);
+    cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, nullptr,
+                                                                           p->ao, nullptr, nullptr);
     p->launches += 1;
   }
   mark(p, st, 5);
@@ -556,6 +627,7 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   mark(p, st, kNumStages);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_policy_act launch: %s", cudaGetErrorString(err));
+  if (p->launch_error) { p->launch_error = false; return 1; }
   return 0;
 }
 
@@ -578,8 +650,8 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
     return cn_set_error("cn_internal_gemm_tc: need bn in {64,256}, N %% bn == 0 and K %% 64 == 0");
   cn_policy tmp;
   tmp.launches = 0;
-  tmp.st2 = nullptr;
-  tmp.num_sms = 148; tmp.attn_qb = 1;
+  tmp.st2 = nullptr; tmp.st3 = nullptr;
+  tmp.num_sms = 148; tmp.qkv_chunks = 1; tmp.launch_error = false;
   cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, 0);
   TcMat A, B;
   int rc = tc_alloc(&tmp, A, M, K, TC_BM);
@@ -591,8 +663,10 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
     gemm_tc(&tmp, 0, A, B, M, N, K, bn, dbias, act, out32(dC, N));
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) rc = cn_set_error("cn_internal_gemm_tc: %s", cudaGetErrorString(err));
+    else if (tmp.launch_error) rc = 1;
   }
   for (void* q : tmp.allocs) cudaFree(q);
+  for (auto* m : tmp.omaps) delete m;
   return rc;
 }
 

@@ -314,13 +314,14 @@ __global__ void __launch_bounds__(256) cn_embed1_kernel(const float* __restrict_
 //  * soft-max is two-pass (pass 1: scores -> shared memory + running max; pass 2: p = exp(s - max),
 //    P V): one exp per (key, head) and no rescaling of the accumulators;
 //  * the p of the other three chunks come from the neighbouring lanes of the aligned 4-lane group.
-// K (pass 1) and V (pass 2) rows are software-pipelined one key ahead.
 #define CN_ATTN_WARPS 4
 #define CN_ATTN_MAXKEYS 128
+#define CN_ATTN_KB 4          // keys whose rows are in flight together
 __global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(const float* __restrict__ qkv,
                                                                              const int* __restrict__ row_start,
                                                                              const int* __restrict__ row_env,
                                                                              const int* __restrict__ mc_ptr,
+                                                                             const int* __restrict__ r0_ptr /* first row or null */,
                                                                              float* __restrict__ out /* [Mc,512] or null */,
                                                                              __half* __restrict__ out_hi,
                                                                              __half* __restrict__ out_lo) {
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(con
   const int grp = lane & ~3;
   float (*myc)[8] = sc[warp];
   // grid-stride over the compacted rows: the launch is sized to the machine, not to the worst case
-  for (int r = blockIdx.x * CN_ATTN_WARPS + warp; r < mc; r += nwarps) {
+  const int r_first = r0_ptr ? *r0_ptr : 0;                    // row chunk [r_first, mc) of this launch
+  for (int r = r_first + blockIdx.x * CN_ATTN_WARPS + warp; r < mc; r += nwarps) {
     const int e = row_env[r];
     const int row0 = row_start[e];
     const int n = row_start[e + 1] - row0;
@@ -348,40 +350,41 @@ __global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(con
         q[c] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
       }
     }
-    // ---- pass 1: scores
+    // ---- pass 1: scores.  Keys are processed in blocks of CN_ATTN_KB with all of a block's K rows requested
+    // before the first is used: the kernel is load-latency bound (ncu: long-scoreboard stalls = 70 % of the
+    // issue latency at ~4 keys per query), so memory-level parallelism matters more than instruction count.
     float m = -INFINITY;
-    float4 nx[4];
-    {
-      const float4* kv = reinterpret_cast<const float4*>(qkv + (size_t)row0 * 1536 + 512) + lane;
+    for (int jb = 0; jb < n; jb += CN_ATTN_KB) {
+      float4 kr[CN_ATTN_KB][4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) nx[c] = __ldg(kv + 32 * c);
-    }
-    for (int j = 0; j < n; ++j) {
-      float4 kr[4];
+      for (int t = 0; t < CN_ATTN_KB; ++t) {
+        const int j = (jb + t < n) ? jb + t : n - 1;             // clamped: the duplicate load hits L1
+        const float4* kv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j) * 1536 + 512) + lane;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) kr[c] = nx[c];
-      if (j + 1 < n) {
-        const float4* kv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j + 1) * 1536 + 512) + lane;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) nx[c] = __ldg(kv + 32 * c);
+        for (int c = 0; c < 4; ++c) kr[t][c] = __ldg(kv + 32 * c);
       }
-      float s[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float t = q[c].x * kr[c].x;
-        t = fmaf(q[c].y, kr[c].y, t); t = fmaf(q[c].z, kr[c].z, t); t = fmaf(q[c].w, kr[c].w, t);
-        s[c] = t;
+      for (int t = 0; t < CN_ATTN_KB; ++t) {
+        if (jb + t < n) {                                        // warp-uniform
+          float s[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float x = q[c].x * kr[t][c].x;
+            x = fmaf(q[c].y, kr[t][c].y, x); x = fmaf(q[c].z, kr[t][c].z, x); x = fmaf(q[c].w, kr[t][c].w, x);
+            s[c] = x;
+          }
+          // packed butterfly over the 16 lanes of the half: 4 values -> 1 per lane
+          const float x0 = b0 ? s[0] : s[2], x1 = b0 ? s[1] : s[3];               // what the xor-1 partner keeps
+          const float r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
+          const float u0 = (b0 ? s[2] : s[0]) + r0, u1 = (b0 ? s[3] : s[1]) + r1; // chunks (2 b0, 2 b0 + 1) over 2 lanes
+          const float y = b1 ? u0 : u1;
+          float v = (b1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, y, 2);          // chunk `own` over 4 lanes
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);                                // ... over the 16 lanes of the half
+          m = fmaxf(m, v);
+          if ((lane & 12) == 0) myc[jb + t][col] = v;                             // lanes 0-3 and 16-19
+        }
       }
-      // packed butterfly over the 16 lanes of the half: 4 values -> 1 per lane
-      const float x0 = b0 ? s[0] : s[2], x1 = b0 ? s[1] : s[3];                 // what the xor-1 partner keeps
-      const float r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
-      const float u0 = (b0 ? s[2] : s[0]) + r0, u1 = (b0 ? s[3] : s[1]) + r1;   // chunks (2 b0, 2 b0 + 1) over 2 lanes
-      const float y = b1 ? u0 : u1;
-      float v = (b1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, y, 2);            // chunk `own` over 4 lanes
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);                                  // ... over the 16 lanes of the half
-      m = fmaxf(m, v);
-      if ((lane & 12) == 0) myc[j][col] = v;                                    // lanes 0-3 and 16-19
     }
     __syncwarp();
     // ---- pass 2: p = exp(s - max), accumulate P V
@@ -389,28 +392,28 @@ __global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(con
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float l = 0.0f;
-    {
-      const float4* vv = reinterpret_cast<const float4*>(qkv + (size_t)row0 * 1536 + 1024) + lane;
+    for (int jb = 0; jb < n; jb += CN_ATTN_KB) {
+      float4 vr[CN_ATTN_KB][4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) nx[c] = __ldg(vv + 32 * c);
-    }
-    for (int j = 0; j < n; ++j) {
-      float4 vr[4];
+      for (int t = 0; t < CN_ATTN_KB; ++t) {
+        const int j = (jb + t < n) ? jb + t : n - 1;
+        const float4* vv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j) * 1536 + 1024) + lane;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) vr[c] = nx[c];
-      if (j + 1 < n) {
-        const float4* vv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j + 1) * 1536 + 1024) + lane;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) nx[c] = __ldg(vv + 32 * c);
+        for (int c = 0; c < 4; ++c) vr[t][c] = __ldg(vv + 32 * c);
       }
-      const float p = expf(myc[j][col] - m);
-      l += p;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        // chunk c was finished by the lane of this 4-lane group with (b0, b1) = (c >> 1, c & 1)
-        const float pc = __shfl_sync(0xffffffffu, p, grp | (c >> 1) | ((c & 1) << 1));
-        acc[c].x = fmaf(pc, vr[c].x, acc[c].x); acc[c].y = fmaf(pc, vr[c].y, acc[c].y);
-        acc[c].z = fmaf(pc, vr[c].z, acc[c].z); acc[c].w = fmaf(pc, vr[c].w, acc[c].w);
+      for (int t = 0; t < CN_ATTN_KB; ++t) {
+        if (jb + t < n) {
+          const float p = expf(myc[jb + t][col] - m);
+          l += p;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            // chunk c was finished by the lane of this 4-lane group with (b0, b1) = (c >> 1, c & 1)
+            const float pc = __shfl_sync(0xffffffffu, p, grp | (c >> 1) | ((c & 1) << 1));
+            acc[c].x = fmaf(pc, vr[t][c].x, acc[c].x); acc[c].y = fmaf(pc, vr[t][c].y, acc[c].y);
+            acc[c].z = fmaf(pc, vr[t][c].z, acc[c].z); acc[c].w = fmaf(pc, vr[t][c].w, acc[c].w);
+          }
+        }
       }
     }
     __syncwarp();                                      // sc is reused by this warp's next row

@@ -198,7 +198,16 @@ class Policy(nn.Module):
             self._cuda = CudaPolicy(N, self.human_num, self.input_size, device=device,
                                     gemm_mode=int(os.environ.get("CN_GEMM_MODE", "1")))
             self._cuda_version = -1
-        ver = sum(int(p._version) for p in self.parameters())
+        # parameter objects are fixed after construction: walk the module tree once, then only read the
+        # version counters (the tree walk alone cost ~0.1 ms of host time per act)
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        v, a = 0, 0
+        for p in plist:
+            v += p._version
+            a ^= p.data_ptr()             # .to() / .data swaps replace storage without bumping the version
+        ver = (v, a)
         if ver != self._cuda_version:                       # parameters changed (optimizer step / load_state_dict)
             self._cuda.load_state_dict(self.state_dict())
             self._cuda_version = ver
@@ -208,9 +217,11 @@ class Policy(nn.Module):
         sp = inputs['spatial_edges']
         eng = self._engine(sp.shape[0], sp.device)
         value, action, logp, h_new = eng.act(inputs, rnn_hxs['human_node_rnn'], masks, deterministic=deterministic)
-        out_hxs = {'human_node_rnn': h_new,
-                   # all-zeros in the reference (selfAttn_srnn_temp_node.py:390-395): stride-0 view, no 2.7 GB buffer
-                   'human_human_edge_rnn': torch.zeros(1, 1, 1, device=sp.device).expand(sp.shape[0], self.human_num + 1, 256)}
+        z = self.__dict__.get("_zero_edge")
+        if z is None or z.device != sp.device or z.shape[0] != sp.shape[0]:
+            # all-zeros in the reference (selfAttn_srnn_temp_node.py:390-395): stride-0 view, no 2.7 GB buffer
+            z = self.__dict__["_zero_edge"] = torch.zeros(1, 1, 1, device=sp.device).expand(sp.shape[0], self.human_num + 1, 256)
+        out_hxs = {'human_node_rnn': h_new, 'human_human_edge_rnn': z}
         return value, action, logp, out_hxs
 
     def get_value(self, inputs, rnn_hxs, masks):
