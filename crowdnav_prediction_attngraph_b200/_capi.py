@@ -32,6 +32,10 @@ class CnStepPtrs(C.Structure):
                 ("ep_ret", C.c_void_p), ("ep_len", C.c_void_p), ("not_done", C.c_void_p)]
 
 
+class CnCopySeg(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("bytes", C.c_size_t)]
+
+
 class CnPolicyConfig(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("human_num", C.c_int32), ("input_size", C.c_int32),
                 ("device", C.c_int32), ("gemm_mode", C.c_int32)]
@@ -49,7 +53,7 @@ EXPORTS = [
     "cn_env_step_host", "cn_env_state_bytes", "cn_env_state_copy", "cn_env_launch_count",
     "cn_policy_create", "cn_policy_destroy", "cn_policy_set_param", "cn_policy_finalize",
     "cn_policy_act", "cn_policy_launch_count", "cn_policy_last_rows", "cn_policy_profile", "cn_policy_stage_count",
-    "cn_policy_stage_name", "cn_policy_stage_ms",
+    "cn_policy_stage_name", "cn_policy_stage_ms", "cn_copy_segments",
 ]
 
 _lib = None
@@ -100,6 +104,8 @@ def load_library(path=None):
     lib.cn_env_state_bytes.restype = C.c_size_t
     lib.cn_env_state_bytes.argtypes = [C.c_void_p, C.c_char_p]
     lib.cn_env_state_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
+    lib.cn_copy_segments.restype = C.c_int
+    lib.cn_copy_segments.argtypes = [C.POINTER(CnCopySeg), C.c_int, C.c_int, C.c_void_p]
     lib.cn_env_launch_count.restype = C.c_int64
     lib.cn_env_launch_count.argtypes = [C.c_void_p]
     lib.cn_policy_create.argtypes = [C.POINTER(CnPolicyConfig), C.POINTER(C.c_void_p)]

@@ -205,6 +205,24 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
   }
 }
 
+// Several small device-to-device copies in one launch (RolloutStorage.insert): blockIdx.y = segment.
+struct CopySegs {
+  cn_copy_seg s[CN_MAX_COPY_SEGS];
+};
+__global__ void __launch_bounds__(256) cn_copy_segments_kernel(CopySegs p) {
+  const cn_copy_seg sg = p.s[blockIdx.y];
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if ((((uintptr_t)sg.dst | (uintptr_t)sg.src | sg.bytes) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(sg.src);
+    uint4* d4 = reinterpret_cast<uint4*>(sg.dst);
+    for (size_t i = tid; i < sg.bytes / 16; i += nth) d4[i] = s4[i];
+  } else {
+    const unsigned char* s1 = reinterpret_cast<const unsigned char*>(sg.src);
+    unsigned char* d1 = reinterpret_cast<unsigned char*>(sg.dst);
+    for (size_t i = tid; i < sg.bytes; i += nth) d1[i] = s1[i];
+  }
+}
+
 struct Field {
   void* ptr;
   size_t bytes;
@@ -558,6 +576,26 @@ int cn_env_state_copy(cn_env* env, const char* name, void* h_buf, size_t bytes, 
               : cudaMemcpy(h_buf, it->second.ptr, bytes, cudaMemcpyDeviceToHost);
   if (err != cudaSuccess) return cn_set_error("cn_env_state_copy(%s): %s", name, cudaGetErrorString(err));
   if (dir) env->prep_dirty = true;
+  return 0;
+}
+
+int cn_copy_segments(const cn_copy_seg* segs, int n, int device, void* stream) {
+  if (!segs || n < 0 || n > CN_MAX_COPY_SEGS) return cn_set_error("cn_copy_segments: need 0 <= n <= %d segments", CN_MAX_COPY_SEGS);
+  if (n == 0) return 0;
+  CopySegs p;
+  size_t maxb = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!segs[i].dst || !segs[i].src) return cn_set_error("cn_copy_segments: null pointer in segment %d", i);
+    p.s[i] = segs[i];
+    if (segs[i].bytes > maxb) maxb = segs[i].bytes;
+  }
+  cudaSetDevice(device);
+  size_t blocks = (maxb / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 1184) blocks = 1184;
+  cn_copy_segments_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return cn_set_error("cn_copy_segments launch: %s", cudaGetErrorString(err));
   return 0;
 }
 

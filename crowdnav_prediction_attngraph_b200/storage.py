@@ -6,6 +6,8 @@ Differences that do not change results: tensors are created directly on `device`
 `human_human_edge_rnn` hidden state (2.7 GB at N=4096, H=20 in the reference, storage.py:34) is a
 stride-0 expanded zero; `recurrent_generator` gathers minibatches with one index_select per
 tensor instead of a Python loop over environments (storage.py:208-223)."""
+import ctypes as C
+
 import torch
 
 
@@ -51,17 +53,40 @@ class RolloutStorage(object):
         self.device = dev
 
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs, value_preds, rewards, masks, bad_masks=None):
+        """rl/networks/storage.py:70-86.  Device-resident sources (observations, hidden state, action, log-prob,
+        value) are copied by ONE cn_copy_segments launch instead of nine torch copy_ calls; host tensors
+        (reward / masks built by the caller from `done`) take the usual async H2D copies."""
         s = self.step
-        for key in self.obs:
-            self.obs[key][s + 1].copy_(obs[key], non_blocking=True)
-        self.recurrent_hidden_states['human_node_rnn'][s + 1].copy_(recurrent_hidden_states['human_node_rnn'])
-        self.actions[s].copy_(actions)
-        self.action_log_probs[s].copy_(action_log_probs)
-        self.value_preds[s].copy_(value_preds)
-        self.rewards[s].copy_(rewards.reshape(-1, 1), non_blocking=True)
-        self.masks[s + 1].copy_(masks, non_blocking=True)
+        pairs = [(self.obs[key][s + 1], obs[key]) for key in self.obs]
+        pairs.append((self.recurrent_hidden_states['human_node_rnn'][s + 1], recurrent_hidden_states['human_node_rnn']))
+        pairs.append((self.actions[s], actions))
+        pairs.append((self.action_log_probs[s], action_log_probs))
+        pairs.append((self.value_preds[s], value_preds))
+        pairs.append((self.rewards[s], rewards.reshape(-1, 1)))
+        pairs.append((self.masks[s + 1], masks))
         if bad_masks is not None:
-            self.bad_masks[s + 1].copy_(bad_masks, non_blocking=True)
+            pairs.append((self.bad_masks[s + 1], bad_masks))
+        segs = None
+        if self.device.type == "cuda":
+            segs = self.__dict__.get("_segs")
+            if segs is None:
+                from . import _capi
+                self._lib = _capi.load_library()
+                segs = self._segs = (_capi.CnCopySeg * 16)()
+        n = 0
+        for dst, src in pairs:
+            if (segs is not None and n < 16 and src.is_cuda and src.device == dst.device and src.dtype == dst.dtype
+                    and src.is_contiguous() and src.numel() == dst.numel()):
+                if src.data_ptr() != dst.data_ptr():
+                    g = segs[n]
+                    g.dst, g.src, g.bytes = dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size()
+                    n += 1
+            else:
+                dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
+        if n:
+            from . import _capi
+            _capi.check(self._lib, self._lib.cn_copy_segments(segs, n, self.device.index or 0, C.c_void_p(
+                torch.cuda.current_stream(self.device).cuda_stream)), "cn_copy_segments")
         self.step = (s + 1) % self.num_steps
 
     def rollout_step_zero_copy(self, engine, env, deterministic=False):

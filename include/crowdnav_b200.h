@@ -79,6 +79,16 @@ typedef struct cn_step_ptrs {
   float *not_done;     /* [N] optional (may be NULL): 1 - done, the `masks` row train.py:185 builds */
 } cn_step_ptrs;
 
+/* replaces: the per-tensor copies of RolloutStorage.insert (rl/networks/storage.py:70-86) -- up to
+ * CN_MAX_COPY_SEGS device-to-device copies in ONE kernel launch on `stream`.                    */
+#define CN_MAX_COPY_SEGS 16
+typedef struct cn_copy_seg {
+  void *dst;
+  const void *src;
+  size_t bytes;
+} cn_copy_seg;
+int cn_copy_segments(const cn_copy_seg *segs, int n, int device, void *stream);
+
 typedef struct cn_env cn_env;
 
 const char *cn_last_error(void);
