@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_PKG, "libcrowdnav_b200.so")
 class CnConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "num_envs", "nenv_total", "rank_offset", "seed", "human_num", "predict_steps", "const_vel",
-        "randomize_attributes", "random_goal_changing", "end_goal_changing", "sort_humans", "device")] + \
+        "randomize_attributes", "random_goal_changing", "end_goal_changing", "sort_humans", "device",
+        "phase", "val_size", "test_size", "reserved0")] + \
         [(n, C.c_double) for n in (
             "time_step", "time_limit", "pred_timestep", "circle_radius", "arena_size",
             "discomfort_dist", "discomfort_penalty_factor", "success_reward", "collision_penalty",
@@ -48,6 +49,8 @@ class CnActPtrs(C.Structure):
 
 
 # every symbol include/crowdnav_b200.h declares (tests check the library exports all of them)
+ABI_VERSION = 2          # include/crowdnav_b200.h CN_ABI_VERSION
+
 EXPORTS = [
     "cn_last_error", "cn_abi_version", "cn_env_create", "cn_env_destroy", "cn_env_reset", "cn_env_step",
     "cn_env_step_host", "cn_env_state_bytes", "cn_env_state_copy", "cn_env_launch_count",
@@ -71,6 +74,7 @@ def default_config_dict(**over):
     d = dict(
         num_envs=16, nenv_total=16, rank_offset=0, seed=425, human_num=20, predict_steps=5, const_vel=1,
         randomize_attributes=0, random_goal_changing=0, end_goal_changing=1, sort_humans=1, device=0,
+        phase=0, val_size=100, test_size=500, reserved0=0,
         time_step=0.25, time_limit=50.0, pred_timestep=0.25, circle_radius=6 * 2 ** 0.5, arena_size=6.0,
         discomfort_dist=0.25, discomfort_penalty_factor=10.0, success_reward=10.0, collision_penalty=-20.0,
         human_radius=0.3, human_v_pref=1.0, human_fov=2.0, robot_radius=0.3, robot_v_pref=1.0, robot_fov=2.0,
@@ -96,6 +100,9 @@ def load_library(path=None):
     lib = C.CDLL(p)
     lib.cn_last_error.restype = C.c_char_p
     lib.cn_abi_version.restype = C.c_int
+    if lib.cn_abi_version() != ABI_VERSION:
+        raise ImportError("%s has C ABI version %d, this package needs %d: rebuild the extension" % (
+            p, lib.cn_abi_version(), ABI_VERSION))
     lib.cn_env_create.argtypes = [C.POINTER(CnConfig), C.POINTER(C.c_void_p)]
     lib.cn_env_destroy.argtypes = [C.c_void_p]
     lib.cn_env_reset.argtypes = [C.c_void_p, C.POINTER(CnObsPtrs), C.c_void_p]

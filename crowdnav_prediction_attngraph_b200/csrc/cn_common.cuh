@@ -33,7 +33,11 @@ struct CnParams {
   int sort_humans;        // args.sort_humans
   int nenv_total;         // env.nenv (global, across shards)
   uint32_t seed_base;     // thisSeed of env 0 of this shard = seed + rank_offset
-  uint32_t phase_offset;  // 2000 for 'train' (crowd_sim_var_num.py:329-334)
+  uint32_t phase_offset;  // 2000 'train', 0 'val', 1000 'test' (crowd_sim_var_num.py:329-334)
+  uint32_t case_size;     // case_counter wraps at case_size[phase] (crowd_sim.py:104-105)
+  int test_phase;         // 1: phase == 'test' (ground-truth look-ahead + 'future' danger zone)
+  int lookahead_steps;    // buffer_len = predict_steps * pred_interval
+  int pred_interval;
   double time_step, time_limit, pred_dt;   // pred_dt = time_step * pred_interval
   double circle_radius, arena_size;
   double discomfort_dist, discomfort_penalty_factor, success_reward, collision_penalty;
@@ -56,7 +60,9 @@ struct CnState {
   double *ep_ret;                    // bench.Monitor episode return
   int *ep_len;
   int *step_count;                   // global_time = step_count * time_step
-  uint32_t *case_counter;            // case_counter['train']
+  uint32_t *case_counter;            // case_counter[phase]
+  int32_t *seed_off;                 // thisSeed - seed_base of every environment (default: its index; a batched
+                                     // evaluation replays the single-env test protocol with all zeros)
   // humans [N][H]
   double *hpx, *hpy, *hgx, *hgy, *hrad, *hvpref;
   float *hvx, *hvy;

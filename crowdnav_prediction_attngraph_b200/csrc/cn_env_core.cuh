@@ -39,6 +39,19 @@ CN_HD double cn_norm_dot(double x, double y) { return sqrt(cn_fma(y, y, x * x));
 CN_HD double cn_norm_plain(double x, double y) { return sqrt(x * x + y * y); }
 CN_HD double cn_dot2(double a0, double a1, double b0, double b1) { return cn_fma(a1, b1, a0 * b0); }
 
+// phase-dependent constants (crowd_sim.py:103-105, crowd_sim_var_num.py:329-334).  phase: 0 'train', 2 'test'.
+// Call after P / time_step / pred_dt are set.
+inline void cn_fill_phase(CnParams& p, int phase, int val_size, int test_size) {
+  (void)val_size;
+  p.test_phase = (phase == 2) ? 1 : 0;
+  p.phase_offset = p.test_phase ? 1000u : 2000u;
+  p.case_size = p.test_phase ? (uint32_t)(test_size > 0 ? test_size : 1) : (4294967295u - 2000u);
+  int interval = (int)floor(p.pred_dt / p.time_step + 0.5);
+  if (interval < 1) interval = 1;
+  p.pred_interval = interval;
+  p.lookahead_steps = p.P * interval;
+}
+
 // Working set of ONE environment while a step is in flight (shared memory on the GPU).
 struct CnEnvSh {
   // human arrays, length H
@@ -109,7 +122,7 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
 // neighbour selection and ORCA half-plane construction into `lines` (sorted by distance).
 template <int MAXH>
 CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnLineStore lines, int& nl_out,
-                         float& vmax_out, CnF2& pref_out) {
+                         float& vmax_out, CnF2& pref_out, bool use_fov = true) {
   const int H = p.H;
   const size_t i = cn_idx(p, e, h);
   const double fov = p.human_fov;
@@ -156,7 +169,8 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   int nl = 0;
   for (int j = 0; j < H; ++j) {
     if (j == h) continue;
-    const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
+    // use_fov = false: act_joint_state of the ground-truth look-ahead passes every other human as is
+    const bool v = !use_fov || cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
     const CnF2 op = v ? f2(s.fx[j], s.fy[j]) : f2(7.0f, 7.0f);     // dummy_human (crowd_sim.py:130-133)
     const float d = f2abssq(f2sub(pos, op));
     if (d < rangeSq) { vd[nl] = d; vj[nl] = (uint8_t)(j | (v ? 0 : 0x80)); ++nl; }
@@ -176,12 +190,39 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   nl_out = nl; vmax_out = vmax; pref_out = pref;
 }
 
+// Diagnostics of the LAST ORCA solve of a human's simulator (what reading the reference's rvo2 sims after a
+// step shows; in the test phase that is the final look-ahead solve).
+CN_HD void cn_orca_diag(const CnParams& p, const CnState& g, int e, int h, CnF2 result, int nl, int fail) {
+  const size_t i = cn_idx(p, e, h);
+  g.last_hvx[i] = result.x; g.last_hvy[i] = result.y;
+  g.orca_nlines[i] = nl; g.orca_fail[i] = fail;
+}
+
+// Ground-truth look-ahead bookkeeping (calc_human_future_traj('truth') + the 'future' danger zone,
+// crowd_sim_var_num.py:180-228,495-511, crowd_sim_pred.py:216-233): one human's kept future position k
+// (1-based) against the robot's CURRENT position.  Humans the robot does not see sit at (15, 15).
+struct CnLookahead {
+  double min_rd;     // min distance among intruding future positions (+inf: none)
+  double pen;        // min over k of [intrusion] * collision_penalty / 2^(k+1)  (<= 0)
+};
+CN_HD void cn_lookahead_accumulate(const CnParams& p, const CnEnvSh& s, bool visible, double x, double y, int k,
+                                   CnLookahead& la) {
+  const double rx = (visible ? x : 15.0) - s.rpx, ry = (visible ? y : 15.0) - s.rpy;
+  const double rd = cn_norm_plain(rx, ry);                    // np.linalg.norm(axis=-1): no fma
+  if (rd < p.robot_radius + p.human_radius) {
+    la.min_rd = rd < la.min_rd ? rd : la.min_rd;
+    double coef = 2.0;
+    for (int q = 0; q < k; ++q) coef = coef * 2.0;            // 2^(k+1)
+    const double c = p.collision_penalty / coef;
+    la.pen = c < la.pen ? c : la.pen;
+  }
+}
+
 // Phase ORCA, part 3 (per thread): publish the solved velocity + the robot-collision distance.
 CN_HD void cn_orca_finish(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnF2 result, int nl, int fail) {
   const size_t i = cn_idx(p, e, h);
   s.nvx[h] = result.x; s.nvy[h] = result.y;
-  g.last_hvx[i] = result.x; g.last_hvy[i] = result.y;
-  g.orca_nlines[i] = nl; g.orca_fail[i] = fail;
+  cn_orca_diag(p, g, e, h, result, nl, fail);
   // collision distance to the robot for calc_reward (state BEFORE the action is applied)
   const double dx = s.px[h] - s.rpx, dy = s.py[h] - s.rpy;
   s.t0[h] = sqrt(dx * dx + dy * dy) - s.rad[h] - p.robot_radius;
@@ -194,12 +235,30 @@ CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int 
   double dmin = INFINITY;
   bool collision = false;
   for (int i = 0; i < H; ++i) {
-    const double c = s.t0[i];
+    double c;
+    if (p.test_phase) {        // t0 carries the look-ahead's min distance there: closest distance recomputed
+      const double dx = s.px[i] - s.rpx, dy = s.py[i] - s.rpy;
+      c = sqrt(dx * dx + dy * dy) - s.rad[i] - p.robot_radius;
+    } else {
+      c = s.t0[i];
+    }
     if (c < 0) { collision = true; break; }
     else if (c < dmin) dmin = c;
   }
   const bool reaching_goal = cn_norm_dot(s.rpx - s.rgx, s.rpy - s.rgy) < p.robot_radius;
-  const bool danger = dmin < p.discomfort_dist;              // phase == 'train' (crowd_sim_var_num.py:495-497)
+  bool danger;
+  double min_danger = 0.0, fut_pen;
+  if (p.test_phase) {
+    // 'future' danger zone on the ground-truth look-ahead (crowd_sim_var_num.py:495-511)
+    double mr = INFINITY, pen = 0.0;
+    for (int i = 0; i < H; ++i) { mr = s.t0[i] < mr ? s.t0[i] : mr; pen = s.t1[i] < pen ? s.t1[i] : pen; }
+    danger = mr < INFINITY;
+    if (danger) min_danger = mr;
+    fut_pen = pen;
+  } else {
+    danger = dmin < p.discomfort_dist;                        // phase == 'train' (crowd_sim_var_num.py:495-497)
+    fut_pen = g.fut_pen[e];
+  }
   const int step = g.step_count[e];
   const double global_time = step * p.time_step;
   double reward; int done, info;
@@ -215,7 +274,7 @@ CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int 
     g.potential[e] = -fabs(pot);
     done = 0; info = CN_INFO_NOTHING;
   }
-  if (p.const_vel) reward = reward + g.fut_pen[e];            // crowd_sim_pred.py:216-233
+  if (p.const_vel) reward = reward + fut_pen;                 // crowd_sim_pred.py:216-233
   s.reward = reward; s.done = done; s.info = info;
   // Monitor bookkeeping + outputs
   const double ret = g.ep_ret[e] + reward;
@@ -224,7 +283,7 @@ CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int 
   out.reward[e] = (float)reward;
   out.done[e] = (uint8_t)done;
   out.info[e] = info;
-  out.info_aux[e] = 0.0f;
+  out.info_aux[e] = (info == CN_INFO_DANGER) ? (float)min_danger : 0.0f;     // Danger(min_dist)
   if (out.not_done) out.not_done[e] = done ? 0.0f : 1.0f;
   if (done) { out.ep_ret[e] = ret; out.ep_len[e] = len; }
   // robot.step(action) (agent.py:170-183); time
@@ -360,7 +419,7 @@ CN_HD void cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   const int H = p.H;
   CnRng rng; rng.key = key; rng.pos = 624;
   const uint32_t cc = g.case_counter[e];
-  const uint32_t this_seed = p.seed_base + (uint32_t)e;
+  const uint32_t this_seed = p.seed_base + (uint32_t)g.seed_off[e];
   cn_rng_seed(rng, p.phase_offset + cc + this_seed, co);
   for (;;) {
     const double px = cn_rng_uniform(rng, co, -p.arena_size, p.arena_size);
@@ -409,9 +468,8 @@ CN_HD void cn_install_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   if (h == 0) {
     const double* r = g.prep_robot + (size_t)e * 4;
     s.rpx = r[0]; s.rpy = r[1]; s.rgx = r[2]; s.rgy = r[3]; s.rvx = 0.0f; s.rvy = 0.0f;
-    // case_counter = (case_counter + nenv) % case_size['train'] with case_size = UINT32_MAX - 2000
-    const uint64_t case_size = 4294967295ull - 2000ull;
-    g.case_counter[e] = (uint32_t)(((uint64_t)g.case_counter[e] + (uint64_t)p.nenv_total) % case_size);
+    // case_counter = (case_counter + nenv) % case_size[phase]  (train: UINT32_MAX - 2000, test: env.test_size)
+    g.case_counter[e] = (uint32_t)(((uint64_t)g.case_counter[e] + (uint64_t)p.nenv_total) % (uint64_t)p.case_size);
     g.potential[e] = -fabs(cn_norm_dot(s.rgx - s.rpx, s.rgy - s.rpy));
     g.step_count[e] = 0;
     g.ep_ret[e] = 0.0; g.ep_len[e] = 0;

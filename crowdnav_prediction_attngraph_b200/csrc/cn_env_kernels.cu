@@ -105,21 +105,24 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
     cn_phase_load(p, g, *s, e, h, action);
   }
   __syncthreads();
-  if (mode != 1) {
-    int nl = 0, fail = -1;
+  // One ORCA solve of every human of the CTA on the joint state currently in shared memory (CTA-uniform
+  // call: contains barriers).  linearProgram3 (needed by ~30 % of the humans in steady state) is
+  // balanced across the whole CTA: failed humans are queued in shared memory and every warp pops tasks
+  // until the queue is dry.
+  int* lp3_count = reinterpret_cast<int*>(lp3_q);
+  int* lp3_head = lp3_count + 1;
+  unsigned short* lp3_tasks = reinterpret_cast<unsigned short*>(lp3_count + 2);
+  auto orca_solve = [&](bool use_fov, CnF2& result, int& nl, int& fail) {
+    nl = 0; fail = -1;
     float vmax = 0.0f;
-    CnF2 pref = f2(0.0f, 0.0f), result = f2(0.0f, 0.0f);
-    if (active) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref);
+    CnF2 pref = f2(0.0f, 0.0f);
+    result = f2(0.0f, 0.0f);
+    if (active) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref, use_fov);
     __syncwarp();
     cn_orca_lp2_warp(co, W, nl, vmax, pref, result, fail);            // all 32 lanes, idle ones with nl = 0
-    // linearProgram3 (needed by ~30 % of the humans in steady state) is balanced across the whole
-    // CTA: failed humans are queued in shared memory and every warp pops tasks until the queue is dry.
-    int* lp3_count = reinterpret_cast<int*>(lp3_q);
-    int* lp3_head = lp3_count + 1;
-    unsigned short* lp3_tasks = reinterpret_cast<unsigned short*>(lp3_count + 2);
     if (fail >= 0) {
       s->nvx[h] = result.x; s->nvy[h] = result.y;                     // LP2 result at the failure point
-      reinterpret_cast<int*>(&s->t0[h])[0] = nl | (fail << 8);        // t0 is free until cn_orca_finish
+      reinterpret_cast<int*>(&s->t0[h])[0] = nl | (fail << 8);        // t0 is free until the solve is published
       reinterpret_cast<float*>(&s->t0[h])[1] = vmax;
       lp3_tasks[atomicAdd(lp3_count, 1)] = (unsigned short)threadIdx.x;
     }
@@ -144,7 +147,49 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
     }
     __syncthreads();
     if (fail >= 0) result = f2(s->nvx[h], s->nvy[h]);
-    if (active) cn_orca_finish(p, g, *s, e, h, result, nl, fail);
+    if (threadIdx.x == 0) { *lp3_count = 0; *lp3_head = 0; }          // ready for the next solve (a barrier follows)
+  };
+  if (mode != 1) {
+    CnF2 result; int nl, fail;
+    orca_solve(true, result, nl, fail);                               // get_human_actions (crowd_sim.py:680-703)
+    if (p.test_phase && p.const_vel) {
+      // phase 'test': ground-truth look-ahead (crowd_sim_pred.py:136-138 -> crowd_sim_var_num.py:180-206):
+      // lookahead_steps nested solves on a scratch copy of the joint state kept in the same shared arrays
+      // (every thread saves / restores its own human), then the 'future' danger zone inputs for the reward.
+      double spx = 0, spy = 0, lx = 0, ly = 0;
+      float svx = 0, svy = 0, lvx = 0, lvy = 0;
+      bool vis_prev = false;
+      if (active) {
+        spx = s->px[h]; spy = s->py[h]; svx = s->vx[h]; svy = s->vy[h];
+        lx = spx; ly = spy; lvx = svx; lvy = svy;
+        vis_prev = g.vis[cn_idx(p, e, h)] != 0;
+      }
+      CnLookahead la; la.min_rd = INFINITY; la.pen = 0.0;
+      CnF2 lres = f2(0.0f, 0.0f); int lnl = 0, lfail = -1;
+      for (int t = 1; t <= p.lookahead_steps; ++t) {
+        __syncthreads();
+        if (active) {
+          s->px[h] = lx; s->py[h] = ly; s->fx[h] = (float)lx; s->fy[h] = (float)ly; s->vx[h] = lvx; s->vy[h] = lvy;
+        }
+        __syncthreads();
+        orca_solve(false, lres, lnl, lfail);
+        lx = lx + (double)lres.x * p.time_step; ly = ly + (double)lres.y * p.time_step;
+        lvx = lres.x; lvy = lres.y;
+        if (active && t % p.pred_interval == 0) cn_lookahead_accumulate(p, *s, vis_prev, lx, ly, t / p.pred_interval, la);
+      }
+      __syncthreads();
+      if (active) {
+        s->px[h] = spx; s->py[h] = spy; s->fx[h] = (float)spx; s->fy[h] = (float)spy; s->vx[h] = svx; s->vy[h] = svy;
+      }
+      __syncthreads();
+      if (active) {
+        cn_orca_finish(p, g, *s, e, h, result, nl, fail);
+        cn_orca_diag(p, g, e, h, lres, lnl, lfail);                   // the simulators' LAST solve
+        s->t0[h] = la.min_rd; s->t1[h] = la.pen;                      // reward inputs (test phase)
+      }
+    } else if (active) {
+      cn_orca_finish(p, g, *s, e, h, result, nl, fail);
+    }
   }
   __syncthreads();
   if (mode != 1 && active && h == 0) cn_phase_reward(p, g, *s, e, out);
@@ -388,13 +433,17 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   p.randomize = cfg->randomize_attributes; p.goal_changing = cfg->random_goal_changing;
   p.end_goal_changing = cfg->end_goal_changing; p.sort_humans = cfg->sort_humans;
   p.nenv_total = cfg->nenv_total; p.seed_base = (uint32_t)(cfg->seed + cfg->rank_offset);
-  p.phase_offset = 2000u;
   p.time_step = cfg->time_step; p.time_limit = cfg->time_limit;
   {
     // pred_interval = int(pred_timestep // time_step) (crowd_sim.py:187)
     const double q = floor(cfg->pred_timestep / cfg->time_step);
     p.pred_dt = cfg->time_step * (double)(int)q;
   }
+  if (cfg->phase != 0 && cfg->phase != 2) {
+    cn_env_destroy(env);
+    return cn_set_error("cn_env_create: phase %d unsupported (0 = 'train', 2 = 'test')", cfg->phase);
+  }
+  cn_fill_phase(p, cfg->phase, cfg->val_size, cfg->test_size);
   p.circle_radius = cfg->circle_radius; p.arena_size = cfg->arena_size;
   p.discomfort_dist = cfg->discomfort_dist; p.discomfort_penalty_factor = cfg->discomfort_penalty_factor;
   p.success_reward = cfg->success_reward; p.collision_penalty = cfg->collision_penalty;
@@ -411,7 +460,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   int rc = 0;
 #define A(field, count) if (!rc) rc = dev_alloc(env, #field, &g.field, (count))
   A(rpx, N); A(rpy, N); A(rgx, N); A(rgy, N); A(rvx, N); A(rvy, N); A(potential, N); A(fut_pen, N);
-  A(nd_global, N); A(ep_ret, N); A(ep_len, N); A(step_count, N); A(case_counter, N);
+  A(nd_global, N); A(ep_ret, N); A(ep_len, N); A(step_count, N); A(case_counter, N); A(seed_off, N);
   A(hpx, NH); A(hpy, NH); A(hgx, NH); A(hgy, NH); A(hrad, NH); A(hvpref, NH); A(hvx, NH); A(hvy, NH);
   A(bpx, NH); A(bpy, NH); A(bvx, NH); A(bvy, NH); A(brad, NH); A(vis, NH);
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH);
@@ -426,6 +475,12 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     std::vector<double> nd(N, cfg->orca_neighbor_dist);
     err = cudaMemcpy(g.nd_global, nd.data(), N * sizeof(double), cudaMemcpyHostToDevice);
     if (err != cudaSuccess) rc = cn_set_error("init nd_global: %s", cudaGetErrorString(err));
+  }
+  if (!rc) {
+    std::vector<int32_t> so(N);
+    for (size_t i = 0; i < N; ++i) so[i] = (int32_t)i;
+    err = cudaMemcpy(g.seed_off, so.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) rc = cn_set_error("init seed_off: %s", cudaGetErrorString(err));
   }
   // staging buffers for cn_env_step_host
   memset(&env->d_obs, 0, sizeof(env->d_obs)); memset(&env->d_out, 0, sizeof(env->d_out));

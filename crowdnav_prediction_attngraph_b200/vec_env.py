@@ -72,8 +72,14 @@ class Box(_Space):
     pass
 
 
-def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None, rank_offset=0, device_index=0):
-    """Snapshot a reference `Config` object (crowd_nav/configs/config.py) into the flat cn_config."""
+def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None, rank_offset=0, device_index=0,
+                               phase=None):
+    """Snapshot a reference `Config` object (crowd_nav/configs/config.py) into the flat cn_config.
+    phase None follows rl/networks/envs.py:55-58: one environment -> 'test', more -> 'train'."""
+    if phase is None:
+        phase = "test" if (nenv_total or num_envs) == 1 else "train"
+    if phase not in ("train", "test"):
+        raise NotImplementedError("phase %r: the engine covers 'train' and 'test'" % (phase,))
     if config.sim.human_num_range != 0:
         raise NotImplementedError("sim.human_num_range > 0 is outside the engine's scope (SURVEY.md §8f row 4)")
     if config.action_space.kinematics != "holonomic" or config.humans.policy != "orca" or config.robot.visible:
@@ -103,7 +109,9 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
         robot_v_pref=float(config.robot.v_pref), robot_fov=float(config.robot.FOV),
         sensor_range=float(config.robot.sensor_range), goal_change_chance=float(config.humans.goal_change_chance),
         orca_neighbor_dist=float(config.orca.neighbor_dist), orca_safety_space=float(config.orca.safety_space),
-        orca_time_horizon=float(config.orca.time_horizon))
+        orca_time_horizon=float(config.orca.time_horizon),
+        phase=2 if phase == "test" else 0, val_size=int(getattr(config.env, "val_size", 100)),
+        test_size=int(getattr(config.env, "test_size", 500)))
 
 
 class LazyInfos(object):
@@ -275,7 +283,7 @@ class CudaCrowdVecEnv(object):
 
     # ------------------------------------------------------------------ parity-test access
     _DT = dict(rpx="f8", rpy="f8", rgx="f8", rgy="f8", rvx="f4", rvy="f4", potential="f8", fut_pen="f8",
-               nd_global="f8", ep_ret="f8", ep_len="i4", step_count="i4", case_counter="u4",
+               nd_global="f8", ep_ret="f8", ep_len="i4", step_count="i4", case_counter="u4", seed_off="i4",
                hpx="f8", hpy="f8", hgx="f8", hgy="f8", hrad="f8", hvpref="f8", hvx="f4", hvy="f4",
                bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
                sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",
@@ -301,12 +309,14 @@ class CudaCrowdVecEnv(object):
 
 def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, device, allow_early_resets,
                   num_frame_stack=None, config=None, ax=None, test_case=-1, wrap_pytorch=True,
-                  pretext_wrapper=False, nenv_total=None, rank_offset=0):
-    """Same signature as rl/networks/envs.py:97-140.  Returns the CUDA vec env (already 'VecPyTorch')."""
+                  pretext_wrapper=False, nenv_total=None, rank_offset=0, phase=None):
+    """Same signature as rl/networks/envs.py:97-140.  Returns the CUDA vec env (already 'VecPyTorch').
+    Like the reference (envs.py:55-58) a single environment runs in phase 'test', several in 'train';
+    `phase=` overrides (batched evaluation)."""
     if pretext_wrapper:
         raise NotImplementedError("VecPretextNormalize / GST predictor is the 'next' row (SURVEY.md §8f row 2)")
     device = torch.device(device)
     d = config_dict_from_reference(config, num_processes, seed, env_name, nenv_total=nenv_total,
                                    rank_offset=rank_offset,
-                                   device_index=device.index if device.index is not None else 0)
+                                   device_index=device.index if device.index is not None else 0, phase=phase)
     return CudaCrowdVecEnv(device=device, cfg=d)

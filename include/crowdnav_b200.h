@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CN_ABI_VERSION 1
+#define CN_ABI_VERSION 2
 
 /* info codes — crowd_sim/envs/utils/info.py (Nothing, Timeout, Collision, ReachGoal, Danger) */
 #define CN_INFO_NOTHING_C 0
@@ -50,6 +50,10 @@ typedef struct cn_config {
   int32_t end_goal_changing;      /* humans.end_goal_changing                                   */
   int32_t sort_humans;            /* args.sort_humans                                           */
   int32_t device;                 /* CUDA device ordinal                                        */
+  int32_t phase;                  /* env.phase: 0 'train', 2 'test' (ground-truth look-ahead, 'future'
+                                   * danger zone, test seeds; crowd_sim_pred.py:136-138)          */
+  int32_t val_size, test_size;    /* env.val_size / env.test_size: case_counter wrap of the phase */
+  int32_t reserved0;
   double time_step, time_limit, pred_timestep;
   double circle_radius, arena_size;
   double discomfort_dist, discomfort_penalty_factor, success_reward, collision_penalty;

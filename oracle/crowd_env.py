@@ -115,8 +115,8 @@ class CrowdEnvOracle(object):
     """One environment.  `this_seed`/`nenv`/`phase` as set by rl/networks/envs.py:51-58."""
 
     def __init__(self, cfg, this_seed, nenv, phase="train"):
-        if phase != "train":
-            raise NotImplementedError("oracle covers phase='train' only (test phase = SURVEY.md §8f row 1)")
+        if phase not in ("train", "val", "test"):
+            raise ValueError("phase must be 'train', 'val' or 'test'")
         self.cfg = cfg
         self.H = cfg.human_num
         self.P = cfg.predict_steps
@@ -292,6 +292,13 @@ class CrowdEnvOracle(object):
 
     # ---------------------------------------------------------------- human actions (ORCA)
     def _human_actions(self):
+        """get_human_actions (crowd_sim.py:680-703): ORCA on the current state, FOV-filtered neighbours."""
+        return self._orca_actions(self.hpx, self.hpy, self.hvx, self.hvy, use_fov=True)
+
+    def _orca_actions(self, px, py, vx, vy, use_fov):
+        """One ORCA solve per human on the joint state (px, py, vx, vy) through its PERSISTENT rvo2 simulator
+        (crowd_nav/policy/orca.py:64-117).  use_fov=False is the ground-truth look-ahead's
+        act_joint_state (crowd_sim_var_num.py:183-196): every other human is passed as is."""
         c, H = self.cfg, self.H
         fov = np.pi * c.human_fov
         acts = []
@@ -302,26 +309,26 @@ class CrowdEnvOracle(object):
                 if j == i:
                     continue
                 # humans have no range limit; FOV test only (always true for FOV = 2 pi unless NaN)
-                if self._in_fov(self.hpx[i], self.hpy[i], self.hvx[i], self.hvy[i], self.hpx[j], self.hpy[j], fov):
-                    others.append((self.hpx[j], self.hpy[j], self.hvx[j], self.hvy[j], self.hrad[j]))
+                if (not use_fov) or self._in_fov(px[i], py[i], vx[i], vy[i], px[j], py[j], fov):
+                    others.append((px[j], py[j], vx[j], vy[j], self.hrad[j]))
                 else:
                     others.append((7, 7, 0, 0, 0.3))   # dummy_human (crowd_sim.py:130-133)
             sim = self.sims[i]
             if sim is None:
                 params = (self.nd_global, len(others), c.orca_time_horizon, c.orca_time_horizon)
                 sim = rvo2.PyRVOSimulator(c.time_step, *params, self.hrad[i], 1)
-                sim.addAgent((self.hpx[i], self.hpy[i]), *params, self.hrad[i] + 0.01 + c.orca_safety_space,
-                             self.hvpref[i], (self.hvx[i], self.hvy[i]))
+                sim.addAgent((px[i], py[i]), *params, self.hrad[i] + 0.01 + c.orca_safety_space,
+                             self.hvpref[i], (vx[i], vy[i]))
                 for o in others:
                     sim.addAgent((o[0], o[1]), *params, o[4] + 0.01 + c.orca_safety_space, 1, (o[2], o[3]))
                 self.sims[i] = sim
             else:
-                sim.setAgentPosition(0, (self.hpx[i], self.hpy[i]))
-                sim.setAgentVelocity(0, (self.hvx[i], self.hvy[i]))
+                sim.setAgentPosition(0, (px[i], py[i]))
+                sim.setAgentVelocity(0, (vx[i], vy[i]))
                 for k, o in enumerate(others):
                     sim.setAgentPosition(k + 1, (o[0], o[1]))
                     sim.setAgentVelocity(k + 1, (o[2], o[3]))
-            velocity = np.array((self.hgx[i] - self.hpx[i], self.hgy[i] - self.hpy[i]))
+            velocity = np.array((self.hgx[i] - px[i], self.hgy[i] - py[i]))
             speed = np.linalg.norm(velocity)
             pref_vel = velocity / speed if speed > 1 else velocity
             sim.setAgentPrefVelocity(0, tuple(pref_vel))
@@ -331,6 +338,28 @@ class CrowdEnvOracle(object):
             acts.append(sim.getAgentVelocity(0))
             self.last_orca_diag.append((sim._numLines(0), sim._lineFail(0)))
         return acts
+
+    def _truth_future_traj(self):
+        """calc_human_future_traj('truth') (crowd_sim_var_num.py:152-228): buffer_len nested ORCA steps of all
+        humans (the invisible robot does not take part), every pred_interval-th state kept, humans the robot
+        does not currently see parked at (15, 15)."""
+        c, H, P = self.cfg, self.H, self.P
+        buffer_len = P * self.pred_interval
+        traj = np.zeros((buffer_len + 1, H, 4))
+        for i in range(H):
+            traj[0, i] = [self.hpx[i], self.hpy[i], self.hvx[i], self.hvy[i]]
+        for t in range(1, buffer_len + 1):
+            acts = self._orca_actions(traj[t - 1, :, 0], traj[t - 1, :, 1], traj[t - 1, :, 2], traj[t - 1, :, 3],
+                                      use_fov=False)
+            for j, (ax, ay) in enumerate(acts):
+                traj[t, j] = [traj[t - 1, j, 0] + ax * c.time_step, traj[t - 1, j, 1] + ay * c.time_step, ax, ay]
+            self.last_sim_actions = acts
+        traj = traj[::self.pred_interval]
+        inv = np.logical_not(np.array(self.human_visibility, dtype=bool))
+        traj[:, inv, :2] = 15
+        traj[:, inv, 2:] = 0
+        self.human_future_traj = traj
+        return traj
 
     # ---------------------------------------------------------------- reward
     def _calc_reward(self):
@@ -377,6 +406,8 @@ class CrowdEnvOracle(object):
             idx = np.linalg.norm(rel, axis=-1) < c.robot_radius + c.human_radius
             coef = 2. ** np.arange(2, self.P + 2).reshape((self.P, 1))
             reward = reward + np.min(idx * (c.collision_penalty / coef))
+        if info != INFO_DANGER:
+            min_danger = 0.0        # only Danger(min_dist) carries it (crowd_sim_var_num.py:526-532)
         return reward, done, info, min_danger
 
     # ---------------------------------------------------------------- step
@@ -389,6 +420,10 @@ class CrowdEnvOracle(object):
             action[1] = action[1] / act_norm * c.robot_v_pref
         avx, avy = action[0], action[1]
         human_actions = self._human_actions()
+        # what reading the per-human simulators after the step shows (tools/make_golden.py does that): the LAST solve
+        self.last_sim_actions = human_actions
+        if self.phase == "test" and c.predict_method == "const_vel":
+            self._truth_future_traj()          # crowd_sim_pred.py:136-138 (number of intrusions in testing)
         reward, done, info, min_danger = self._calc_reward()
         # integrate (agent.py:143-183)
         self.rpx = self.rpx + avx * c.time_step
@@ -477,9 +512,8 @@ class OracleVecEnv(object):
     """N oracle environments stepped serially with the VecEnv contract of
     rl/networks/shmem_vec_env.py (obs float32 [N,...], rewards float64 [N], dones bool [N])."""
 
-    def __init__(self, cfg, num_envs, seed=425, rank_offset=0, nenv_total=None):
+    def __init__(self, cfg, num_envs, seed=425, rank_offset=0, nenv_total=None, phase="train"):
         total = num_envs if nenv_total is None else nenv_total
-        phase = "train"
         self.envs = [CrowdEnvOracle(cfg, seed + rank_offset + k, total, phase) for k in range(num_envs)]
         self.num_envs = num_envs
 

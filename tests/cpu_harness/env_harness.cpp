@@ -69,6 +69,44 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
         cn_orca_lp3_warp(co, W, nl, vmax, proj, result, fail);
         cn_orca_finish(p, g, s, e, h, result, nl, fail);
       }
+      if (p.test_phase && p.const_vel) {
+        // ground-truth look-ahead (phase 'test'): lookahead_steps nested ORCA solves of every human on a
+        // scratch copy of the joint state; mirrors the look-ahead loop of cn_env_step_kernel
+        std::vector<double> sx(s.px, s.px + H), sy(s.py, s.py + H), lx(sx), ly(sy);
+        std::vector<float> svx(s.vx, s.vx + H), svy(s.vy, s.vy + H), lvx(svx), lvy(svy);
+        std::vector<CnLookahead> la(H);
+        std::vector<CnF2> res(H);
+        std::vector<int> nls(H), fails(H);
+        for (int h = 0; h < H; ++h) { la[h].min_rd = INFINITY; la[h].pen = 0.0; }
+        for (int t = 1; t <= p.lookahead_steps; ++t) {
+          for (int h = 0; h < H; ++h) {
+            s.px[h] = lx[h]; s.py[h] = ly[h]; s.fx[h] = (float)lx[h]; s.fy[h] = (float)ly[h];
+            s.vx[h] = lvx[h]; s.vy[h] = lvy[h];
+          }
+          for (int h = 0; h < H; ++h) {
+            CnWarpLines W; W.smem0 = lines.data() + (size_t)h * H; W.stride = 1; W.cap = 3;
+            W.ovf0 = lines.data() + (size_t)h * H + 3; W.ovf_stride = 0;
+            CnLineStore proj; proj.base = projbuf.data(); proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
+            int nl = 0, fail = -1; float vmax = 0; CnF2 pref = f2(0, 0), result = f2(0, 0);
+            cn_orca_build<MAXH>(p, g, s, e, h, W.of(0), nl, vmax, pref, false);
+            cn_orca_lp2_warp(co, W, nl, vmax, pref, result, fail);
+            cn_orca_lp3_warp(co, W, nl, vmax, proj, result, fail);
+            res[h] = result; nls[h] = nl; fails[h] = fail;
+          }
+          for (int h = 0; h < H; ++h) {
+            lx[h] = lx[h] + (double)res[h].x * p.time_step; ly[h] = ly[h] + (double)res[h].y * p.time_step;
+            lvx[h] = res[h].x; lvy[h] = res[h].y;
+            if (t % p.pred_interval == 0)
+              cn_lookahead_accumulate(p, s, g.vis[cn_idx(p, e, h)] != 0, lx[h], ly[h], t / p.pred_interval, la[h]);
+            if (t == p.lookahead_steps) cn_orca_diag(p, g, e, h, res[h], nls[h], fails[h]);
+          }
+        }
+        for (int h = 0; h < H; ++h) {
+          s.px[h] = sx[h]; s.py[h] = sy[h]; s.fx[h] = (float)sx[h]; s.fy[h] = (float)sy[h];
+          s.vx[h] = svx[h]; s.vy[h] = svy[h];
+          s.t0[h] = la[h].min_rd; s.t1[h] = la[h].pen;
+        }
+      }
       cn_phase_reward(p, g, s, e, out);
       if (s.done) { for (int h = H - 1; h >= 0; --h) cn_install_env(p, g, s, e, h); }   // prepared next episode
       else { for (int h = 0; h < H; ++h) cn_phase_integrate(p, s, h); }
@@ -96,9 +134,9 @@ void* harness_create(const cn_config* cfg) {
   p.randomize = cfg->randomize_attributes; p.goal_changing = cfg->random_goal_changing;
   p.end_goal_changing = cfg->end_goal_changing; p.sort_humans = cfg->sort_humans;
   p.nenv_total = cfg->nenv_total; p.seed_base = (uint32_t)(cfg->seed + cfg->rank_offset);
-  p.phase_offset = 2000u;
   p.time_step = cfg->time_step; p.time_limit = cfg->time_limit;
   p.pred_dt = cfg->time_step * (double)(int)floor(cfg->pred_timestep / cfg->time_step);
+  cn_fill_phase(p, cfg->phase, cfg->val_size, cfg->test_size);
   p.circle_radius = cfg->circle_radius; p.arena_size = cfg->arena_size;
   p.discomfort_dist = cfg->discomfort_dist; p.discomfort_penalty_factor = cfg->discomfort_penalty_factor;
   p.success_reward = cfg->success_reward; p.collision_penalty = cfg->collision_penalty;
@@ -112,7 +150,7 @@ void* harness_create(const cn_config* cfg) {
   CnState& g = hn->g;
 #define A(field, count) halloc(hn, #field, &g.field, (count))
   A(rpx, N); A(rpy, N); A(rgx, N); A(rgy, N); A(rvx, N); A(rvy, N); A(potential, N); A(fut_pen, N);
-  A(nd_global, N); A(ep_ret, N); A(ep_len, N); A(step_count, N); A(case_counter, N);
+  A(nd_global, N); A(ep_ret, N); A(ep_len, N); A(step_count, N); A(case_counter, N); A(seed_off, N);
   A(hpx, NH); A(hpy, NH); A(hgx, NH); A(hgy, NH); A(hrad, NH); A(hvpref, NH); A(hvx, NH); A(hvy, NH);
   A(bpx, NH); A(bpy, NH); A(bvx, NH); A(bvy, NH); A(brad, NH); A(vis, NH);
   A(sim_exists, NH); A(sim_nd, NH); A(sim_rself, NH); A(sim_vmax, NH); A(sim_rother, NH * p.H);
@@ -121,7 +159,7 @@ void* harness_create(const cn_config* cfg) {
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
 #undef A
-  for (size_t e = 0; e < N; ++e) g.nd_global[e] = cfg->orca_neighbor_dist;
+  for (size_t e = 0; e < N; ++e) { g.nd_global[e] = cfg->orca_neighbor_dist; g.seed_off[e] = (int32_t)e; }
   return hn;
 }
 

@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ENV_CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5"]
+ENV_CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5", "env_pred_h20_test",
+             "env_pred_h10_test_rand"]
 
 
 def load_env_case(name):
@@ -15,7 +16,8 @@ def load_env_case(name):
     case = ast.literal_eval(str(g["meta"][0]))
     over = dict(num_envs=g["actions"].shape[1], nenv_total=case["nenv"], seed=case["seed"],
                 human_num=case["human_num"], const_vel=1 if case["predict_method"] == "const_vel" else 0,
-                randomize_attributes=int(case["randomize"]), random_goal_changing=int(case["goal_changing"]))
+                randomize_attributes=int(case["randomize"]), random_goal_changing=int(case["goal_changing"]),
+                phase=2 if case.get("phase", "train") == "test" else 0)
     return g, case, over
 
 
@@ -41,6 +43,8 @@ def replay(g, case, reset_fn, step_fn, get_fn, pos_tol=1e-9, obs_tol=1e-5, exact
             msg.append("info")
         if np.abs(out["reward"] - g["reward"][t]).max() > 1e-5:
             msg.append("reward")
+        if "info_aux" in out and np.abs(out["info_aux"] - g["min_danger"][t]).max() > 1e-6:
+            msg.append("min_danger")
         ha = np.stack([get_fn("last_hvx").reshape(N, H), get_fn("last_hvy").reshape(N, H)], -1)
         ok = ~np.isnan(g["human_actions"][t][..., 0])
         if exact_orca:

@@ -15,7 +15,7 @@ CORE = os.path.join(HERE, "..", "crowdnav_prediction_attngraph_b200", "csrc")
 
 STATE_DTYPES = dict(
     rpx="f8", rpy="f8", rgx="f8", rgy="f8", rvx="f4", rvy="f4", potential="f8", fut_pen="f8", nd_global="f8",
-    ep_ret="f8", ep_len="i4", step_count="i4", case_counter="u4",
+    ep_ret="f8", ep_len="i4", step_count="i4", case_counter="u4", seed_off="i4",
     hpx="f8", hpy="f8", hgx="f8", hgy="f8", hrad="f8", hvpref="f8", hvx="f4", hvy="f4",
     bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
     sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",

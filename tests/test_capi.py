@@ -26,12 +26,13 @@ def test_header_symbols_exported(lib):
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cn_abi_version() == 1
+    assert lib.cn_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
-    # 12 int32 + 20 double, no padding surprises
-    assert C.sizeof(_capi.CnConfig) == 12 * 4 + 20 * 8
+    # 16 int32 + 20 double, no padding surprises
+    assert C.sizeof(_capi.CnConfig) == 16 * 4 + 20 * 8
+    assert C.sizeof(_capi.CnCopySeg) == 3 * 8
     assert C.sizeof(_capi.CnObsPtrs) == 5 * 8 and C.sizeof(_capi.CnStepPtrs) == 7 * 8
     assert C.sizeof(_capi.CnActPtrs) == 12 * 8 and C.sizeof(_capi.CnPolicyConfig) == 5 * 4
 

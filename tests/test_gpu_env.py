@@ -32,7 +32,8 @@ def test_cuda_env_matches_reference_golden(name):
 
     def step(a):
         obs, rew, done, info = env.step_device(torch.from_numpy(a).cuda())
-        out = dict(reward=rew.cpu().numpy(), done=done.cpu().numpy(), info=info.cpu().numpy())
+        out = dict(reward=rew.cpu().numpy(), done=done.cpu().numpy(), info=info.cpu().numpy(),
+                   info_aux=env._out["info_aux"].cpu().numpy())        # Danger.min_dist ('future' danger zone in tests)
         return _np_obs(obs), out
 
     bad = replay(g, case, lambda: _np_obs(env.reset()), step, env.get_state, pos_tol=1e-9)

@@ -14,7 +14,8 @@ import pytest
 from oracle.crowd_env import CrowdEnvOracle, EnvConfig
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5"]
+CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5", "env_pred_h20_test",
+         "env_pred_h10_test_rand"]
 
 
 def load_case(name):
@@ -47,7 +48,7 @@ def test_oracle_matches_reference_golden(name):
     T, N = g["actions"].shape[:2]
     obs_keys = [k[3:] for k in g.files if k.startswith("ob_")]
     for k in range(N):
-        env = CrowdEnvOracle(cfg, case["seed"] + k, case["nenv"], "train")
+        env = CrowdEnvOracle(cfg, case["seed"] + k, case["nenv"], case.get("phase", "train"))
         ob = env.reset()
         for key in obs_keys:
             np.testing.assert_allclose(ob[key], g["ob_" + key][0, k], rtol=0, atol=1e-6, err_msg=key)
@@ -58,7 +59,10 @@ def test_oracle_matches_reference_golden(name):
             assert bool(done) == bool(g["done"][t, k]), (name, k, t)
             assert info["info"] == g["info"][t, k], (name, k, t)
             np.testing.assert_allclose(rew, g["reward"][t, k], rtol=0, atol=1e-9)
-            ha = np.asarray(env.last_human_actions, dtype=np.float32)
+            np.testing.assert_allclose(info["min_danger"], g["min_danger"][t, k], rtol=0, atol=1e-9)
+            # the fixture reads the per-human simulators after the step = the last ORCA solve (in the test
+            # phase that is the final ground-truth look-ahead step)
+            ha = np.asarray(env.last_sim_actions, dtype=np.float32)
             ref_ha = g["human_actions"][t, k]
             ok = ~np.isnan(ref_ha[:, 0])
             assert np.array_equal(ha[ok], ref_ha[ok]), (name, k, t)        # bit-exact fp32 ORCA output

@@ -33,6 +33,12 @@ CASES = {
     # BASELINE config 1 (CrowdSimVarNum-v0, predict_method none, 5 humans, 4 envs)
     "env_varnum_h5": dict(env_name="CrowdSimVarNum-v0", human_num=5, predict_method="none",
                           randomize=False, goal_changing=False, nenv=4, steps=260, seed=425),
+    # phase='test' (SURVEY.md §8f row 1): ground-truth ORCA look-ahead before the reward, 'future' danger zone,
+    # test seeds (offset 1000, case_size = env.test_size)
+    "env_pred_h20_test": dict(env_name="CrowdSimPred-v0", human_num=20, predict_method="const_vel",
+                              randomize=False, goal_changing=False, nenv=3, steps=200, seed=425, phase="test"),
+    "env_pred_h10_test_rand": dict(env_name="CrowdSimPred-v0", human_num=10, predict_method="const_vel",
+                                   randomize=True, goal_changing=True, nenv=2, steps=200, seed=11, phase="test"),
 }
 
 
@@ -67,7 +73,7 @@ def build_reference_env(case, rank):
     env.configure(cfg)
     env.thisSeed = case["seed"] + rank
     env.nenv = case["nenv"]
-    env.phase = "train"
+    env.phase = case.get("phase", "train")
     return env, cfg
 
 
