@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   if (mode != 1) {
     CnF2 result; int nl, fail;
     orca_solve(true, result, nl, fail);                               // get_human_actions (crowd_sim.py:680-703)
-    if (p.test_phase && p.const_vel) {
+    if (p.test_phase) {
       // phase 'test': ground-truth look-ahead (crowd_sim_pred.py:136-138 -> crowd_sim_var_num.py:180-206):
       // lookahead_steps nested solves on a scratch copy of the joint state kept in the same shared arrays
       // (every thread saves / restores its own human), then the 'future' danger zone inputs for the reward.

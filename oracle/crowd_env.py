@@ -422,8 +422,8 @@ class CrowdEnvOracle(object):
         human_actions = self._human_actions()
         # what reading the per-human simulators after the step shows (tools/make_golden.py does that): the LAST solve
         self.last_sim_actions = human_actions
-        if self.phase == "test" and c.predict_method == "const_vel":
-            self._truth_future_traj()          # crowd_sim_pred.py:136-138 (number of intrusions in testing)
+        if self.phase == "test":
+            self._truth_future_traj()          # crowd_sim_pred.py:136-138 / crowd_sim_var_num.py:386-388
         reward, done, info, min_danger = self._calc_reward()
         # integrate (agent.py:143-183)
         self.rpx = self.rpx + avx * c.time_step

@@ -69,7 +69,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
         cn_orca_lp3_warp(co, W, nl, vmax, proj, result, fail);
         cn_orca_finish(p, g, s, e, h, result, nl, fail);
       }
-      if (p.test_phase && p.const_vel) {
+      if (p.test_phase) {
         // ground-truth look-ahead (phase 'test'): lookahead_steps nested ORCA solves of every human on a
         // scratch copy of the joint state; mirrors the look-ahead loop of cn_env_step_kernel
         std::vector<double> sx(s.px, s.px + H), sy(s.py, s.py + H), lx(sx), ly(sy);

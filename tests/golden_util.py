@@ -8,7 +8,7 @@ import numpy as np
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ENV_CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5", "env_pred_h20_test",
-             "env_pred_h10_test_rand"]
+             "env_pred_h10_test_rand", "env_varnum_h5_test"]
 
 
 def load_env_case(name):

@@ -15,7 +15,7 @@ from oracle.crowd_env import CrowdEnvOracle, EnvConfig
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5", "env_pred_h20_test",
-         "env_pred_h10_test_rand"]
+         "env_pred_h10_test_rand", "env_varnum_h5_test"]
 
 
 def load_case(name):

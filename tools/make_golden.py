@@ -37,6 +37,8 @@ CASES = {
     # test seeds (offset 1000, case_size = env.test_size)
     "env_pred_h20_test": dict(env_name="CrowdSimPred-v0", human_num=20, predict_method="const_vel",
                               randomize=False, goal_changing=False, nenv=3, steps=200, seed=425, phase="test"),
+    "env_varnum_h5_test": dict(env_name="CrowdSimVarNum-v0", human_num=5, predict_method="none",
+                               randomize=False, goal_changing=False, nenv=2, steps=160, seed=425, phase="test"),
     "env_pred_h10_test_rand": dict(env_name="CrowdSimPred-v0", human_num=10, predict_method="const_vel",
                                    randomize=True, goal_changing=True, nenv=2, steps=200, seed=11, phase="test"),
 }
@@ -82,6 +84,8 @@ def ref_state(env, cfg):
     f = lambda name: np.array([float(getattr(h, name)) for h in env.humans], dtype=np.float64)
     r = env.robot
     traj = getattr(env, "human_future_traj", None)
+    if cfg.sim.predict_method == "none":
+        traj = None       # VarNum keeps no prediction (the test-phase look-ahead buffer is internal)
     return dict(
         robot=np.array([r.px, r.py, r.vx, r.vy, r.gx, r.gy], dtype=np.float64),
         hpx=f("px"), hpy=f("py"), hvx=f("vx"), hvy=f("vy"), hgx=f("gx"), hgy=f("gy"),
