@@ -148,12 +148,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
                   const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                   const __grid_constant__ CUtensorMap map_c32, const __grid_constant__ CUtensorMap map_ohi,
                   const __grid_constant__ CUtensorMap map_olo, int M, int N, int K, TcEpilogue ep) {
-  if (ep.m_ptr) { const int mc = *ep.m_ptr; M = mc < M ? mc : M; }
-  int m_lo = ep.m0_ptr ? *ep.m0_ptr : 0;
-  if (m_lo > M) m_lo = M;
-  const int n_ntiles = N / BN;
-  const int n_tiles = ((M - m_lo + TC_BM - 1) / TC_BM) * n_ntiles;
-  if ((int)blockIdx.x >= n_tiles) return;           // uniform for the whole CTA: before any barrier / TMEM use
+  cn_pdl_trigger();                                 // PDL: the successor may be scheduled while this grid runs
   constexpr int TC_STAGES = TcCfg<BN>::kStages;
   constexpr int TC_B_TILE_BYTES = TcCfg<BN>::kBTile;
   constexpr int TC_STAGE_BYTES = TcCfg<BN>::kStageBytes;
@@ -200,6 +195,14 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail;
+  // global memory written by it (row counts, operands, bias) is only touched after this wait
+  cn_pdl_wait();
+  if (ep.m_ptr) { const int mc = *ep.m_ptr; M = mc < M ? mc : M; }
+  int m_lo = ep.m0_ptr ? *ep.m0_ptr : 0;
+  if (m_lo > M) m_lo = M;
+  const int n_ntiles = N / BN;
+  const int n_tiles = ((M - m_lo + TC_BM - 1) / TC_BM) * n_ntiles;   // CTAs beyond it run zero tiles and tear down
 
   if (warp == 0) {
     // ===================== TMA producer =====================

@@ -36,6 +36,7 @@ struct cn_policy {
   int64_t launches;
   int attn_hpc;        // heads per CTA of the HH attention kernel
   int num_sms;
+  bool pdl;           // programmatic dependent launch along the kernel chain (CN_PDL=0 disables)
   bool launch_error;  // a GEMM output map could not be built (cn_last_error has the reason)
   int qkv_chunks;     // 1 (default): single pass; 2 (CN_QKV_CHUNKS=2): QKV + attention in two row chunks with overlap
   bool finalized;
@@ -178,6 +179,22 @@ int tc_view(TcMat& v, const TcMat& src, int col0, int rows, int K, int box_rows)
   return rc;
 }
 
+// Kernel launch with (optionally) programmatic dependent launch: the kernel may be scheduled before its
+// predecessor in the stream has finished; every kernel of the chain calls griddepcontrol.wait before touching
+// global memory (cn_pdl_prologue / cn_pdl_wait), so the data dependencies are unchanged.
+template <typename... KArgs, typename... Args>
+void launch_k(cn_policy* p, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = p->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  p->launches += 1;
+}
+
 void split16(cn_policy* p, cudaStream_t st, const float* src, float scale, __half* hi, __half* lo, size_t count) {
   cn_split_f16_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(src, scale, hi, lo, count);
   p->launches += 1;
@@ -207,12 +224,11 @@ void gemm_tc(cn_policy* p, cudaStream_t st, const TcMat& A, const TcMat& B, int 
   const CUtensorMap* mlo = o.ol ? out_map(p, o.ol, 2, N, M, o.ldh) : &A.mh;
   if (!mc32 || !mhi || !mlo) { p->launch_error = true; return; }
   if (bn == 256)
-    cn_gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, *mc32, *mhi, *mlo, M, N,
-                                                                             K, ep);
+    launch_k(p, cn_gemm_tc_kernel<256>, grid, dim3(TC_THREADS), TcCfg<256>::kSmemBytes, st, A.mh, A.ml, B.mh, B.ml, *mc32, *mhi,
+             *mlo, M, N, K, ep);
   else
-    cn_gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, st>>>(A.mh, A.ml, B.mh, B.ml, *mc32, *mhi, *mlo, M, N, K,
-                                                                           ep);
-  p->launches += 1;
+    launch_k(p, cn_gemm_tc_kernel<64>, grid, dim3(TC_THREADS), TcCfg<64>::kSmemBytes, st, A.mh, A.ml, B.mh, B.ml, *mc32, *mhi,
+             *mlo, M, N, K, ep);
 }
 TcOut out32(float* c, int ldc) { TcOut o; o.c32 = c; o.ldc = ldc; return o; }
 TcOut out16(const TcMat& t) { TcOut o; o.oh = t.hi; o.ol = t.lo; o.ldh = t.pitch; return o; }
@@ -231,8 +247,7 @@ void gemm(cn_policy* p, cudaStream_t st, const float* A, int lda, const float* W
           float* C, int ldc, int M, int N, int K, int act, int act_lo = 0, int act_hi = 1 << 30,
           const int* m_ptr = nullptr, __half* oh = nullptr, __half* ol = nullptr) {
   dim3 grid((N + CN_GEMM_BN - 1) / CN_GEMM_BN, (M + CN_GEMM_BM - 1) / CN_GEMM_BM);
-  cn_gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, act_lo, act_hi, m_ptr, oh, ol);
-  p->launches += 1;
+  launch_k(p, cn_gemm_f32_kernel, grid, dim3(256), 0, st, A, lda, W, ldw, bias, C, ldc, M, N, K, act, act_lo, act_hi, m_ptr, oh, ol);
 }
 
 const char* kStageNames[] = {"pack_inputs", "embed1_gemm", "embed2_gemm", "qkv_gemm", "hh_attention",
@@ -289,6 +304,8 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   p->num_sms = 148;
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   {
+    const char* pd = getenv("CN_PDL");
+    p->pdl = !(pd && pd[0] == '0');
     const char* qc = getenv("CN_QKV_CHUNKS");
     p->qkv_chunks = (qc && qc[0] == '2') ? 2 : 1;
   }
@@ -511,13 +528,12 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   mark(p, st, 0);
   // 0. compaction offsets, pack / pad inputs, h0 = h * mask
   {
-    cn_row_offsets_kernel<<<1, 1024, 0, st>>>(d->detected_human_num, N, H, p->row_start, p->mc);
+    launch_k(p, cn_row_offsets_kernel, dim3(1), dim3(1024), 0, st, d->detected_human_num, N, H, p->row_start, p->mc);
     const int total = (!tcm && M * 16 > N * 128) ? M * 16 : N * 128;
-    cn_pack_inputs_kernel<<<(total + 255) / 256, 256, 0, st>>>(d->spatial_edges, p->Win, H, N, p->row_start, p->row_env,
+    launch_k(p, cn_pack_inputs_kernel, dim3((total + 255) / 256), dim3(256), 0, st, d->spatial_edges, p->Win, H, N, p->row_start, p->row_env,
                                                                tcm ? nullptr : p->x16,
                                                                d->temporal_edges, d->robot_node, d->h_in, d->masks, p->xr,
                                                                p->h0, tcm ? p->tH0.hi : nullptr, tcm ? p->tH0.lo : nullptr);
-    p->launches += 2;
   }
   // fork: the robot branch (rs, [enc|te], u) and gh only depend on the packed inputs
   cudaStream_t s2 = p->st2;
@@ -538,9 +554,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   // 1. human-human branch over the Mc = sum_e n_e valid rows (device-side count p->mc)
   mark(p, st, 1);
   if (tcm) {
-    cn_embed1_kernel<<<p->num_sms * 6, 256, 0, st>>>(d->spatial_edges, p->Win, H, p->row_start, p->row_env, p->mc, p->W1, p->b1,
+    launch_k(p, cn_embed1_kernel, dim3(p->num_sms * 6), dim3(256), 0, st, d->spatial_edges, p->Win, H, p->row_start, p->row_env, p->mc, p->W1, p->b1,
                                                      p->tE1.hi, p->tE1.lo);
-    p->launches += 1;
   } else gemm(p, st, p->x16, 16, p->W1, 16, p->b1, p->e1, 128, M, 128, 16, CN_ACT_RELU, 0, ALL, mc);
   mark(p, st, 2);
   if (tcm) gemm_tc(p, st, p->tE1, p->tW2, M, 512, 128, 256, p->b2, CN_ACT_RELU, out16(p->tE2), mc);
@@ -556,29 +571,26 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
     if (p->qkv_chunks == 1) {
       gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc);
       mark(p, st, 4);
-      cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, mc, nullptr,
+      launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, nullptr,
                                                                              nullptr, ah, al);
-      p->launches += 1;
     } else {
     gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mid);
     cudaEventRecord(p->ev_fork3, st);
     cudaStreamWaitEvent(p->st3, p->ev_fork3, 0);
-    cn_hh_attention_kernel<<<p->num_sms * 8, CN_ATTN_WARPS * 32, 0, p->st3>>>(p->qkv, p->row_start, p->row_env, mid, nullptr,
+    launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 8), dim3(CN_ATTN_WARPS * 32), 0, p->st3, p->qkv, p->row_start, p->row_env, mid, nullptr,
                                                                               nullptr, ah, al);
     cudaEventRecord(p->ev_join3, p->st3);
     gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc, 0, 1 << 30, mid);
     mark(p, st, 4);
-    cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, mc, mid, nullptr,
+    launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, mid, nullptr,
                                                                            ah, al);
     cudaStreamWaitEvent(st, p->ev_join3, 0);
-    p->launches += 2;
     }
   } else {
     gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
     mark(p, st, 4);
-    cn_hh_attention_kernel<<<p->num_sms * 16, CN_ATTN_WARPS * 32, 0, st>>>(p->qkv, p->row_start, p->row_env, p->mc, nullptr,
+    launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, p->mc, nullptr,
                                                                            p->ao, nullptr, nullptr);
-    p->launches += 1;
   }
   mark(p, st, 5);
   if (tcm) gemm_tc(p, st, p->tAo, p->tWos, M, 256, 512, 256, p->bos, CN_ACT_RELU, out32(p->sout, 256), mc);
@@ -587,9 +599,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   mark(p, st, 6);
   cudaStreamWaitEvent(st, p->ev_join, 0);
   mark(p, st, 7);
-  cn_hr_attention_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->sout, p->u, p->t1, 128, 64, p->bs, p->row_start, N, H, p->wv,
+  launch_k(p, cn_hr_attention_kernel, dim3((N + 3) / 4), dim3(128), 0, st, p->sout, p->u, p->t1, 128, 64, p->bs, p->row_start, N, H, p->wv,
                                                       tcm ? p->tWv.hi : nullptr, tcm ? p->tWv.lo : nullptr);
-  p->launches += 1;
   // 3. GRU: emb overwrites the te half of t1 -> t1 = [enc | emb] = GRU input (gh came from the side stream)
   mark(p, st, 8);
   if (tcm) {
@@ -600,9 +611,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
     gemm(p, st, p->wv, 256, p->Wa, 256, p->ba, p->t1 + 64, 128, N, 64, 256, CN_ACT_RELU);
     gemm(p, st, p->t1, 128, p->Wih, 128, p->bih, p->gi, 384, N, 384, 128, CN_ACT_NONE);
   }
-  cn_gru_gate_kernel<<<(N * 128 + 255) / 256, 256, 0, st>>>(p->gi, p->gh, p->h0, N, d->h_out, tcm ? p->tH1.hi : nullptr,
+  launch_k(p, cn_gru_gate_kernel, dim3((N * 128 + 255) / 256), dim3(256), 0, st, p->gi, p->gh, p->h0, N, d->h_out, tcm ? p->tH1.hi : nullptr,
                                                             tcm ? p->tH1.lo : nullptr);
-  p->launches += 1;
   // 4. output_linear, actor / critic MLPs (critic.2 on the side stream), heads
   mark(p, st, 9);
   if (tcm) {
@@ -621,9 +631,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
     gemm(p, st, p->ac1, 512, p->Wa2, 256, p->ba2, p->a2, 256, N, 256, 256, CN_ACT_TANH);
   }
   cudaStreamWaitEvent(st, p->ev_join2, 0);
-  cn_heads_kernel<<<(N + 3) / 4, 128, 0, st>>>(p->a2, 256, p->c2, 256, p->wv_, p->bv, p->Wm, p->bm, p->logstd, d->noise, N,
+  launch_k(p, cn_heads_kernel, dim3((N + 3) / 4), dim3(128), 0, st, p->a2, 256, p->c2, 256, p->wv_, p->bv, p->Wm, p->bm, p->logstd, d->noise, N,
                                                d->value, d->action, d->log_prob, d->action_mean);
-  p->launches += 1;
   mark(p, st, kNumStages);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_policy_act launch: %s", cudaGetErrorString(err));
@@ -651,7 +660,7 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
   cn_policy tmp;
   tmp.launches = 0;
   tmp.st2 = nullptr; tmp.st3 = nullptr;
-  tmp.num_sms = 148; tmp.qkv_chunks = 1; tmp.launch_error = false;
+  tmp.num_sms = 148; tmp.qkv_chunks = 1; tmp.launch_error = false; tmp.pdl = false;
   cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, 0);
   TcMat A, B;
   int rc = tc_alloc(&tmp, A, M, K, TC_BM);

@@ -15,6 +15,14 @@ enum { CN_ACT_NONE = 0, CN_ACT_RELU = 1, CN_ACT_TANH = 2 };
 // fp32 CUDA-core GEMM:  C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]),  act on columns [act_lo, act_hi).
 // 128x128x16 tiles, 256 threads, 8x8 register tile per thread, register-prefetched double
 // buffering through shared memory.  K % 16 == 0 (buffers are zero padded), M and N ragged.
+// Programmatic dependent launch (PDL): kernels of the policy chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization; each one lets its successor be scheduled as early as
+// possible (launch_dependents) and itself waits for the full completion + memory flush of its predecessor
+// (wait) before it touches global memory.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void cn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void cn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cn_pdl_prologue() { cn_pdl_trigger(); cn_pdl_wait(); }
+
 #define CN_GEMM_BM 128
 #define CN_GEMM_BN 128
 #define CN_GEMM_BK 16
@@ -32,6 +40,7 @@ __global__ void __launch_bounds__(256) cn_gemm_f32_kernel(const float* __restric
                                                           int ldc, int M, int N, int K, int act, int act_lo,
                                                           int act_hi, const int* __restrict__ m_ptr,
                                                           __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  cn_pdl_prologue();
   // m_ptr: optional device-side row count (compacted human rows); tiles past it exit immediately
   if (m_ptr) { const int mc = *m_ptr; M = mc < M ? mc : M; }
   if ((int)(blockIdx.y * CN_GEMM_BM) >= M) return;
@@ -177,6 +186,7 @@ __global__ void cn_fold_mv_kernel(const float* __restrict__ A, const float* __re
 // Single CTA, 1024 threads, chunked inclusive scan (N <= a few 10^4).
 __global__ void __launch_bounds__(1024) cn_row_offsets_kernel(const float* __restrict__ detected, int N, int H,
                                                               int* __restrict__ row_start, int* __restrict__ mc) {
+  cn_pdl_prologue();
   __shared__ int warp_sums[32];
   __shared__ int carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -216,6 +226,7 @@ __global__ void cn_pack_inputs_kernel(const float* __restrict__ spatial, int Win
                                       const float* __restrict__ h_in, const float* __restrict__ masks,
                                       float* __restrict__ xr, float* __restrict__ h0, __half* __restrict__ h0_hi,
                                       __half* __restrict__ h0_lo) {
+  cn_pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (x16 && idx < N * H * 16) {
     const int r = idx >> 4, c = idx & 15;
@@ -262,6 +273,7 @@ __global__ void __launch_bounds__(256) cn_embed1_kernel(const float* __restrict_
                                                         const float* __restrict__ W1 /* [128][16], zero padded */,
                                                         const float* __restrict__ b1, __half* __restrict__ e_hi,
                                                         __half* __restrict__ e_lo /* [Mc,128] */) {
+  cn_pdl_prologue();
   __shared__ __align__(16) float ws[16][128];        // transposed weights: ws[c][out]
   for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) ws[i & 15][i >> 4] = W1[i];
   __syncthreads();
@@ -325,6 +337,7 @@ __global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(con
                                                                              float* __restrict__ out /* [Mc,512] or null */,
                                                                              __half* __restrict__ out_hi,
                                                                              __half* __restrict__ out_lo) {
+  cn_pdl_prologue();
   __shared__ float sc[CN_ATTN_WARPS][CN_ATTN_MAXKEYS][8];       // scores [key][half * 4 + chunk]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mc = *mc_ptr;
@@ -462,6 +475,7 @@ __global__ void __launch_bounds__(128) cn_hr_attention_kernel(const float* __res
                                                               const int* __restrict__ row_start, int N, int H,
                                                               float* __restrict__ wv /* [N,256] */,
                                                               __half* __restrict__ wv_hi, __half* __restrict__ wv_lo) {
+  cn_pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 4 + warp;
   if (e >= N) return;
@@ -527,6 +541,7 @@ __device__ __forceinline__ float cn_sigmoid(float x) { return 1.0f / (1.0f + exp
 __global__ void cn_gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
                                    const float* __restrict__ h0, int N, float* __restrict__ h1,
                                    __half* __restrict__ h1_hi, __half* __restrict__ h1_lo) {
+  cn_pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * 128) return;
   const int e = idx >> 7, c = idx & 127;
@@ -555,6 +570,7 @@ __global__ void __launch_bounds__(128) cn_heads_kernel(const float* __restrict__
                                                        const float* __restrict__ noise, int N,
                                                        float* __restrict__ value, float* __restrict__ action,
                                                        float* __restrict__ logp, float* __restrict__ mean_out) {
+  cn_pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 4 + warp;
   if (e >= N) return;
