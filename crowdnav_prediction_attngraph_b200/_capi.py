@@ -57,6 +57,8 @@ EXPORTS = [
     "cn_policy_create", "cn_policy_destroy", "cn_policy_set_param", "cn_policy_finalize",
     "cn_policy_act", "cn_policy_launch_count", "cn_policy_last_rows", "cn_policy_profile", "cn_policy_stage_count",
     "cn_policy_stage_name", "cn_policy_stage_ms", "cn_copy_segments",
+    "cn_gst_create", "cn_gst_destroy", "cn_gst_set_param", "cn_gst_finalize", "cn_gst_reset", "cn_gst_step",
+    "cn_gst_launch_count",
 ]
 
 _lib = None
@@ -111,6 +113,19 @@ def load_library(path=None):
     lib.cn_env_state_bytes.restype = C.c_size_t
     lib.cn_env_state_bytes.argtypes = [C.c_void_p, C.c_char_p]
     lib.cn_env_state_copy.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
+    lib.cn_gst_create.restype = C.c_int
+    lib.cn_gst_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+    lib.cn_gst_destroy.argtypes = [C.c_void_p]
+    lib.cn_gst_set_param.restype = C.c_int
+    lib.cn_gst_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    lib.cn_gst_finalize.restype = C.c_int
+    lib.cn_gst_finalize.argtypes = [C.c_void_p]
+    lib.cn_gst_reset.restype = C.c_int
+    lib.cn_gst_reset.argtypes = [C.c_void_p, C.c_void_p]
+    lib.cn_gst_step.restype = C.c_int
+    lib.cn_gst_step.argtypes = [C.c_void_p] * 7 + [C.c_void_p]
+    lib.cn_gst_launch_count.restype = C.c_int64
+    lib.cn_gst_launch_count.argtypes = [C.c_void_p]
     lib.cn_copy_segments.restype = C.c_int
     lib.cn_copy_segments.argtypes = [C.POINTER(CnCopySeg), C.c_int, C.c_int, C.c_void_p]
     lib.cn_env_launch_count.restype = C.c_int64

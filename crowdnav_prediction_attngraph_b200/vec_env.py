@@ -309,14 +309,120 @@ class CudaCrowdVecEnv(object):
 
 def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, device, allow_early_resets,
                   num_frame_stack=None, config=None, ax=None, test_case=-1, wrap_pytorch=True,
-                  pretext_wrapper=False, nenv_total=None, rank_offset=0, phase=None):
+                  pretext_wrapper=False, nenv_total=None, rank_offset=0, phase=None, gst_params=None):
     """Same signature as rl/networks/envs.py:97-140.  Returns the CUDA vec env (already 'VecPyTorch').
     Like the reference (envs.py:55-58) a single environment runs in phase 'test', several in 'train';
     `phase=` overrides (batched evaluation)."""
-    if pretext_wrapper:
-        raise NotImplementedError("VecPretextNormalize / GST predictor is the 'next' row (SURVEY.md §8f row 2)")
     device = torch.device(device)
+    if pretext_wrapper or env_name == "CrowdSimPredRealGST-v0":
+        if gst_params is None:
+            raise ValueError("CrowdSimPredRealGST-v0 / pretext_wrapper=True needs gst_params= (the predictor checkpoint's "
+                             "model_state_dict, config.pred.model_dir/checkpoint/epoch_100.pt)")
+        d = config_dict_from_reference(config, num_processes, seed, "CrowdSimVarNum-v0", nenv_total=nenv_total,
+                                       rank_offset=rank_offset, device_index=device.index if device.index is not None else 0,
+                                       phase=phase)
+        return CudaPretextVecEnv(gst_params, device=device, cfg=d)
     d = config_dict_from_reference(config, num_processes, seed, env_name, nenv_total=nenv_total,
                                    rank_offset=rank_offset,
                                    device_index=device.index if device.index is not None else 0, phase=phase)
     return CudaCrowdVecEnv(device=device, cfg=d)
+
+
+class CudaPretextVecEnv(object):
+    """`VecPretextNormalize(ShmemVecEnv([CrowdSimPredRealGST-v0 ...]))` on one GPU (BASELINE config 3).
+
+    The environments run in the engine's CrowdSimVarNum-v0 mode without sorting (that IS the raw RealGST
+    observation, crowd_sim_pred_real_gst.py:73-88); one fused kernel per step keeps the wrapper's 5-frame
+    trajectory / mask buffers, runs the GST predictor, adds the future-collision penalty to the reward, writes the
+    predicted relative positions into the 2(P+1)-wide spatial_edges and sorts the rows by distance
+    (rl/vec_env/vec_pretext_normalize.py:112-191).  Like the reference, the buffers are NOT cleared when a
+    single environment finishes an episode.  `gst_params`: dict name -> array with the predictor checkpoint's
+    model_state_dict (e.g. np.load('tests/golden/gst_params.npz'))."""
+
+    def __init__(self, gst_params, num_envs=None, device=None, cfg=None, **cfg_over):
+        over = dict(cfg_over)
+        d = dict(cfg) if cfg is not None else None
+        if d is not None:
+            d.update(const_vel=0, sort_humans=0)
+        else:
+            over.update(const_vel=0, sort_humans=0)
+        self.env = CudaCrowdVecEnv(num_envs=num_envs, device=device, cfg=d, **over)
+        e = self.env
+        self.lib, self.device, self.cfgd = e.lib, e.device, e.cfgd
+        self.num_envs, self.human_num = e.num_envs, e.human_num
+        self.P = int(self.cfgd["predict_steps"])
+        N, H, W = self.num_envs, self.human_num, 2 * (self.P + 1)
+        self.row_width = W
+        spaces = dict(e.observation_space.spaces)
+        spaces['spatial_edges'] = Box((H, W))
+        self.observation_space = _DictSpace(spaces)
+        self.action_space = e.action_space
+        self._h = C.c_void_p()
+        _capi.check(self.lib, self.lib.cn_gst_create(N, H, self.P, float(self.cfgd["robot_radius"]),
+                                                     float(self.cfgd["human_radius"]), float(self.cfgd["collision_penalty"]),
+                                                     self.device.index or 0, C.byref(self._h)), "cn_gst_create")
+        for k, v in gst_params.items():
+            arr = np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+            _capi.check(self.lib, self.lib.cn_gst_set_param(self._h, k.encode(), arr.ctypes.data, arr.size),
+                        "cn_gst_set_param(%s)" % k)
+        _capi.check(self.lib, self.lib.cn_gst_finalize(self._h), "cn_gst_finalize")
+        self._sp = [torch.zeros(N, H, W, device=self.device) for _ in range(2)]
+        self._pen = torch.zeros(N, device=self.device)
+        self._flip = 0
+        self.closed = False
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _process(self, obs, reward):
+        self._flip ^= 1
+        sp = self._sp[self._flip]
+        vm = obs['visible_masks']
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib, self.lib.cn_gst_step(
+                self._h, C.c_void_p(obs['robot_node'].data_ptr()), C.c_void_p(obs['spatial_edges'].data_ptr()),
+                C.c_void_p(vm.data_ptr()), C.c_void_p(reward.data_ptr()) if reward is not None else None,
+                C.c_void_p(self._pen.data_ptr()), C.c_void_p(sp.data_ptr()), self._stream()), "cn_gst_step")
+        out = dict(obs)
+        out['spatial_edges'] = sp
+        out['visible_masks'] = vm.bool() if vm.dtype != torch.bool else vm
+        return out
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib, self.lib.cn_gst_reset(self._h, self._stream()), "cn_gst_reset")
+        return self._process(self.env.reset(), None)
+
+    def step_device(self, actions):
+        """Device-resident step: (obs, reward [N] incl. the prediction penalty, done [N] u8, info [N] i32)."""
+        obs, reward, done, info = self.env.step_device(actions)
+        return self._process(obs, reward), reward, done, info
+
+    def step(self, actions):
+        obs, reward, done, info = self.step_device(actions)
+        e = self.env
+        e._host_packed.copy_(e._out_packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        h = e._host
+        done_np = h["done"].numpy().astype(np.bool_)
+        infos = LazyInfos(h["info"].numpy().copy(), h["info_aux"].numpy().copy(), done_np, h["ep_ret"].numpy().copy(),
+                          h["ep_len"].numpy().copy())
+        return obs, h["reward"].clone().unsqueeze(1), done_np, infos
+
+    def talk2Env(self, data):
+        return np.ones(self.num_envs, dtype=bool)
+
+    def launch_count(self):
+        return self.env.launch_count() + int(self.lib.cn_gst_launch_count(self._h))
+
+    def close(self):
+        if not self.closed:
+            self.lib.cn_gst_destroy(self._h)
+            self.env.close()
+            self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

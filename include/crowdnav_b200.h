@@ -93,6 +93,24 @@ typedef struct cn_copy_seg {
 } cn_copy_seg;
 int cn_copy_segments(const cn_copy_seg *segs, int n, int device, void *stream);
 
+/* BASELINE config 3: GST trajectory predictor + VecPretextNormalize processing (one fused launch per step).
+ * replaces: VecPretextNormalize.reset / process_obs_rew (rl/vec_env/vec_pretext_normalize.py:85-191) and
+ * CrowdNavPredInterfaceMultiEnv.forward (gst_updated/scripts/wrapper/crowd_nav_interface_parallel.py:45-114).     */
+typedef struct cn_gst cn_gst;
+int cn_gst_create(int num_envs, int human_num, int predict_steps, double robot_radius, double human_radius,
+                  double collision_penalty, int device, cn_gst **out);
+int cn_gst_destroy(cn_gst *g);
+/* name = key of the predictor checkpoint's model_state_dict (st_model), data = float32 host array              */
+int cn_gst_set_param(cn_gst *g, const char *name, const float *data, size_t count);
+int cn_gst_finalize(cn_gst *g);
+int cn_gst_reset(cn_gst *g, void *stream);
+/* d_robot_node [N,7], d_spatial2 [N,H,2], d_visible [N,H]: raw CrowdSimPredRealGST-v0 observation (unsorted);
+ * d_reward [N] in/out or NULL (+= future-collision penalty), d_penalty [N] out or NULL,
+ * d_spatial_out [N,H,2*(predict_steps+1)]: predicted, distance-sorted spatial_edges.                           */
+int cn_gst_step(cn_gst *g, const float *d_robot_node, const float *d_spatial2, const uint8_t *d_visible,
+                float *d_reward, float *d_penalty, float *d_spatial_out, void *stream);
+int64_t cn_gst_launch_count(cn_gst *g);
+
 typedef struct cn_env cn_env;
 
 const char *cn_last_error(void);
