@@ -29,7 +29,7 @@ namespace {
 
 #define GST_D 64
 #define GST_T 5          // observed frames = predicted steps
-#define GST_THREADS 256
+#define GST_THREADS 1024
 #define GST_INVALID (-999.0f)
 
 struct GstW {
@@ -37,30 +37,36 @@ struct GstW {
   const float *W1_t, *b1, *W2_t, *b2, *Wih_t, *bih, *Whh_t, *bhh, *Wp, *bp;
 };
 
-// out[r][c] = act(res[r][c] + bias[c] + sum_k in[r][k] * Wt[k][c]); 4 x 4 register tiles, column tiles fastest
-// across the threads (coalesced float4 weight loads, broadcast activation loads).  R % 4 == 0, Nout % 4 == 0.
-__device__ void gst_dense(const float* __restrict__ in, int ldi, const float* __restrict__ Wt, const float* __restrict__ bias,
-                          const float* res, int ldr, float* out, int ldo, int R, int K, int Nout, bool relu) {
-  const int ct = Nout >> 2, rt = R >> 2;
+// out[r][c] = act(res[r][c] + bias[c] + sum_k in[r][k] * Wt[k][c]); RT x 4 register tiles, column tiles fastest
+// across the threads (coalesced float4 weight loads, broadcast activation loads).  R % RT == 0, Nout % 4 == 0.
+template <int RT>
+__device__ void gst_dense_t(const float* __restrict__ in, int ldi, const float* __restrict__ Wt, const float* __restrict__ bias,
+                            const float* res, int ldr, float* out, int ldo, int R, int K, int Nout, bool relu) {
+  const int ct = Nout >> 2, rt = R / RT;
   for (int tile = threadIdx.x; tile < ct * rt; tile += blockDim.x) {
-    const int c0 = (tile % ct) << 2, r0 = (tile / ct) << 2;
-    float acc[4][4];
+    const int c0 = (tile % ct) << 2, r0 = (tile / ct) * RT;
+    float acc[RT][4];
     const float4 b = *reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w; }
+    for (int i = 0; i < RT; ++i) { acc[i][0] = b.x; acc[i][1] = b.y; acc[i][2] = b.z; acc[i][3] = b.w; }
     const float* ip = in + (size_t)r0 * ldi;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * Nout + c0));
+    for (int k = 0; k < K; k += 4) {                       // K % 4 == 0; activations fetched as LDS.128 over k
+      float4 wv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = ip[i * ldi + k];
-        acc[i][0] = fmaf(a, w.x, acc[i][0]); acc[i][1] = fmaf(a, w.y, acc[i][1]);
-        acc[i][2] = fmaf(a, w.z, acc[i][2]); acc[i][3] = fmaf(a, w.w, acc[i][3]);
+      for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k + kk) * Nout + c0));
+#pragma unroll
+      for (int i = 0; i < RT; ++i) {
+        const float4 a4 = *reinterpret_cast<const float4*>(ip + i * ldi + k);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[i][0] = fmaf(a[kk], wv[kk].x, acc[i][0]); acc[i][1] = fmaf(a[kk], wv[kk].y, acc[i][1]);
+          acc[i][2] = fmaf(a[kk], wv[kk].z, acc[i][2]); acc[i][3] = fmaf(a[kk], wv[kk].w, acc[i][3]);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RT; ++i) {
       float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       if (res) {
         const float4 r = *reinterpret_cast<const float4*>(res + (size_t)(r0 + i) * ldr + c0);
@@ -70,6 +76,14 @@ __device__ void gst_dense(const float* __restrict__ in, int ldi, const float* __
       *reinterpret_cast<float4*>(out + (size_t)(r0 + i) * ldo + c0) = v;
     }
   }
+}
+// tile height chosen so that (almost) every thread of the CTA gets a tile
+__device__ void gst_dense(const float* __restrict__ in, int ldi, const float* __restrict__ Wt, const float* __restrict__ bias,
+                          const float* res, int ldr, float* out, int ldo, int R, int K, int Nout, bool relu) {
+  const int ct = Nout >> 2;
+  if ((R >> 2) * ct >= (int)blockDim.x) gst_dense_t<4>(in, ldi, Wt, bias, res, ldr, out, ldo, R, K, Nout, relu);
+  else if ((R >> 1) * ct >= (int)blockDim.x) gst_dense_t<2>(in, ldi, Wt, bias, res, ldr, out, ldo, R, K, Nout, relu);
+  else gst_dense_t<1>(in, ldi, Wt, bias, res, ldr, out, ldo, R, K, Nout, relu);
 }
 
 // LayerNorm over the 64 features of every row (one warp per row, two features per lane), optional row mask.

@@ -17,6 +17,8 @@ CONFIGS = {
     "c4": (dict(human_num=50, randomize_attributes=1, random_goal_changing=1, goal_change_chance=0.5), 2048),
     "c2_h50": (dict(human_num=50), 4096),
     "c1_varnum": (dict(human_num=5, const_vel=0), 4096),
+    # BASELINE config 3: CrowdSimPredRealGST-v0 + VecPretextNormalize (GST predictor), H = 20, N = 4096
+    "c3": (dict(human_num=20), 4096),
 }
 
 
@@ -27,6 +29,8 @@ def run(name, steps, warmup):
     from crowdnav_prediction_attngraph_b200.storage import RolloutStorage
     kw, N = CONFIGS[name]
     dev = torch.device("cuda", 0)
+    if name == "c3":
+        return run_c3(kw, N, dev, steps, warmup)
     env = CudaCrowdVecEnv(num_envs=N, nenv_total=N, rank_offset=0, seed=425, device=dev, **kw)
 
     class Args(object):
@@ -68,6 +72,50 @@ def run(name, steps, warmup):
                       "env_only_ms_per_step": ms_env, "valid_human_rows": int(eng.lib.cn_policy_last_rows(eng._h)),
                       "spawn_overflow_envs": overflow}))
     del eng, policy, env
+
+
+def run_c3(kw, N, dev, steps, warmup):
+    import numpy as np
+    import torch
+    from crowdnav_prediction_attngraph_b200.vec_env import CudaPretextVecEnv
+    from crowdnav_prediction_attngraph_b200.policy import Policy
+    params = dict(np.load(os.path.join(REPO, "tests", "golden", "gst_params.npz")))
+    env = CudaPretextVecEnv(params, num_envs=N, nenv_total=N, rank_offset=0, seed=425, device=dev, **kw)
+
+    class Args(object):
+        num_processes, seq_length, num_mini_batch = N, 30, 2
+    torch.manual_seed(425)
+    policy = Policy(env.observation_space.spaces, env.action_space, base_kwargs=Args(), base='selfAttn_merge_srnn').to(dev)
+    eng = policy._engine(N, dev)
+    obs = env.reset()
+    h = torch.zeros(N, 1, 128, device=dev)
+    masks = torch.ones(N, 1, device=dev)
+
+    def step(obs, h, masks):
+        value, action, logp, h2 = eng.act(obs, h, masks)
+        obs, rew, done, info = env.step_device(action)
+        return obs, h2, (1.0 - done.float()).unsqueeze(1)
+
+    for _ in range(warmup):
+        obs, h, masks = step(obs, h, masks)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        obs, h, masks = step(obs, h, masks)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    raw = env.env.reset()
+    f0.record()
+    for _ in range(20):
+        env._process(raw, None)
+    f1.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"config": "c3", "env_kwargs": kw, "envs": N, "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3,
+                      "gst_pretext_kernel_ms": f0.elapsed_time(f1) / 20,
+                      "valid_human_rows": int(eng.lib.cn_policy_last_rows(eng._h))}))
 
 
 if __name__ == "__main__":
