@@ -169,6 +169,17 @@ class CudaPolicy(object):
             pass
 
 
+def _hh_attention(q, k, v, valid):
+    """softmax(q k^T / 8 + key mask) v for [B, 8, H, 64] tensors with H <= ~20 keys.  Written as two batched
+    matmuls: at this shape the fused 'memory efficient' SDPA kernels (64 x 64 tiles for a 20-key sequence) cost
+    3x the explicit form in forward + backward (CN_SDPA=1 switches back)."""
+    if os.environ.get("CN_SDPA", "0") == "1":
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=valid[:, None, None, :])
+    s = torch.matmul(q, k.transpose(-1, -2)) * 0.125
+    s = s.masked_fill(~valid[:, None, None, :], float("-inf"))
+    return torch.matmul(torch.softmax(s, dim=-1), v)
+
+
 class Policy(nn.Module):
     """Drop-in for rl.networks.model.Policy(obs_space.spaces, action_space, base_kwargs=args, base=...)."""
 
@@ -240,19 +251,51 @@ class Policy(nn.Module):
         rs = b.robot_linear(torch.cat([inputs['temporal_edges'].reshape(T * N, 2),
                                        inputs['robot_node'].reshape(T * N, 7)], -1).float())
         sa = b.spatial_attn
-        e = sa.embedding_layer(sp)
         mha = sa.multihead_attn
         wq, wk, wv = mha.in_proj_weight.chunk(3, 0)
         bq, bk, bv = mha.in_proj_bias.chunk(3, 0)
+        B = T * N
+
         def heads(x):
-            return x.reshape(T * N, H, 8, 64).transpose(1, 2)
-        q = heads(F.linear(sa.q_linear(e), wq, bq))
-        k = heads(F.linear(sa.k_linear(e), wk, bk))
-        v = heads(F.linear(sa.v_linear(e), wv, bv))
+            return x.reshape(B, H, 8, 64).transpose(1, 2)
         amask = valid[:, None, None, :]
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=amask)
-        o = mha.out_proj(o.transpose(1, 2).reshape(T * N, H, 512))
-        hs = b.spatial_linear(o)
+        if getattr(self, "pack_valid_rows", True):
+            # Same compaction as the rollout kernels: rows j >= detected_human_num are keys masked by
+            # key_padding_mask and queries whose outputs get weight exactly 0 in the robot-human soft-max
+            # (masked_fill(-1e9)), so they contribute neither to the outputs nor to any gradient.  The per-row
+            # layers (98 % of the FLOPs) run on the valid rows only; the tiny H x H attention runs padded.
+            sp_p = sp[valid]                                             # [Mc, W]
+            e = sa.embedding_layer(sp_p)
+
+            def pad(x):
+                out = x.new_zeros(B, H, x.shape[-1])
+                out[valid] = x
+                return out
+            # The same exact folds as the rollout engine, written so that autograd sees them: in_proj o q/k/v_linear
+            # is ONE 512 -> 1536 projection whose weight is the (differentiable) product of the two parameter
+            # matrices, and out_proj o spatial_linear one 512 -> 256 projection: the per-row GEMMs of forward AND
+            # backward shrink 2x, the parameter gradients flow back through the small 512^3 products.
+            wl = torch.cat([sa.q_linear.weight, sa.k_linear.weight, sa.v_linear.weight], 0).reshape(3, 512, 512)
+            bl = torch.stack([sa.q_linear.bias, sa.k_linear.bias, sa.v_linear.bias], 0)
+            win = mha.in_proj_weight.reshape(3, 512, 512)
+            w_qkv = torch.bmm(win, wl).reshape(1536, 512)
+            b_qkv = (torch.bmm(win, bl.unsqueeze(-1)).squeeze(-1) + mha.in_proj_bias.reshape(3, 512)).reshape(1536)
+            qkv = F.linear(e, w_qkv, b_qkv)
+            q, k, v = [heads(pad(t)) for t in qkv.chunk(3, -1)]
+            o = _hh_attention(q, k, v, valid)
+            o = o.transpose(1, 2).reshape(B, H, 512)[valid]
+            sl = b.spatial_linear[0]
+            w_os = sl.weight @ mha.out_proj.weight
+            b_os = sl.weight @ mha.out_proj.bias + sl.bias
+            hs = pad(torch.relu(F.linear(o, w_os, b_os)))
+        else:
+            e = sa.embedding_layer(sp)
+            q = heads(F.linear(sa.q_linear(e), wq, bq))
+            k = heads(F.linear(sa.k_linear(e), wk, bk))
+            v = heads(F.linear(sa.v_linear(e), wv, bv))
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=amask)
+            o = mha.out_proj(o.transpose(1, 2).reshape(B, H, 512))
+            hs = b.spatial_linear(o)
         te = b.attn.temporal_edge_layer[0](rs)
         se = b.attn.spatial_edge_layer[0](hs)
         att = (te[:, None, :] * se).sum(-1) * (H / 8.0)

@@ -45,7 +45,11 @@ def allreduce_gradients(params):
 
 class PPO(object):
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
-                 lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True):
+                 lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True, matmul_precision=None):
+        """Same constructor as rl/ppo/ppo.py:8-34.  matmul_precision (extension): None keeps PyTorch's setting
+        (fp32 matmuls like the reference); 'tf32' runs the update's matmuls on TF32 tensor cores
+        (torch.set_float32_matmul_precision('high') for the duration of update())."""
+        self.matmul_precision = matmul_precision
         self.actor_critic = actor_critic
         self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
         self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
@@ -53,6 +57,16 @@ class PPO(object):
         self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, eps=eps)
 
     def update(self, rollouts):
+        if self.matmul_precision == 'tf32':
+            prev = torch.get_float32_matmul_precision()
+            torch.set_float32_matmul_precision('high')
+            try:
+                return self._update(rollouts)
+            finally:
+                torch.set_float32_matmul_precision(prev)
+        return self._update(rollouts)
+
+    def _update(self, rollouts):
         advantages = rollouts.returns[:-1] - rollouts.value_preds[:-1]
         advantages = global_advantage_normalize(advantages)
         v_sum = a_sum = e_sum = 0.0
