@@ -17,7 +17,8 @@ Quirks of the reference that are reproduced on purpose (they shape the numbers i
 import numpy as np
 import torch
 
-from .vec_env import CudaCrowdVecEnv, Danger, ReachGoal, Collision, Timeout, config_dict_from_reference
+from .vec_env import (CudaCrowdVecEnv, CudaPretextVecEnv, Danger, ReachGoal, Collision, Timeout,
+                      config_dict_from_reference)
 
 INFO_TIMEOUT, INFO_COLLISION, INFO_REACHGOAL, INFO_DANGER = 1, 2, 3, 4
 
@@ -103,9 +104,11 @@ def evaluate(actor_critic, eval_envs, num_processes, device, test_size, logging,
     return out
 
 
-def evaluate_batched(actor_critic, config, env_name, seed, test_size, device, logging=None, cfg_dict=None):
+def evaluate_batched(actor_critic, config, env_name, seed, test_size, device, logging=None, cfg_dict=None, gst_params=None):
     """The same test cases as `evaluate`, as test_size parallel environments on one GPU.
-    config: reference Config object (or pass cfg_dict = a flat cn_config dict)."""
+    config: reference Config object (or pass cfg_dict = a flat cn_config dict).  gst_params: predictor parameters
+    for CrowdSimPredRealGST-v0 + VecPretextNormalize (config 3); the wrapper's buffers start empty for every test
+    case exactly like the sequential protocol's explicit reset()."""
     dev = torch.device(device)
     N = test_size
     if cfg_dict is None:
@@ -113,10 +116,11 @@ def evaluate_batched(actor_critic, config, env_name, seed, test_size, device, lo
                                               device_index=dev.index or 0, phase="test")
     d = dict(cfg_dict)
     d.update(num_envs=N, nenv_total=1, rank_offset=0, seed=seed, phase=2)
-    env = CudaCrowdVecEnv(device=dev, cfg=d)
+    env = CudaPretextVecEnv(gst_params, device=dev, cfg=d) if gst_params is not None else CudaCrowdVecEnv(device=dev, cfg=d)
+    base = env.env if gst_params is not None else env
     size = int(d["test_size"])
-    env.set_state("seed_off", np.zeros(N, np.int32))
-    env.set_state("case_counter", ((2 * np.arange(N)) % size).astype(np.uint32))
+    base.set_state("seed_off", np.zeros(N, np.int32))
+    base.set_state("case_counter", ((2 * np.arange(N)) % size).astype(np.uint32))
     time_limit, dt = float(d["time_limit"]), float(d["time_step"])
     hxs = {'human_node_rnn': torch.zeros(N, 1, 128, device=dev)}
     masks = torch.zeros(N, 1, device=dev)

@@ -51,3 +51,43 @@ def test_single_env_defaults_to_test_phase_and_val_is_rejected():
     from crowdnav_prediction_attngraph_b200.vec_env import CudaCrowdVecEnv
     with pytest.raises(RuntimeError):
         CudaCrowdVecEnv(device="cuda:0", cfg=_capi.default_config_dict(num_envs=2, phase=1))
+
+
+SHIPPED_COLLISIONS = [0, 1, 12, 17, 31, 34, 35, 42, 48, 57, 60, 68, 71, 89, 98, 99, 113, 117, 119, 121, 131, 142, 153, 158,
+                      161, 164, 170, 214, 239, 246, 248, 250, 251, 262, 267, 281, 284, 285, 292, 298, 307, 310, 318, 321,
+                      339, 348, 349, 363, 367, 369, 371, 381, 392, 403, 408, 411, 414, 420, 464, 489, 496, 498]
+
+
+def test_shipped_checkpoint_reproduces_shipped_test_log():
+    """End-to-end results parity (config 3, phase 'test'): the reference's 500-case protocol with its shipped policy
+    checkpoint and GST predictor on this engine vs trained_models/GST_predictor_rand/test/test_41665.pt.log
+    (success 0.88, collision 0.12, timeout 0.00, nav time 14.14, path length 20.08, intrusion ratio 8.35 %, min
+    distance 0.41).  Needs the 10 MB checkpoint at local_ckpt/41665.pt (a reference artefact, not committed)."""
+    import os
+    from crowdnav_prediction_attngraph_b200 import _capi
+    from crowdnav_prediction_attngraph_b200.vec_env import Box
+    from crowdnav_prediction_attngraph_b200.policy import Policy
+    from crowdnav_prediction_attngraph_b200.evaluation import evaluate_batched
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ckpt = os.path.join(repo, "local_ckpt", "41665.pt")
+    if not os.path.exists(ckpt):
+        pytest.skip("shipped checkpoint not present (copy trained_models/GST_predictor_rand/checkpoints/41665.pt to local_ckpt/)")
+    dev = torch.device("cuda:0")
+
+    class Args(object):
+        num_processes, seq_length, num_mini_batch = 500, 30, 2
+    spaces = {'robot_node': Box((1, 7)), 'temporal_edges': Box((1, 2)), 'spatial_edges': Box((20, 12)),
+              'detected_human_num': Box((1,)), 'visible_masks': Box((20,), np.bool_)}
+    pol = Policy(spaces, Box((2,)), base_kwargs=Args(), base='selfAttn_merge_srnn').to(dev)
+    pol.load_state_dict(torch.load(ckpt, map_location="cpu", weights_only=True))
+    gst = dict(np.load(os.path.join(repo, "tests", "golden", "gst_params.npz")))
+    d = _capi.default_config_dict(num_envs=500, nenv_total=1, seed=425, human_num=20, phase=2, test_size=500,
+                                  randomize_attributes=1, random_goal_changing=1, goal_change_chance=0.5)
+    out = evaluate_batched(pol, None, "CrowdSimPredRealGST-v0", 425, 500, dev, cfg_dict=d, gst_params=gst)
+    assert round(out["success_rate"], 2) == 0.88 and round(out["collision_rate"], 2) == 0.12 and out["timeout_rate"] == 0.0
+    assert abs(out["avg_nav_time"] - 14.14) < 0.2 and abs(out["path_length"] - 20.08) < 0.15
+    assert abs(out["intrusion_ratio"] - 8.35) < 0.3 and abs(out["min_intrusion_dist"] - 0.41) < 0.02
+    same = len(set(out["collision_cases"]) & set(SHIPPED_COLLISIONS))
+    assert same >= 56, "only %d of the 62 collision episodes of the shipped log collide here" % same
+    # the case counter wraps at test_size: episode k + 250 repeats episode k
+    assert all(((c + 250) % 500) in out["collision_cases"] for c in out["collision_cases"])
