@@ -13,10 +13,12 @@
 // relative positions written into the 2(P+1)-wide spatial_edges rows, rows sorted by distance to the robot.
 // All activations live in shared memory; weights are stored transposed ([K][N]) so the register-tiled dense
 // layers read them coalesced (they stay L2 resident: 269 KB).  fp32 CUDA cores: this first version favours
-// parity (<= 2e-5 on the predicted positions); moving the dense layers to the tcgen05 path is listed as next.
+// parity (<= 2e-5 on the predicted positions).  The default path since is cn_gst_tc.cuh (batched tcgen05 GEMMs over
+// all environments + row-wise kernels); this fused kernel stays as CN_GST_MODE=fused (one launch, no workspace).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -344,7 +346,16 @@ const int kNumParams = 20;
 
 }  // namespace
 
+// tensor-core implementation (cn_gst_tc.cuh, compiled inside cn_policy.cu)
+void* cn_gst_tc_create(int N, int H, int P, float thr, float pen, int device, const float* const* host, const int* rows,
+                       const int* cols);
+void cn_gst_tc_destroy(void* handle);
+int64_t cn_gst_tc_launches(void* handle);
+int cn_gst_tc_step(void* handle, float* ring_pos, uint8_t* ring_mask, int newest, const float* robot, const float* sp2,
+                   const uint8_t* vis, float* reward, float* penalty, float* out_sp, cudaStream_t st);
+
 struct cn_gst {
+  void* tc;           // non-null: dense layers on the tcgen05 GEMM (CN_GST_MODE=tc)
   int N, H, P, device;
   float thr, collision_penalty;
   std::map<std::string, std::vector<float>> host;
@@ -380,7 +391,7 @@ int cn_gst_create(int num_envs, int human_num, int predict_steps, double robot_r
   cn_gst* g = new cn_gst();
   g->N = num_envs; g->H = human_num; g->P = predict_steps; g->device = device;
   g->thr = (float)(robot_radius + human_radius); g->collision_penalty = (float)collision_penalty;
-  g->newest = GST_T - 1; g->finalized = false; g->launches = 0; g->smem = smem;
+  g->newest = GST_T - 1; g->finalized = false; g->launches = 0; g->smem = smem; g->tc = nullptr;
   g->ring_pos = nullptr; g->ring_mask = nullptr;
   void* q = nullptr;
   err = cudaMalloc(&q, (size_t)GST_T * num_envs * human_num * 2 * sizeof(float));
@@ -400,6 +411,7 @@ int cn_gst_destroy(cn_gst* g) {
   if (!g) return 0;
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
+  if (g->tc) cn_gst_tc_destroy(g->tc);
   for (void* a : g->allocs) cudaFree(a);
   delete g;
   return 0;
@@ -440,6 +452,16 @@ int cn_gst_finalize(cn_gst* g) {
     g->allocs.push_back(q);
     g->dev[i] = (const float*)q;
   }
+  // default: dense layers as batched tcgen05 GEMMs over all environments (cn_gst_tc.cuh, 2.5x faster at N = 4096);
+  // CN_GST_MODE=fused selects the single fused CUDA-core kernel of this file (no workspace, one launch)
+  const char* mode = getenv("CN_GST_MODE");
+  if (!(mode && strcmp(mode, "fused") == 0)) {
+    if (g->tc) { cn_gst_tc_destroy(g->tc); g->tc = nullptr; }
+    const float* hp[kNumParams];
+    for (int i = 0; i < kNumParams; ++i) hp[i] = g->host[kParamNames[i]].data();
+    g->tc = cn_gst_tc_create(g->N, g->H, g->P, g->thr, g->collision_penalty, g->device, hp, kParamRows, kParamCols);
+    if (!g->tc) return 1;                       // cn_last_error holds the reason
+  }
   g->finalized = true;
   return 0;
 }
@@ -468,6 +490,11 @@ int cn_gst_step(cn_gst* g, const float* d_robot_node, const float* d_spatial2, c
   if (!g->finalized) return cn_set_error("cn_gst_step: call cn_gst_finalize after setting the parameters");
   cudaSetDevice(g->device);
   g->newest = (g->newest + 1) % GST_T;
+  if (g->tc) {
+    g->launches += 1;
+    return cn_gst_tc_step(g->tc, g->ring_pos, g->ring_mask, g->newest, d_robot_node, d_spatial2, d_visible, d_reward, d_penalty,
+                          d_spatial_out, (cudaStream_t)stream);
+  }
   GstW w;
   w.We_t = g->dev[0]; w.be = g->dev[1]; w.ln0_g = g->dev[2]; w.ln0_b = g->dev[3]; w.Win_t = g->dev[4]; w.bin = g->dev[5];
   w.Wout_t = g->dev[6]; w.bout = g->dev[7]; w.ln1_g = g->dev[8]; w.ln1_b = g->dev[9]; w.W1_t = g->dev[10]; w.b1 = g->dev[11];
@@ -482,6 +509,6 @@ int cn_gst_step(cn_gst* g, const float* d_robot_node, const float* d_spatial2, c
   return 0;
 }
 
-int64_t cn_gst_launch_count(cn_gst* g) { return g ? g->launches : 0; }
+int64_t cn_gst_launch_count(cn_gst* g) { return !g ? 0 : (g->tc ? cn_gst_tc_launches(g->tc) : g->launches); }
 
 }  // extern "C"

@@ -680,3 +680,5 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
 }
 
 }  // extern "C"
+
+#include "cn_gst_tc.cuh"

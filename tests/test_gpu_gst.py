@@ -52,6 +52,13 @@ def _unsort(sp2, rows):
     return out
 
 
+@pytest.fixture(params=["tc", "fused"], autouse=True)
+def gst_mode(request, monkeypatch):
+    """both implementations: batched tcgen05 GEMMs (default) and the single fused CUDA-core kernel"""
+    monkeypatch.setenv("CN_GST_MODE", request.param)
+    return request.param
+
+
 def test_gst_kernel_matches_reference_predictor():
     g = np.load(os.path.join(GOLD, "gst_io.npz"))
     N, H = g["in_traj"].shape[:2]
