@@ -384,6 +384,7 @@ int cn_gst_create(int num_envs, int human_num, int predict_steps, double robot_r
     return cn_set_error("cn_gst_create: no CUDA device (%s); this engine has no CPU fallback",
                         err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
   if (device < 0 || device >= ndev) return cn_set_error("cn_gst_create: bad device %d", device);
+  if (human_num > 32) return cn_set_error("cn_gst_create: human_num %d > 32 is not supported by the predictor kernels", human_num);
   const size_t smem = gst_smem_floats(human_num) * sizeof(float);
   if (smem > 227 * 1024)
     return cn_set_error("cn_gst_create: human_num %d needs %zu bytes of shared memory (max 232448)", human_num, smem);
