@@ -89,6 +89,9 @@ struct CnState {
   // per-step event flags written by the step kernel, consumed by the event kernel:
   // 0 = nothing, 1 = goal dynamics (respawn / goal change) pending, 2 = episode finished (reset)
   uint8_t *evt;                      // [N]
+  // load balancing of the step kernel: slot -> environment permutation (identity until the first balance pass)
+  int *perm;                         // [grid * epb] (entries >= N: empty slot)
+  int *lp_cost;                      // [N] humans whose last solve needed linearProgram3 (cost estimate)
   uint8_t *spawn_overflow;           // [N] set when a rejection-sampling loop hit CN_MAX_SPAWN_TRIES
   // overflow ORCA lines (k >= line_cap) of every step-kernel thread: [grid * block][ovf_stride] float4
   void *line_ovf;

@@ -70,6 +70,7 @@ struct CnEnvSh {
   int done, info, reset_flag;
   int nvis;
   int goal_flag;         // some human is within its radius of its goal (respawn pending)
+  int lp3_cost;          // humans of this environment whose solve fell through to linearProgram3 (balancing)
   int lean;              // step kernel: gx / gy / rad / vpref point straight into HBM (read-only there)
 };
 
@@ -106,7 +107,7 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   if (h == 0) {
     s.rpx = g.rpx[e]; s.rpy = g.rpy[e]; s.rgx = g.rgx[e]; s.rgy = g.rgy[e];
     s.rvx = g.rvx[e]; s.rvy = g.rvy[e];
-    s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
+    s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0; s.lp3_cost = 0;
     if (action) {
       float ax = action[2 * e], ay = action[2 * e + 1];
       const float nrm = sqrtf(ax * ax + ay * ay);          // np.linalg.norm(float32[2])

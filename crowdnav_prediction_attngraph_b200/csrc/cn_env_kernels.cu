@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   const int H = p.H;
   const int le = threadIdx.x / H;
   const int h = threadIdx.x - le * H;
-  const int e = blockIdx.x * epb + le;
+  // slot -> environment through the balancing permutation (cn_env_balance_kernel): CTAs get environments of
+  // similar total linear-programming cost; results do not depend on the assignment
+  const int e = (le < epb) ? g.perm[blockIdx.x * epb + le] : p.N;
   const bool active = (le < epb) && (e < p.N);
   const EnvSmemLayout L = env_layout(H, true);
   CnEnvSh* s = nullptr;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   const CnCoop co = {lane, 32};
 
   if (mode == 1) {
-    if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; }
+    if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; s->lp3_cost = 0; }
   } else if (active) {
     cn_phase_load(p, g, *s, e, h, action);
   }
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   if (mode != 1) {
     CnF2 result; int nl, fail;
     orca_solve(true, result, nl, fail);                               // get_human_actions (crowd_sim.py:680-703)
+    if (active && fail >= 0) atomicAdd(&s->lp3_cost, 1);              // cost estimate for the next step's balancing
     if (p.test_phase) {
       // phase 'test': ground-truth look-ahead (crowd_sim_pred.py:136-138 -> crowd_sim_var_num.py:180-206):
       // lookahead_steps nested solves on a scratch copy of the joint state kept in the same shared arrays
@@ -208,7 +211,10 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
     cn_phase_obs_c(p, *s, e, h, ob);
     cn_phase_store(p, g, *s, e, h);
   }
-  if (active && h == 0) g.evt[e] = (uint8_t)cn_event_flag(p, g, *s, e);
+  if (active && h == 0) {
+    g.evt[e] = (uint8_t)cn_event_flag(p, g, *s, e);
+    g.lp_cost[e] = s->lp3_cost;
+  }
 }
 
 // Event kernel: ONE WARP per environment, for everything that consumes the legacy numpy MT19937
@@ -247,6 +253,34 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
     __syncwarp();
     for (int h = lane; h < H; h += 32) cn_phase_store(p, g, *s, e, h);
     for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
+  }
+}
+
+// Load balancing for the step kernel (side stream, off the critical path).  The kernel's duration is set by its
+// slowest SM (ncu: SMs busy 78 % on average); the work of an environment is dominated by its linearProgram3
+// fall-throughs, which change slowly from step to step.  Cost estimate = number of humans whose last solve needed
+// linearProgram3 (counted by the step kernel); environments are bucketed by cost (counting sort, one CTA) and dealt to the CTAs in
+// serpentine order, heaviest first, so every CTA gets a similar sum.
+__global__ void __launch_bounds__(1024) cn_env_balance_kernel(CnParams p, CnState g, int grid, int epb) {
+  __shared__ int bucket[130];                 // cost 0..H (H <= 128) -> count, then start offset
+  __shared__ int cursor[130];
+  const int H = p.H, N = p.N, slots = grid * epb;
+  for (int i = threadIdx.x; i <= H; i += blockDim.x) bucket[i] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < N; e += blockDim.x) atomicAdd(&bucket[min(g.lp_cost[e], H)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {                       // descending cost: offsets of the buckets H, H-1, ..., 0
+    int off = 0;
+    for (int c = H; c >= 0; --c) { cursor[c] = off; off += bucket[c]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < slots; i += blockDim.x) g.perm[i] = N;          // empty
+  __syncthreads();
+  for (int e = threadIdx.x; e < N; e += blockDim.x) {
+    const int k = atomicAdd(&cursor[min(g.lp_cost[e], H)], 1);     // rank in the descending order (ties arbitrary)
+    const int round = k / grid, pos = k - round * grid;
+    const int cta = (round & 1) ? grid - 1 - pos : pos;                         // serpentine deal
+    g.perm[cta * epb + round] = e;
   }
 }
 
@@ -294,6 +328,7 @@ struct cn_env {
   cudaEvent_t ev_step, ev_side;
   bool side_pending;      // an event kernel is in flight: the next launch on the caller's stream waits for it
   bool use_side;
+  bool balance;           // re-deal environments to CTAs by their linearProgram3 load after every step (side stream)
   bool prep_dirty;        // a state upload may have invalidated the prepared episodes
   // staging for the host-buffer entry point
   float* d_action;
@@ -382,6 +417,10 @@ int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const 
   if (err != cudaSuccess) return cn_set_error("fork to side stream: %s", cudaGetErrorString(err));
   rc = event_kernel(env, 0, env->side);
   if (rc) return rc;
+  if (env->balance && mode == 0) {
+    cn_env_balance_kernel<<<1, 1024, 0, env->side>>>(env->p, env->g, grid, env->epb);
+    env->launches += 1;
+  }
   err = cudaEventRecord(env->ev_side, env->side);
   if (err != cudaSuccess) return cn_set_error("cudaEventRecord(side): %s", cudaGetErrorString(err));
   env->side_pending = true;
@@ -469,6 +508,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
+  A(lp_cost, N);
 #undef A
   if (!rc) {
     // nd_global starts at the configured value (config.orca.neighbor_dist)
@@ -546,6 +586,19 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     int rc2 = dev_alloc(env, nullptr, &ovf, (size_t)grid * env->threads * env->g.ovf_stride);
     if (rc2) { cn_env_destroy(env); return rc2; }
     env->g.line_ovf = ovf;
+  }
+  {
+    // slot -> environment permutation of the step kernel, identity to start with
+    int* perm = nullptr;
+    int rc3 = dev_alloc(env, nullptr, &perm, (size_t)grid * env->epb);
+    if (rc3) { cn_env_destroy(env); return rc3; }
+    std::vector<int> id((size_t)grid * env->epb);
+    for (size_t i = 0; i < id.size(); ++i) id[i] = (int)i;      // entries >= N are empty slots
+    err = cudaMemcpy(perm, id.data(), id.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("init perm: %s", cudaGetErrorString(err)); }
+    env->g.perm = perm;
+    const char* nb = getenv("CN_NO_BALANCE");
+    env->balance = !(nb && nb[0] == '1') && env->use_side;
   }
   // event kernel: per-warp working set + MT19937 state
   env->reset_warp_bytes = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t));

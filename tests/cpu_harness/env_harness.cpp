@@ -157,7 +157,7 @@ void* harness_create(const cn_config* cfg) {
   A(mt, N * 624); A(mt_pos, N);
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
-  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N); A(lp_cost, N);
 #undef A
   for (size_t e = 0; e < N; ++e) { g.nd_global[e] = cfg->orca_neighbor_dist; g.seed_off[e] = (int32_t)e; }
   return hn;
