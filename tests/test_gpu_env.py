@@ -65,6 +65,30 @@ def test_cuda_env_matches_oracle_lockstep():
                 assert abs(i["episode"]["r"] - oi["episode"]["r"]) < 1e-4
 
 
+def test_cuda_env_test_phase_h50_randomized_matches_oracle_lockstep():
+    """phase 'test' at H = 50 with randomised humans and goal changes: the look-ahead runs through the 64-human kernel
+    variant with the two-tier line store (no golden covers that combination)."""
+    from oracle.crowd_env import EnvConfig, OracleVecEnv
+    import rvo2
+    rvo2.ONLY_AGENT0 = True
+    N, H, T = 3, 50, 24
+    env = _engine(num_envs=N, human_num=H, seed=77, phase=2, randomize_attributes=1, random_goal_changing=1)
+    orc = OracleVecEnv(EnvConfig(human_num=H, randomize_attributes=True, random_goal_changing=True), N, seed=77, phase="test")
+    obs, oobs = _np_obs(env.reset()), orc.reset()
+    rng = np.random.RandomState(9)
+    for t in range(T):
+        for k in oobs:
+            np.testing.assert_allclose(obs[k], oobs[k], atol=1e-5, err_msg="%s t=%d" % (k, t))
+        a = rng.uniform(-1.0, 1.0, (N, 2)).astype(np.float32)
+        o, rew, done, infos = env.step(torch.from_numpy(a).cuda())
+        obs = _np_obs(o)
+        oobs, orew, odone, oinfos = orc.step(a)
+        assert np.array_equal(done, odone), t
+        assert [int(i["info"]) for i in oinfos] == [int(c) for c in env._host["info"].numpy()], t
+        np.testing.assert_allclose(rew.numpy()[:, 0], orew, atol=1e-5)
+        np.testing.assert_allclose(env._host["info_aux"].numpy(), [i["min_danger"] for i in oinfos], atol=1e-6)
+
+
 def test_full_size_properties():
     N, H, T = 4096, 20, 40
     a_env = _engine(num_envs=N, human_num=H, seed=425)
