@@ -34,7 +34,6 @@ struct cn_policy {
   cn_policy_config cfg;
   int N, H, Win, M;
   int64_t launches;
-  int attn_hpc;        // heads per CTA of the HH attention kernel
   int num_sms;
   bool pdl;           // programmatic dependent launch along the kernel chain (CN_PDL=0 disables)
   bool launch_error;  // a GEMM output map could not be built (cn_last_error has the reason)
@@ -353,7 +352,6 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
   }
   if (rc) { cn_policy_destroy(p); return rc; }
   p->ws_allocs = p->allocs.size();
-  p->attn_hpc = 8;
   *out = p;
   return 0;
 }
