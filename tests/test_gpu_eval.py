@@ -91,3 +91,33 @@ def test_shipped_checkpoint_reproduces_shipped_test_log():
     assert same >= 56, "only %d of the 62 collision episodes of the shipped log collide here" % same
     # the case counter wraps at test_size: episode k + 250 repeats episode k
     assert all(((c + 250) % 500) in out["collision_cases"] for c in out["collision_cases"])
+
+
+def test_shipped_non_rand_checkpoint_reproduces_its_test_log_exactly():
+    """trained_models/GST_predictor_non_rand (fixed human attributes, seed 125, predictor ..._seed_1000): every episode
+    outcome listed in test/test_41200.pt.log is reproduced.  Needs local_ckpt/41200.pt and local_ckpt/gst_params_nonrand.npz
+    (reference artefacts, not committed; tools/eval_shipped.py documents how they are made)."""
+    import os
+    from crowdnav_prediction_attngraph_b200 import _capi
+    from crowdnav_prediction_attngraph_b200.vec_env import Box
+    from crowdnav_prediction_attngraph_b200.policy import Policy
+    from crowdnav_prediction_attngraph_b200.evaluation import evaluate_batched
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ckpt, gstp = os.path.join(repo, "local_ckpt", "41200.pt"), os.path.join(repo, "local_ckpt", "gst_params_nonrand.npz")
+    if not (os.path.exists(ckpt) and os.path.exists(gstp)):
+        pytest.skip("shipped non_rand checkpoint / predictor parameters not present under local_ckpt/")
+    dev = torch.device("cuda:0")
+
+    class Args(object):
+        num_processes, seq_length, num_mini_batch = 500, 30, 2
+    spaces = {'robot_node': Box((1, 7)), 'temporal_edges': Box((1, 2)), 'spatial_edges': Box((20, 12)),
+              'detected_human_num': Box((1,)), 'visible_masks': Box((20,), np.bool_)}
+    pol = Policy(spaces, Box((2,)), base_kwargs=Args(), base='selfAttn_merge_srnn').to(dev)
+    pol.load_state_dict(torch.load(ckpt, map_location="cpu", weights_only=True))
+    d = _capi.default_config_dict(num_envs=500, nenv_total=1, seed=125, human_num=20, phase=2, test_size=500)
+    out = evaluate_batched(pol, None, "CrowdSimPredRealGST-v0", 125, 500, dev, cfg_dict=d, gst_params=dict(np.load(gstp)))
+    assert out["collision_cases"] == [5, 71, 74, 95, 98, 103, 111, 159, 166, 171, 182, 186, 191, 205, 209, 227, 233, 235, 255,
+                                      321, 324, 345, 348, 353, 361, 409, 416, 421, 432, 436, 441, 455, 459, 477, 483, 485]
+    assert out["timeout_cases"] == [49, 299]
+    assert round(out["avg_nav_time"], 2) == 15.42 and round(out["path_length"], 2) == 20.96
+    assert round(out["intrusion_ratio"], 2) == 4.23 and round(out["min_intrusion_dist"], 2) == 0.44
