@@ -43,6 +43,7 @@ class EnvConfig(object):
 
     def __init__(self, **kw):
         self.human_num = 20
+        self.human_num_range = 0             # sim.human_num_range: humans join / leave every 5 s
         self.predict_steps = 5
         self.predict_method = "const_vel"      # 'const_vel' | 'none' (CrowdSimVarNum-v0 obs)
         self.time_limit = 50.0
@@ -79,11 +80,11 @@ class EnvConfig(object):
     @classmethod
     def from_reference(cls, config):
         """Snapshot a reference `crowd_nav.configs.config.Config` object."""
-        assert config.sim.human_num_range == 0 and config.action_space.kinematics == "holonomic"
+        assert config.action_space.kinematics == "holonomic"
         assert config.humans.policy == "orca" and not config.robot.visible
         pm = config.sim.predict_method
         return cls(
-            human_num=config.sim.human_num, predict_steps=config.sim.predict_steps,
+            human_num=config.sim.human_num, human_num_range=config.sim.human_num_range, predict_steps=config.sim.predict_steps,
             predict_method=pm, time_limit=config.env.time_limit, time_step=config.env.time_step,
             pred_timestep=config.data.pred_timestep,
             randomize_attributes=config.env.randomize_attributes,
@@ -118,7 +119,11 @@ class CrowdEnvOracle(object):
         if phase not in ("train", "val", "test"):
             raise ValueError("phase must be 'train', 'val' or 'test'")
         self.cfg = cfg
-        self.H = cfg.human_num
+        self.H = cfg.human_num               # CURRENT number of humans (changes when human_num_range > 0)
+        self.Hmax = cfg.human_num + cfg.human_num_range
+        self.Hmin = cfg.human_num - cfg.human_num_range
+        assert cfg.human_num > cfg.human_num_range
+        self.observed_human_ids = []
         self.P = cfg.predict_steps
         self.this_seed = this_seed
         self.nenv = nenv
@@ -191,6 +196,9 @@ class CrowdEnvOracle(object):
         self.rvx, self.rvy = 0, 0
         self.rtheta = np.pi / 2
         # humans: randint(lo, hi) with hi - lo == 1 consumes no draw (human_num_range == 0)
+        self.observed_human_ids = []
+        if c.human_num_range > 0:                # crowd_sim_var_num.py:103-104
+            self.H = int(self.rng.randint(low=c.human_num - c.human_num_range, high=c.human_num + c.human_num_range + 1))
         self.hpx, self.hpy, self.hvx, self.hvy = [], [], [], []
         self.hgx, self.hgy, self.hrad, self.hvpref = [], [], [], []
         self.sims = []
@@ -259,27 +267,28 @@ class CrowdEnvOracle(object):
             traj[:, inv, :2] = 15
             traj[:, inv, 2:] = 0
             self.human_future_traj = traj
-            spatial = np.ones((H, 2 * (P + 1))) * np.inf
+            spatial = np.ones((self.Hmax, 2 * (P + 1))) * np.inf        # storage for max_human_num humans
             pred_pos = np.transpose(traj[:, :, :2], (1, 0, 2)) - np.array([self.rpx, self.rpy])
-            spatial[np.array(vis, dtype=bool)] = pred_pos.reshape((H, -1))[np.array(vis, dtype=bool)]
+            spatial[:H][np.array(vis, dtype=bool)] = pred_pos.reshape((H, -1))[np.array(vis, dtype=bool)]
             if c.sort_humans:
                 spatial = np.array(sorted(spatial, key=lambda x: np.linalg.norm(x[:2])))
             spatial[np.isinf(spatial)] = 15
             vmask = None
         else:
             # CrowdSimVarNum.generate_ob (crowd_sim_var_num.py:233-279)
-            spatial = np.ones((H, 2)) * np.inf
+            spatial = np.ones((self.Hmax, 2)) * np.inf
             for i in range(H):
                 if vis[i]:
                     spatial[i, :] = [self.last_human_states[i, 0] - self.rpx, self.last_human_states[i, 1] - self.rpy]
-            vmask = np.zeros(H, dtype=bool)
+            vmask = np.zeros(self.Hmax, dtype=bool)
             if c.sort_humans:
                 spatial = np.array(sorted(spatial, key=lambda x: np.linalg.norm(x)))
                 if num_vis > 0:
                     vmask[:num_vis] = True
             else:
-                vmask[:] = vis
+                vmask[:H] = vis
             spatial[np.isinf(spatial)] = 15
+            self.observed_human_ids = np.where(vis)[0]                 # only CrowdSimVarNum.generate_ob updates it
         ob = {
             "robot_node": np.asarray(robot_node, dtype=np.float32).reshape(1, 7),
             "temporal_edges": np.asarray(temporal, dtype=np.float32).reshape(1, 2),
@@ -314,6 +323,8 @@ class CrowdEnvOracle(object):
                 else:
                     others.append((7, 7, 0, 0, 0.3))   # dummy_human (crowd_sim.py:130-133)
             sim = self.sims[i]
+            if sim is not None and sim.getNumAgents() != len(others) + 1:     # orca.py:80-82: humans joined / left
+                sim = self.sims[i] = None
             if sim is None:
                 params = (self.nd_global, len(others), c.orca_time_horizon, c.orca_time_horizon)
                 sim = rvo2.PyRVOSimulator(c.time_step, *params, self.hrad[i], 1)
@@ -435,6 +446,9 @@ class CrowdEnvOracle(object):
             self.hvx[i], self.hvy[i] = vx, vy
         self.global_time += c.time_step
         self.step_counter += 1
+        if c.human_num_range > 0 and self.global_time % 5 == 0:
+            self._add_or_remove_humans()
+            H = self.H
         ob = self._generate_ob(reset=False)
         if c.random_goal_changing and self.global_time % 5 == 0:
             self._update_goals_randomly()
@@ -448,6 +462,42 @@ class CrowdEnvOracle(object):
                     self.sims[i] = None     # new Human object => new ORCA policy => new rvo2 sim
         self.last_human_actions = human_actions
         return ob, reward, done, {"info": info, "min_danger": min_danger}
+
+    def _add_or_remove_humans(self):
+        """crowd_sim_var_num.py:404-437 (CrowdSimVarNum-v0) / crowd_sim_pred.py:165-194 (CrowdSimPred-v0): every 5 s
+        at most human_num_range humans leave (the LAST ones, never below a currently observed id) or join."""
+        c = self.cfg
+        if self.rng.rand() < 0.5:
+            seen = self.observed_human_ids          # CrowdSimPred never updates it after reset: always empty there
+            if c.predict_method == "const_vel":
+                max_remove = self.H - 1 if len(seen) == 0 else (self.H - 1) - max(seen)
+                remove_num = int(self.rng.randint(low=0, high=min(c.human_num_range, max_remove) + 1))
+            else:
+                if len(seen) == 0:
+                    max_remove = self.H - self.Hmin
+                else:
+                    max_remove = min(self.H - self.Hmin, (self.H - 1) - max(seen))
+                remove_num = int(self.rng.randint(low=0, high=max_remove + 1))
+            for _ in range(remove_num):
+                for lst in (self.hpx, self.hpy, self.hvx, self.hvy, self.hgx, self.hgy, self.hrad, self.hvpref, self.sims):
+                    lst.pop()
+            self.H -= remove_num
+            self.last_human_states = self.last_human_states[:self.H]
+        else:
+            add_num = int(self.rng.randint(low=0, high=c.human_num_range + 1))
+            true_add = 0
+            for i in range(self.H, self.H + add_num):
+                if i == self.Hmax:
+                    break
+                px, py, v_pref, radius = self._circle_crossing_human()
+                self.hpx.append(px); self.hpy.append(py); self.hvx.append(0); self.hvy.append(0)
+                self.hgx.append(-px); self.hgy.append(-py); self.hrad.append(radius); self.hvpref.append(v_pref)
+                self.sims.append(None)
+                true_add += 1
+            self.H += true_add
+            if true_add > 0:
+                self.last_human_states = np.concatenate((self.last_human_states, np.array([[15, 15, 0, 0, 0.3]] * true_add)), axis=0)
+        assert 1 <= self.H <= self.Hmax
 
     def _update_goals_randomly(self):
         """crowd_sim.py:415-450."""

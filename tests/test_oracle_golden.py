@@ -76,3 +76,48 @@ def test_oracle_matches_reference_golden(name):
                     np.testing.assert_allclose(ob[key], g["ob_" + key][t + 1, k], rtol=0, atol=1e-6,
                                                err_msg="%s t=%d" % (key, t))
             check_state(env.get_state(), g, t + 1, k)
+
+
+RANGE_CASES = ["env_varnum_h5_range2", "env_pred_h6_range3"]
+
+
+@pytest.mark.parametrize("name", RANGE_CASES)
+def test_oracle_variable_human_count_matches_reference_golden(name):
+    """sim.human_num_range > 0 (oracle only so far: the CUDA engine still rejects it): humans join and
+    leave every 5 s, per-human ORCA simulators are rebuilt when the agent count changes, observations are padded to
+    max_human_num.  Fixture arrays are NaN-padded; st_count is the live human count."""
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fixture %s missing" % name)
+    g = np.load(path, allow_pickle=False)
+    case = ast.literal_eval(str(g["meta"][0]))
+    cfg = EnvConfig(human_num=case["human_num"], human_num_range=case["human_num_range"],
+                    predict_method=case["predict_method"], randomize_attributes=case["randomize"],
+                    random_goal_changing=case["goal_changing"])
+    T, N = g["actions"].shape[:2]
+    obs_keys = [k[3:] for k in g.files if k.startswith("ob_")]
+    counts = set()
+    for k in range(N):
+        env = CrowdEnvOracle(cfg, case["seed"] + k, case["nenv"], "train")
+        ob = env.reset()
+        for t in range(T + 1):
+            n = int(g["st_count"][t, k])
+            counts.add(n)
+            st = env.get_state()
+            assert len(st["hpx"]) == n, (name, k, t)
+            for key in ("hpx", "hpy", "hgx", "hgy", "hrad", "hvpref"):
+                np.testing.assert_allclose(st[key], g["st_" + key][t, k][:n], rtol=0, atol=1e-9, err_msg="%s t=%d" % (key, t))
+            np.testing.assert_allclose(st["belief"], g["st_belief"][t, k][:n], rtol=0, atol=1e-9)
+            assert np.array_equal(st["vis"], g["st_vis"][t, k][:n])
+            for key in obs_keys:
+                ref = g["ob_" + key][t, k]
+                if ref.dtype == bool:
+                    assert np.array_equal(ob[key], ref), (key, t)
+                else:
+                    np.testing.assert_allclose(ob[key], ref, rtol=0, atol=1e-6, err_msg="%s t=%d" % (key, t))
+            if t == T:
+                break
+            ob, rew, done, info = env.worker_step(g["actions"][t, k].copy())
+            assert bool(done) == bool(g["done"][t, k]) and info["info"] == g["info"][t, k], (name, k, t)
+            np.testing.assert_allclose(rew, g["reward"][t, k], rtol=0, atol=1e-9)
+    assert len(counts) >= 3, "the fixture should exercise several human counts: %r" % (counts,)

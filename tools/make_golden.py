@@ -39,6 +39,12 @@ CASES = {
                               randomize=False, goal_changing=False, nenv=3, steps=200, seed=425, phase="test"),
     "env_varnum_h5_test": dict(env_name="CrowdSimVarNum-v0", human_num=5, predict_method="none",
                                randomize=False, goal_changing=False, nenv=2, steps=160, seed=425, phase="test"),
+    # sim.human_num_range > 0: humans join / leave every 5 s; per-human arrays are padded to
+    # human_num + range with NaN, `st_count` holds the live count
+    "env_varnum_h5_range2": dict(env_name="CrowdSimVarNum-v0", human_num=5, predict_method="none", human_num_range=2,
+                                 randomize=False, goal_changing=False, nenv=3, steps=200, seed=425),
+    "env_pred_h6_range3": dict(env_name="CrowdSimPred-v0", human_num=6, predict_method="const_vel", human_num_range=3,
+                               randomize=True, goal_changing=True, nenv=2, steps=200, seed=9),
     "env_pred_h10_test_rand": dict(env_name="CrowdSimPred-v0", human_num=10, predict_method="const_vel",
                                    randomize=True, goal_changing=True, nenv=2, steps=200, seed=11, phase="test"),
 }
@@ -66,6 +72,7 @@ def build_reference_env(case, rank):
     from crowd_nav.configs.config import Config
     cfg = Config()
     cfg.sim.human_num = case["human_num"]
+    cfg.sim.human_num_range = case.get("human_num_range", 0)
     cfg.sim.predict_method = case["predict_method"]
     cfg.env.use_wrapper = False
     cfg.env.randomize_attributes = case["randomize"]
@@ -79,23 +86,34 @@ def build_reference_env(case, rank):
     return env, cfg
 
 
+def _pad(a, n, fill=np.nan):
+    a = np.asarray(a)
+    if a.shape[0] == n:
+        return a
+    out = np.full((n,) + a.shape[1:], fill, dtype=a.dtype if a.dtype != bool else bool)
+    out[:a.shape[0]] = a
+    return out
+
+
 def ref_state(env, cfg):
     H = env.human_num
-    f = lambda name: np.array([float(getattr(h, name)) for h in env.humans], dtype=np.float64)
+    Hmax = cfg.sim.human_num + cfg.sim.human_num_range
+    f = lambda name: _pad(np.array([float(getattr(h, name)) for h in env.humans], dtype=np.float64), Hmax)
     r = env.robot
     traj = getattr(env, "human_future_traj", None)
-    if cfg.sim.predict_method == "none":
+    if cfg.sim.predict_method == "none" or cfg.sim.human_num_range > 0:
         traj = None       # VarNum keeps no prediction (the test-phase look-ahead buffer is internal)
     return dict(
         robot=np.array([r.px, r.py, r.vx, r.vy, r.gx, r.gy], dtype=np.float64),
         hpx=f("px"), hpy=f("py"), hvx=f("vx"), hvy=f("vy"), hgx=f("gx"), hgy=f("gy"),
         hrad=f("radius"), hvpref=f("v_pref"),
-        belief=np.array(env.last_human_states, dtype=np.float64).reshape(H, 5),
+        belief=_pad(np.array(env.last_human_states, dtype=np.float64).reshape(H, 5), Hmax),
+        count=int(H),
         traj=np.zeros((0,)) if traj is None else np.array(traj, dtype=np.float64),
-        vis=np.array(env.human_visibility, dtype=bool),
+        vis=_pad(np.array(env.human_visibility, dtype=bool), Hmax, False),
         global_time=float(env.global_time), potential=float(env.potential),
         nd_global=float(cfg.orca.neighbor_dist),
-        sim_exists=np.array([h.policy.sim is not None for h in env.humans], dtype=bool),
+        sim_exists=_pad(np.array([h.policy.sim is not None for h in env.humans], dtype=bool), Hmax, False),
     )
 
 
@@ -115,7 +133,7 @@ def run_case(name, case):
     sys.argv = ["x", "--no-cuda", "--env-name", case["env_name"]]
     import rvo2
     rvo2.ONLY_AGENT0 = False          # the genuine full doStep of every per-human simulator
-    H = case["human_num"]
+    H = case["human_num"] + case.get("human_num_range", 0)          # array width = max_human_num
     W = 12 if case["predict_method"] == "const_vel" else 2
     N, T = case["nenv"], case["steps"]
     mode = ["goal", "goal", "rand", "idle"]
@@ -126,7 +144,7 @@ def run_case(name, case):
     obs_keys = ["robot_node", "temporal_edges", "spatial_edges", "detected_human_num"] + \
                (["visible_masks"] if W == 2 else [])
     state_keys = ["robot", "hpx", "hpy", "hvx", "hvy", "hgx", "hgy", "hrad", "hvpref", "belief", "traj",
-                  "vis", "global_time", "potential", "nd_global", "sim_exists"]
+                  "vis", "global_time", "potential", "nd_global", "sim_exists", "count"]
     obs_rec = {k: [[None] * N for _ in range(T + 1)] for k in obs_keys}
     st_rec = {k: [[None] * N for _ in range(T + 1)] for k in state_keys}
     for k in range(N):
@@ -150,6 +168,9 @@ def run_case(name, case):
             rec["min_danger"][t, k] = getattr(info["info"], "min_dist", 0.0)
             # velocities/diagnostics of the step just taken (before a possible respawn zeroes them
             # we read the sims, which always hold the solved velocity of agent 0)
+            rec["human_actions"][t, k, len(env.humans):] = np.nan
+            rec["orca_nlines"][t, k, len(env.humans):] = -1
+            rec["orca_fail"][t, k, len(env.humans):] = -2
             for i, h in enumerate(env.humans):
                 sim = h.policy.sim
                 if sim is not None:
