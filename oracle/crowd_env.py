@@ -44,6 +44,8 @@ class EnvConfig(object):
     def __init__(self, **kw):
         self.human_num = 20
         self.human_num_range = 0             # sim.human_num_range: humans join / leave every 5 s
+        self.human_policy = "orca"           # humans.policy: 'orca' | 'social_force' (crowd_nav/policy/social_force.py)
+        self.sf_A, self.sf_B, self.sf_KI = 2.0, 1.0, 1.0     # config.sf
         self.predict_steps = 5
         self.predict_method = "const_vel"      # 'const_vel' | 'none' (CrowdSimVarNum-v0 obs)
         self.time_limit = 50.0
@@ -81,10 +83,11 @@ class EnvConfig(object):
     def from_reference(cls, config):
         """Snapshot a reference `crowd_nav.configs.config.Config` object."""
         assert config.action_space.kinematics == "holonomic"
-        assert config.humans.policy == "orca" and not config.robot.visible
+        assert config.humans.policy in ("orca", "social_force") and not config.robot.visible
         pm = config.sim.predict_method
         return cls(
             human_num=config.sim.human_num, human_num_range=config.sim.human_num_range, predict_steps=config.sim.predict_steps,
+            human_policy=config.humans.policy, sf_A=config.sf.A, sf_B=config.sf.B, sf_KI=config.sf.KI,
             predict_method=pm, time_limit=config.env.time_limit, time_step=config.env.time_step,
             pred_timestep=config.data.pred_timestep,
             randomize_attributes=config.env.randomize_attributes,
@@ -312,6 +315,8 @@ class CrowdEnvOracle(object):
         fov = np.pi * c.human_fov
         acts = []
         self.last_orca_diag = []
+        if c.human_policy == "social_force":
+            return self._social_force_actions(px, py, vx, vy, use_fov)
         for i in range(H):
             others = []
             for j in range(H):
@@ -348,6 +353,38 @@ class CrowdEnvOracle(object):
             sim.doStep()
             acts.append(sim.getAgentVelocity(0))
             self.last_orca_diag.append((sim._numLines(0), sim._lineFail(0)))
+        return acts
+
+    def _social_force_actions(self, px, py, vx, vy, use_fov):
+        """SOCIAL_FORCE.predict (crowd_nav/policy/social_force.py:11-49) for every human: pull towards the goal,
+        exponential push from every other human (out-of-FOV ones replaced by the dummy at (7, 7)), speed clipped."""
+        c, H = self.cfg, self.H
+        fov = np.pi * c.human_fov
+        acts = []
+        for i in range(H):
+            dx, dy = self.hgx[i] - px[i], self.hgy[i] - py[i]
+            dist = np.sqrt(dx ** 2 + dy ** 2)
+            dvx = c.sf_KI * ((dx / dist) * self.hvpref[i] - vx[i])
+            dvy = c.sf_KI * ((dy / dist) * self.hvpref[i] - vy[i])
+            ivx = ivy = 0
+            for j in range(H):
+                if j == i:
+                    continue
+                if (not use_fov) or self._in_fov(px[i], py[i], vx[i], vy[i], px[j], py[j], fov):
+                    ox, oy, orad = px[j], py[j], self.hrad[j]
+                else:
+                    ox, oy, orad = 7, 7, 0.3
+                ex, ey = px[i] - ox, py[i] - oy
+                d = np.sqrt(ex ** 2 + ey ** 2)
+                ivx += c.sf_A * np.exp((self.hrad[i] + orad - d) / c.sf_B) * (ex / d)
+                ivy += c.sf_A * np.exp((self.hrad[i] + orad - d) / c.sf_B) * (ey / d)
+            nvx = vx[i] + (dvx + ivx) * c.time_step
+            nvy = vy[i] + (dvy + ivy) * c.time_step
+            nrm = np.linalg.norm([nvx, nvy])
+            if nrm > self.hvpref[i]:
+                nvx, nvy = nvx / nrm * self.hvpref[i], nvy / nrm * self.hvpref[i]
+            acts.append((nvx, nvy))
+            self.last_orca_diag.append((0, -1))
         return acts
 
     def _truth_future_traj(self):

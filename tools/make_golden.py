@@ -45,6 +45,9 @@ CASES = {
                                  randomize=False, goal_changing=False, nenv=3, steps=200, seed=425),
     "env_pred_h6_range3": dict(env_name="CrowdSimPred-v0", human_num=6, predict_method="const_vel", human_num_range=3,
                                randomize=True, goal_changing=True, nenv=2, steps=200, seed=9),
+    # humans.policy = 'social_force' 
+    "env_pred_h8_sf": dict(env_name="CrowdSimPred-v0", human_num=8, predict_method="const_vel", human_policy="social_force",
+                           randomize=True, goal_changing=True, nenv=2, steps=160, seed=21),
     "env_pred_h10_test_rand": dict(env_name="CrowdSimPred-v0", human_num=10, predict_method="const_vel",
                                    randomize=True, goal_changing=True, nenv=2, steps=200, seed=11, phase="test"),
 }
@@ -73,6 +76,7 @@ def build_reference_env(case, rank):
     cfg = Config()
     cfg.sim.human_num = case["human_num"]
     cfg.sim.human_num_range = case.get("human_num_range", 0)
+    cfg.humans.policy = case.get("human_policy", "orca")
     cfg.sim.predict_method = case["predict_method"]
     cfg.env.use_wrapper = False
     cfg.env.randomize_attributes = case["randomize"]
@@ -113,7 +117,7 @@ def ref_state(env, cfg):
         vis=_pad(np.array(env.human_visibility, dtype=bool), Hmax, False),
         global_time=float(env.global_time), potential=float(env.potential),
         nd_global=float(cfg.orca.neighbor_dist),
-        sim_exists=_pad(np.array([h.policy.sim is not None for h in env.humans], dtype=bool), Hmax, False),
+        sim_exists=_pad(np.array([getattr(h.policy, "sim", None) is not None for h in env.humans], dtype=bool), Hmax, False),
     )
 
 
@@ -172,7 +176,7 @@ def run_case(name, case):
             rec["orca_nlines"][t, k, len(env.humans):] = -1
             rec["orca_fail"][t, k, len(env.humans):] = -2
             for i, h in enumerate(env.humans):
-                sim = h.policy.sim
+                sim = getattr(h.policy, "sim", None)
                 if sim is not None:
                     rec["human_actions"][t, k, i] = sim.getAgentVelocity(0)
                     rec["orca_nlines"][t, k, i] = sim._numLines(0)
