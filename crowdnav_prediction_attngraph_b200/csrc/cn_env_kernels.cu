@@ -441,6 +441,16 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
                         cfg->human_num);
   if (cfg->const_vel && (cfg->predict_steps < 0 || 2 * (cfg->predict_steps + 1) > 16))
     return cn_set_error("cn_env_create: predict_steps %d unsupported (row width > 16)", cfg->predict_steps);
+  {
+    // global_time is kept as step_count * time_step; the reference ACCUMULATES `global_time += time_step`
+    // (crowd_sim_pred.py:160).  The two agree bit for bit iff every partial sum is exact, i.e. time_step is a
+    // dyadic rational with a short mantissa (0.25, the reference's value; 0.5; 0.125 ...).  Anything else (0.1)
+    // could shift the time-out / 5-second events by one step, so it is refused rather than approximated.
+    const double ts = cfg->time_step * 1024.0;
+    if (!(cfg->time_step > 0) || ts != floor(ts))
+      return cn_set_error("cn_env_create: time_step %.17g is not a multiple of 1/1024 (the engine keeps global_time as "
+                          "step * time_step, exact only for such steps)", cfg->time_step);
+  }
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);
   if (err != cudaSuccess || ndev == 0)

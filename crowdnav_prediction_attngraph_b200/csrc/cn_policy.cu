@@ -36,7 +36,8 @@ struct cn_policy {
   int64_t launches;
   int num_sms;
   bool pdl;           // programmatic dependent launch along the kernel chain (CN_PDL=0 disables)
-  bool launch_error;  // a GEMM output map could not be built (cn_last_error has the reason)
+  bool launch_error;  // a launch or a GEMM output map failed (cn_last_error has the stage and the reason)
+  const char* cur_stage = nullptr;   // stage name of the launches being enqueued (error reports)
   int qkv_chunks;     // 1 (default): single pass; 2 (CN_QKV_CHUNKS=2): QKV + attention in two row chunks with overlap
   bool finalized;
   std::map<std::string, std::vector<float>> host;
@@ -190,7 +191,12 @@ void launch_k(cn_policy* p, void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = p->pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess && !p->launch_error) {     // keep the FIRST failure and the stage it happened in
+    p->launch_error = true;
+    cn_set_error("kernel launch failed in stage '%s' (launch #%lld of this handle): %s",
+                 p->cur_stage ? p->cur_stage : "?", (long long)p->launches, cudaGetErrorString(e));
+  }
   p->launches += 1;
 }
 
@@ -254,6 +260,7 @@ const char* kStageNames[] = {"pack_inputs", "embed1_gemm", "embed2_gemm", "qkv_g
 const int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
 inline void mark(cn_policy* p, cudaStream_t st, int i) {
+  p->cur_stage = i < kNumStages ? kStageNames[i] : "end";
   if (p->profile) cudaEventRecord(p->ev[i], st);
 }
 
@@ -633,8 +640,8 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
                                                d->value, d->action, d->log_prob, d->action_mean);
   mark(p, st, kNumStages);
   cudaError_t err = cudaGetLastError();
+  if (p->launch_error) { p->launch_error = false; return 1; }      // cn_last_error names the stage
   if (err != cudaSuccess) return cn_set_error("cn_policy_act launch: %s", cudaGetErrorString(err));
-  if (p->launch_error) { p->launch_error = false; return 1; }
   return 0;
 }
 

@@ -331,5 +331,7 @@ class Policy(nn.Module):
         logstd = self.dist.logstd._bias.t().view(1, -1).expand_as(mean)
         dist = torch.distributions.Normal(mean, logstd.exp())
         logp = dist.log_prob(action).sum(-1, keepdim=True)
-        entropy = dist.entropy().sum(-1).mean()
+        # the reference's FixedNormal defines `entrop` (typo, distributions.py:42), so model.py:88 reaches
+        # torch's Normal.entropy() -> [B, 2] and .mean() averages over BOTH action dimensions
+        entropy = dist.entropy().mean()
         return value, logp, entropy, {'human_node_rnn': h}

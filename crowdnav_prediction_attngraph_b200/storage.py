@@ -85,8 +85,9 @@ class RolloutStorage(object):
                 dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
         if n:
             from . import _capi
-            _capi.check(self._lib, self._lib.cn_copy_segments(segs, n, self.device.index or 0, C.c_void_p(
-                torch.cuda.current_stream(self.device).cuda_stream)), "cn_copy_segments")
+            with torch.cuda.device(self.device):      # cn_copy_segments calls cudaSetDevice: keep the caller's device
+                _capi.check(self._lib, self._lib.cn_copy_segments(segs, n, self.device.index or 0, C.c_void_p(
+                    torch.cuda.current_stream(self.device).cuda_stream)), "cn_copy_segments")
         self.step = (s + 1) % self.num_steps
 
     def rollout_step_zero_copy(self, engine, env, deterministic=False):

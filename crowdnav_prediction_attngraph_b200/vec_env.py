@@ -11,6 +11,7 @@ A zero-host-round-trip variant (`step_device`) returns reward/done/info as devic
 device-resident rollout loop.
 """
 import ctypes as C
+import time
 from collections import OrderedDict
 
 import numpy as np
@@ -73,7 +74,7 @@ class Box(_Space):
 
 
 def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None, rank_offset=0, device_index=0,
-                               phase=None):
+                               phase=None, allow_unsorted=False):
     """Snapshot a reference `Config` object (crowd_nav/configs/config.py) into the flat cn_config.
     phase None follows rl/networks/envs.py:55-58: one environment -> 'test', more -> 'train'."""
     if phase is None:
@@ -93,6 +94,10 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
     else:
         raise NotImplementedError("env id %r is not covered by the CUDA engine" % env_name)
     sort_humans = getattr(getattr(config, "args", None), "sort_humans", True)
+    if not sort_humans and not allow_unsorted:
+        # the policy mirror masks attention with detected_human_num, which is only valid for distance-sorted rows
+        # (selfAttn_srnn_temp_node.py:398-404 uses visible_masks otherwise); the GST wrapper sorts on its own
+        raise NotImplementedError("args.sort_humans=False is covered only behind the GST wrapper (pretext_wrapper=True)")
     return _capi.default_config_dict(
         num_envs=num_envs, nenv_total=nenv_total or num_envs, rank_offset=rank_offset, seed=seed,
         human_num=config.sim.human_num, predict_steps=config.sim.predict_steps, const_vel=const_vel,
@@ -117,8 +122,9 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
 class LazyInfos(object):
     """Sequence of per-env info dicts, materialised on access (train.py:180-189 iterates it)."""
 
-    def __init__(self, info_codes, aux, done, ep_ret, ep_len):
+    def __init__(self, info_codes, aux, done, ep_ret, ep_len, t_start=None):
         self._codes, self._aux, self._done, self._ret, self._len = info_codes, aux, done, ep_ret, ep_len
+        self._t = round(time.time() - t_start, 6) if t_start is not None else 0.0     # Monitor's 't': seconds since creation
 
     def __len__(self):
         return len(self._codes)
@@ -128,7 +134,7 @@ class LazyInfos(object):
         obj = Danger(float(self._aux[i])) if code == 4 else _INFO_CLASSES[code]()
         d = {'info': obj}
         if self._done[i]:
-            d['episode'] = {'r': round(float(self._ret[i]), 6), 'l': int(self._len[i])}
+            d['episode'] = {'r': round(float(self._ret[i]), 6), 'l': int(self._len[i]), 't': self._t}
         return d
 
     def __iter__(self):
@@ -154,7 +160,8 @@ class CudaCrowdVecEnv(object):
         self.cfgd = d
         self._cfg = _capi.config_from_dict(d)
         self._h = C.c_void_p()
-        _capi.check(self.lib, self.lib.cn_env_create(C.byref(self._cfg), C.byref(self._h)), "cn_env_create")
+        with torch.cuda.device(self.device):       # the C entry point calls cudaSetDevice: keep the caller's current device
+            _capi.check(self.lib, self.lib.cn_env_create(C.byref(self._cfg), C.byref(self._h)), "cn_env_create")
         N, H = d["num_envs"], d["human_num"]
         W = 2 * (d["predict_steps"] + 1) if d["const_vel"] else 2
         self.num_envs, self.human_num, self.row_width = N, H, W
@@ -186,6 +193,7 @@ class CudaCrowdVecEnv(object):
             off += nb
         self._outp = _capi.CnStepPtrs(*[self._out[k].data_ptr() if k in self._out else None
                                         for k, _ in _capi.CnStepPtrs._fields_])
+        self._t_start = time.time()
         self.closed = False
 
     def _alloc_obs(self, dev):
@@ -230,11 +238,13 @@ class CudaCrowdVecEnv(object):
         if reward_out is not None or not_done_out is not None:
             vals = {k: self._out[k].data_ptr() for k in self._out}
             if reward_out is not None:
-                assert reward_out.is_contiguous() and reward_out.numel() == self.num_envs and reward_out.dtype == torch.float32
+                assert reward_out.is_cuda and reward_out.is_contiguous() and reward_out.numel() == self.num_envs \
+                    and reward_out.dtype == torch.float32
                 vals["reward"] = reward_out.data_ptr()
                 reward = reward_out
             if not_done_out is not None:
-                assert not_done_out.is_contiguous() and not_done_out.numel() == self.num_envs
+                assert not_done_out.is_cuda and not_done_out.is_contiguous() and not_done_out.numel() == self.num_envs \
+                    and not_done_out.dtype == torch.float32      # the kernel stores float 0.0 / 1.0
                 vals["not_done"] = not_done_out.data_ptr()
             outp = _capi.CnStepPtrs(*[vals.get(k) for k, _ in _capi.CnStepPtrs._fields_])
         with torch.cuda.device(self.device):
@@ -253,7 +263,7 @@ class CudaCrowdVecEnv(object):
         reward = h["reward"].clone().unsqueeze(1)
         done = h["done"].numpy().astype(np.bool_)
         infos = LazyInfos(h["info"].numpy().copy(), h["info_aux"].numpy().copy(), done, h["ep_ret"].numpy().copy(),
-                          h["ep_len"].numpy().copy())
+                          h["ep_len"].numpy().copy(), self._t_start)
         return obs, reward, done, infos
 
     def step(self, actions):
@@ -320,7 +330,7 @@ def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, device, allow_e
                              "model_state_dict, config.pred.model_dir/checkpoint/epoch_100.pt)")
         d = config_dict_from_reference(config, num_processes, seed, "CrowdSimVarNum-v0", nenv_total=nenv_total,
                                        rank_offset=rank_offset, device_index=device.index if device.index is not None else 0,
-                                       phase=phase)
+                                       phase=phase, allow_unsorted=True)
         return CudaPretextVecEnv(gst_params, device=device, cfg=d)
     d = config_dict_from_reference(config, num_processes, seed, env_name, nenv_total=nenv_total,
                                    rank_offset=rank_offset,
@@ -358,14 +368,15 @@ class CudaPretextVecEnv(object):
         self.observation_space = _DictSpace(spaces)
         self.action_space = e.action_space
         self._h = C.c_void_p()
-        _capi.check(self.lib, self.lib.cn_gst_create(N, H, self.P, float(self.cfgd["robot_radius"]),
-                                                     float(self.cfgd["human_radius"]), float(self.cfgd["collision_penalty"]),
-                                                     self.device.index or 0, C.byref(self._h)), "cn_gst_create")
-        for k, v in gst_params.items():
-            arr = np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
-            _capi.check(self.lib, self.lib.cn_gst_set_param(self._h, k.encode(), arr.ctypes.data, arr.size),
-                        "cn_gst_set_param(%s)" % k)
-        _capi.check(self.lib, self.lib.cn_gst_finalize(self._h), "cn_gst_finalize")
+        with torch.cuda.device(self.device):       # cn_gst_* call cudaSetDevice: keep the caller's current device
+            _capi.check(self.lib, self.lib.cn_gst_create(N, H, self.P, float(self.cfgd["robot_radius"]),
+                                                         float(self.cfgd["human_radius"]), float(self.cfgd["collision_penalty"]),
+                                                         self.device.index or 0, C.byref(self._h)), "cn_gst_create")
+            for k, v in gst_params.items():
+                arr = np.ascontiguousarray(v.detach().cpu().numpy() if hasattr(v, "detach") else v, dtype=np.float32)
+                _capi.check(self.lib, self.lib.cn_gst_set_param(self._h, k.encode(), arr.ctypes.data, arr.size),
+                            "cn_gst_set_param(%s)" % k)
+            _capi.check(self.lib, self.lib.cn_gst_finalize(self._h), "cn_gst_finalize")
         self._sp = [torch.zeros(N, H, W, device=self.device) for _ in range(2)]
         self._pen = torch.zeros(N, device=self.device)
         self._flip = 0
@@ -406,7 +417,7 @@ class CudaPretextVecEnv(object):
         h = e._host
         done_np = h["done"].numpy().astype(np.bool_)
         infos = LazyInfos(h["info"].numpy().copy(), h["info_aux"].numpy().copy(), done_np, h["ep_ret"].numpy().copy(),
-                          h["ep_len"].numpy().copy())
+                          h["ep_len"].numpy().copy(), e._t_start)
         return obs, h["reward"].clone().unsqueeze(1), done_np, infos
 
     def talk2Env(self, data):

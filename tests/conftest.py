@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: long-running CPU test")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests are the parity tests proper and need a CUDA device: without one they SKIP (a plain
+    `pytest tests` on a CPU machine must not error out)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_oracle():
     """The oracle's C++ part (test infrastructure) is built on demand."""
