@@ -1,0 +1,3 @@
+from crowdnav_prediction_attngraph_b200.compat import extend_with_reference
+
+extend_with_reference(__path__, "rl/networks")

@@ -135,7 +135,13 @@ class CudaPolicy(object):
                     assert out[k].is_cuda and out[k].is_contiguous() and out[k].dtype == torch.float32, k
                     b[k] = out[k]
         if not deterministic and noise is None:
-            noise = torch.randn(N, 2, device=self.device)      # torch.normal(mean, std) == randn * std + mean
+            # torch.normal(mean, std) == randn * std + mean.  Data-parallel replicas are seeded alike by train.py
+            # (identical initial weights): give every rank its own noise stream so their actions decorrelate.
+            if self._gen is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                    and torch.distributed.get_world_size() > 1:
+                self._gen = torch.Generator(device=self.device)
+                self._gen.manual_seed(torch.initial_seed() + 7919 * torch.distributed.get_rank())
+            noise = torch.randn(N, 2, device=self.device, generator=self._gen)
         sp = obs["spatial_edges"]
         args = dict(robot_node=obs["robot_node"], temporal_edges=obs["temporal_edges"], spatial_edges=sp,
                     detected_human_num=obs["detected_human_num"], h_in=h, masks=masks)
@@ -195,13 +201,23 @@ class Policy(nn.Module):
         self.nminibatch = int(getattr(args, 'num_mini_batch', 2)) if args is not None else 2
         p = _Params(self.input_size)
         self.base = p.base
+        # attributes the reference's callers read / write on `actor_critic.base` (test.py:148, rl/evaluation.py:15-21)
         self.base.nenv = self.nenv
+        self.base.human_num = self.human_num
+        self.base.seq_length, self.base.nminibatch = self.seq_length, self.nminibatch
+        self.base.human_node_rnn_size = int(getattr(args, 'human_node_rnn_size', HIDDEN)) if args is not None else HIDDEN
+        self.base.human_human_edge_rnn_size = int(getattr(args, 'human_human_edge_rnn_size', 256)) if args is not None else 256
+        self.base.output_size = 256
         self.dist = p.dist
         self.srnn = True
         self._cuda = None
         self._cuda_version = -1
 
     is_recurrent = True
+
+    @property
+    def recurrent_hidden_state_size(self):
+        return HIDDEN
 
     # ------------------------------------------------------------------ CUDA rollout path
     def _engine(self, N, device):

@@ -55,6 +55,10 @@ class PPO(object):
         self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
         self.max_grad_norm, self.use_clipped_value_loss = max_grad_norm, use_clipped_value_loss
         self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, eps=eps)
+        if _dist_ready():
+            # replicas must start from the same weights (train.py seeds every rank alike; this makes it a guarantee)
+            for p in actor_critic.parameters():
+                torch.distributed.broadcast(p.data, src=0)
 
     def update(self, rollouts):
         if self.matmul_precision == 'tf32':

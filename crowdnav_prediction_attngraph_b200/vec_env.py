@@ -11,6 +11,7 @@ A zero-host-round-trip variant (`step_device`) returns reward/done/info as devic
 device-resident rollout loop.
 """
 import ctypes as C
+import os
 import time
 from collections import OrderedDict
 
@@ -49,6 +50,13 @@ class Danger(object):
 
 
 _INFO_CLASSES = (Nothing, Timeout, Collision, ReachGoal, Danger)
+
+
+def _trace(msg):
+    """CROWDNAV_B200_TRACE=1: one stderr line per engine object (the drop-in tests look for it)."""
+    if os.environ.get("CROWDNAV_B200_TRACE", "0") == "1":
+        import sys
+        sys.stderr.write("crowdnav_b200: %s\n" % msg)
 
 
 class _Space(object):
@@ -142,6 +150,44 @@ class LazyInfos(object):
             yield self[i]
 
 
+class _BaseEnvView(object):
+    """What rl/evaluation.py:42-50,75 reaches through `eval_envs.venv.envs[0].env`: the raw environment's
+    `time_limit`, `global_time` (simulation time of environment 0) and the writable `episode_k`."""
+
+    def __init__(self, venv):
+        self._venv = venv
+        self.episode_k = 0
+
+    @property
+    def time_limit(self):
+        return self._venv.cfgd["time_limit"]
+
+    @property
+    def global_time(self):
+        return float(self._venv.get_state("step_count")[0]) * float(self._venv.cfgd["time_step"])
+
+
+class _MonitorView(object):
+    def __init__(self, venv):
+        self.env = _BaseEnvView(venv)
+
+
+class _VenvView(object):
+    """Stands for the wrapped `DummyVecEnv` / `ShmemVecEnv` the reference's VecPyTorch holds in `.venv`."""
+
+    def __init__(self, venv):
+        self._venv = venv
+        self.envs = [_MonitorView(venv)]
+        self.num_envs = venv.num_envs
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def __getattr__(self, name):           # VecEnvWrapper.__getattr__ passthrough (rl/vec_env/vec_env.py:194-197)
+        return getattr(self._venv, name)
+
+
 class CudaCrowdVecEnv(object):
     """N crowd-navigation environments resident on one GPU (one shard of the job)."""
 
@@ -195,6 +241,8 @@ class CudaCrowdVecEnv(object):
                                         for k, _ in _capi.CnStepPtrs._fields_])
         self._t_start = time.time()
         self.closed = False
+        _trace("engine CudaCrowdVecEnv N=%d (of %d, offset %d) H=%d const_vel=%d phase=%d device=%s gst=0" % (
+            N, d["nenv_total"], d["rank_offset"], H, d["const_vel"], d["phase"], self.device))
 
     def _alloc_obs(self, dev):
         N, H, W = self.num_envs, self.human_num, self.row_width
@@ -274,7 +322,20 @@ class CudaCrowdVecEnv(object):
         return np.ones(self.num_envs, dtype=bool)
 
     def render(self, mode='human'):
-        raise NotImplementedError("rendering is out of scope (SURVEY.md §2.1 row 1)")
+        """Rendering is out of scope: a no-op with one warning, so that the reference's
+        test.py (whose --visualize defaults to True) still runs."""
+        if not getattr(self, "_render_warned", False):
+            self._render_warned = True
+            import warnings
+            warnings.warn("crowdnav_b200: render() is a no-op (rendering is outside the engine's scope)")
+        return None
+
+    @property
+    def venv(self):
+        v = self.__dict__.get("_venv_view")
+        if v is None:
+            v = self.__dict__["_venv_view"] = _VenvView(self)
+        return v
 
     def close(self):
         if not self.closed and self._h:
@@ -377,6 +438,7 @@ class CudaPretextVecEnv(object):
                 _capi.check(self.lib, self.lib.cn_gst_set_param(self._h, k.encode(), arr.ctypes.data, arr.size),
                             "cn_gst_set_param(%s)" % k)
             _capi.check(self.lib, self.lib.cn_gst_finalize(self._h), "cn_gst_finalize")
+        _trace("engine CudaPretextVecEnv N=%d H=%d P=%d device=%s gst=1" % (N, H, self.P, self.device))
         self._sp = [torch.zeros(N, H, W, device=self.device) for _ in range(2)]
         self._pen = torch.zeros(N, device=self.device)
         self._flip = 0
@@ -422,6 +484,23 @@ class CudaPretextVecEnv(object):
 
     def talk2Env(self, data):
         return np.ones(self.num_envs, dtype=bool)
+
+    def render(self, mode='human'):
+        return self.env.render(mode)
+
+    @property
+    def venv(self):
+        return self.env.venv
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def get_state(self, name):
+        return self.env.get_state(name)
+
+    def set_state(self, name, arr):
+        return self.env.set_state(name, arr)
 
     def launch_count(self):
         return self.env.launch_count() + int(self.lib.cn_gst_launch_count(self._h))
