@@ -46,6 +46,7 @@ struct CnParams {
   double goal_change_chance;
   double orca_safety_space, orca_neighbor_dist;   // neighbor_dist: initial value of the global
   float orca_time_horizon;
+  int defer_tries;        // warp-scope rejection-sampling budget (cn_env_event_kernel -> cn_env_event_heavy_kernel)
 };
 
 // Struct-of-arrays environment state in HBM.  Per-human arrays are [N][H] (human index
@@ -93,6 +94,9 @@ struct CnState {
   int *perm;                         // [grid * epb] (entries >= N: empty slot)
   int *lp_cost;                      // [N] humans whose last solve needed linearProgram3 (cost estimate)
   uint8_t *spawn_overflow;           // [N] set when a rejection-sampling loop hit CN_MAX_SPAWN_TRIES
+  // events whose rejection sampling exceeded the warp-scope budget, redone by cn_env_event_heavy_kernel:
+  int *defer_list;                   // [N] env | event kind << 24
+  int *defer_ctl;                    // [4] {count, finished-CTA ticket, total deferrals (diagnostic), unused}
   // overflow ORCA lines (k >= line_cap) of every step-kernel thread: [grid * block][ovf_stride] float4
   void *line_ovf;
   int ovf_stride;

@@ -27,6 +27,10 @@
 
 #define CN_PI 3.141592653589793
 #define CN_MAX_SPAWN_TRIES 20000
+// heavy (CTA-scope) rejection sampling: threads per try, and the warp-scope budget of tries before an event is deferred
+#define CN_HEAVY_SUB 4
+#define CN_HEAVY_THREADS 512
+#define CN_DEFER_TRIES 320
 
 CN_HD double cn_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
@@ -364,10 +368,47 @@ CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng
                                  int skip, double rad_i, double vp, uint8_t* overflow) {
   CnCand c; c.x = 0; c.y = 0;
   for (int tries = 0;;) {
+    // warp scope: a search that has used up its budget is handed to cn_env_event_heavy_kernel (warp-uniform exit)
+    if (rng.budget > 0 && tries >= rng.budget) { rng.deferred = 1; return c; }
     int nb = (624 - rng.pos) / 6;                              // whole tries left before the next twist
-    if (nb > co.nlanes) nb = co.nlanes;
+    if (co.nlanes <= 32 && nb > co.nlanes) nb = co.nlanes;
     if (nb > CN_MAX_SPAWN_TRIES - tries + 1) nb = CN_MAX_SPAWN_TRIES - tries + 1;
-    if (co.nlanes > 1 && nb >= 1) {
+#if defined(__CUDA_ARCH__)
+    if (co.nlanes > 32 && nb >= 1) {
+      // CTA scope (heavy path): all <= 104 tries up to the next twist at once, CN_HEAVY_SUB consecutive threads
+      // share one try and split the agent list; the FIRST free try wins, exactly like the sequential loop.
+      const int t = co.lane / CN_HEAVY_SUB, sub = co.lane - t * CN_HEAVY_SUB;
+      if (nb > co.nlanes / CN_HEAVY_SUB) nb = co.nlanes / CN_HEAVY_SUB;
+      if (co.lane == 0) co.scratch[0] = 0x7fffffff;
+      __syncthreads();
+      bool collide = false;
+      if (t < nb) {
+        const int off = 6 * t;
+        const CnCand cc = cn_cand_point(p, cn_rng_peek_double(rng, off), cn_rng_peek_double(rng, off + 2),
+                                        cn_rng_peek_double(rng, off + 4), goal_kind, vp);
+        for (int k = -1 + sub; k < n && !collide; k += CN_HEAVY_SUB)
+          if (k != skip) collide = cn_cand_collides(p, s, cc.x, cc.y, rad_i, k);
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, collide);
+      const uint32_t gmask = ((1u << CN_HEAVY_SUB) - 1u) << ((threadIdx.x & 31) / CN_HEAVY_SUB * CN_HEAVY_SUB);
+      if (t < nb && sub == 0 && !(m & gmask)) atomicMin(co.scratch, t);
+      __syncthreads();
+      const int first = co.scratch[0];
+      __syncthreads();
+      const bool last = (tries + nb - 1 >= CN_MAX_SPAWN_TRIES);
+      if (first != 0x7fffffff || last) {
+        const int j = (first != 0x7fffffff) ? first : nb - 1;
+        c = cn_cand_point(p, cn_rng_peek_double(rng, 6 * j), cn_rng_peek_double(rng, 6 * j + 2),
+                          cn_rng_peek_double(rng, 6 * j + 4), goal_kind, vp);
+        rng.pos += 6 * (j + 1);
+        if (first == 0x7fffffff && co.lane == 0) *overflow = 1;
+        return c;
+      }
+      rng.pos += 6 * nb; tries += nb;
+      continue;
+    }
+#endif
+    if (co.nlanes > 1 && co.nlanes <= 32 && nb >= 1) {
       bool collide = true;
       if (co.lane < nb) {
         const int off = 6 * co.lane;
@@ -416,9 +457,12 @@ CN_HD CnSpawn cn_circle_crossing_human(const CnParams& p, const CnEnvSh& s, CnRn
 // legacy MT19937 with the CURRENT case_counter, sample robot + humans into the scratch working set `s`
 // and publish the result in g.prep_*.  Pure function of (seed, case_counter): it runs off the critical
 // path.  `key` = 624-word scratch; every lane of `co` runs this function (replicated), lane 0 writes.
-CN_HD void cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
+// Returns true when a rejection-sampling search exhausted `budget` tries (warp scope only): nothing was published and
+// the caller hands the environment to the CTA-scope kernel, which redoes the preparation with budget 0.
+CN_HD bool cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co,
+                          int budget = 0) {
   const int H = p.H;
-  CnRng rng; rng.key = key; rng.pos = 624;
+  CnRng rng; rng.key = key; rng.pos = 624; rng.budget = budget; rng.deferred = 0;
   const uint32_t cc = g.case_counter[e];
   const uint32_t this_seed = p.seed_base + (uint32_t)g.seed_off[e];
   cn_rng_seed(rng, p.phase_offset + cc + this_seed, co);
@@ -436,6 +480,7 @@ CN_HD void cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   double nd = g.nd_global[e];
   for (int i = 0; i < H; ++i) {
     const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, i, nd, g.spawn_overflow + e);
+    if (rng.deferred) return true;
     if (co.lane == 0) {
       s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
     }
@@ -452,6 +497,7 @@ CN_HD void cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
     g.prep_mt_pos[e] = rng.pos;
   }
   cn_coop_sync(co);
+  return false;
 }
 
 // INSTALL the prepared episode (per human thread; the leader also installs the per-env scalars).
@@ -573,9 +619,11 @@ CN_HD void cn_phase_obs_c(const CnParams& p, CnEnvSh& s, int e, int h, const CnO
 // Phase GOALS (only when the episode continues): random goal changes every 5 s and end-goal respawns
 // (crowd_sim_pred.py:202-211).  Replicated execution over the lanes of `co` (see CnCoop): every lane
 // draws the same random numbers from `key`; collision scans are lane-strided; lane 0 owns the writes.
-CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co) {
+// Returns true when a search exhausted `budget` tries (see cn_prepare_env): the caller must NOT store the working set.
+CN_HD bool cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co,
+                          int budget = 0) {
   const int H = p.H;
-  CnRng rng; rng.key = key; rng.pos = g.mt_pos[e];
+  CnRng rng; rng.key = key; rng.pos = g.mt_pos[e]; rng.budget = budget; rng.deferred = 0;
   double nd = g.nd_global[e];
   const int step = g.step_count[e];
   // global_time % 5 == 0 with global_time = step * 0.25 accumulated exactly
@@ -586,6 +634,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
       if (cn_rng_double(rng, co) <= p.goal_change_chance) {
         const double vp = (s.vpref[i] == 0) ? 1.0 : s.vpref[i];
         const CnCand c = cn_rejection_sample(p, s, rng, co, 1, H, i, s.rad[i], vp, g.spawn_overflow + e);
+        if (rng.deferred) return true;
         const double gx = c.x, gy = c.y;
         cn_coop_sync(co);
         if (co.lane == 0) { s.gx[i] = gx; s.gy[i] = gy; }
@@ -597,6 +646,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
     for (int i = 0; i < H; ++i) {
       if (cn_norm_dot(s.gx[i] - s.px[i], s.gy[i] - s.py[i]) < s.rad[i]) {
         const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, H, nd, g.spawn_overflow + e);
+        if (rng.deferred) return true;
         cn_coop_sync(co);
         if (co.lane == 0) {
           s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
@@ -608,6 +658,7 @@ CN_HD void cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
     }
   }
   if (co.lane == 0) { g.mt_pos[e] = rng.pos; if (p.randomize) g.nd_global[e] = nd; }
+  return false;
 }
 
 // Phase STORE: write the working set back to HBM.

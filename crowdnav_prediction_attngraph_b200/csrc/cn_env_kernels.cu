@@ -240,19 +240,73 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
   if (lane == 0) env_view(base, L, H, false, g, e);
   __syncwarp();
   uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
-  const CnCoop co = {lane, 32};
+  const CnCoop co = {lane, 32, nullptr};
+  bool deferred;
   if (evt == 2) {
-    cn_prepare_env(p, g, *s, e, key, co);
-    for (int i = lane; i < 624; i += 32) g.prep_mt[(size_t)e * 624 + i] = key[i];
+    deferred = cn_prepare_env(p, g, *s, e, key, co, p.defer_tries);
+    if (!deferred)
+      for (int i = lane; i < 624; i += 32) g.prep_mt[(size_t)e * 624 + i] = key[i];
   } else {
     // goal dynamics on the state the step kernel just stored
     for (int h = lane; h < H; h += 32) cn_phase_load(p, g, *s, e, h, nullptr);
     for (int i = lane; i < 624; i += 32) key[i] = g.mt[(size_t)e * 624 + i];
     __syncwarp();
-    cn_phase_goals(p, g, *s, e, key, co);
+    deferred = cn_phase_goals(p, g, *s, e, key, co, p.defer_tries);
     __syncwarp();
-    for (int h = lane; h < H; h += 32) cn_phase_store(p, g, *s, e, h);
-    for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
+    if (!deferred) {
+      for (int h = lane; h < H; h += 32) cn_phase_store(p, g, *s, e, h);
+      for (int i = lane; i < 624; i += 32) g.mt[(size_t)e * 624 + i] = key[i];
+    }
+  }
+  // a rejection-sampling search that ran out of its warp-scope budget: nothing was published; the whole event of
+  // this environment is redone by a 512-thread CTA (cn_env_event_heavy_kernel, launched right behind this kernel)
+  if (deferred && lane == 0) {
+    g.defer_list[atomicAdd(g.defer_ctl, 1)] = e | (evt << 24);
+    atomicAdd(g.defer_ctl + 2, 1);
+  }
+}
+
+// Heavy path of the event kernel.  In crowded configurations (BASELINE config 4: 50 randomised humans with random
+// goal changes) a few environments per step reach a state where a free goal / spawn position is found only after
+// thousands of candidates -- or never: the reference would spin there; the engine accepts candidate number
+// CN_MAX_SPAWN_TRIES (cn_env_core.cuh).  One warp needs milliseconds for such a search (every candidate is tested
+// against the position and the goal of every agent in fp64), and the next step kernel waits for it.  Here a CTA of
+// CN_HEAVY_THREADS threads redoes the event of ONE deferred environment from scratch with the same code in CTA
+// scope: the MT19937 twist runs 224 words at a time and the <= 104 candidates up to the next twist are evaluated at
+// once, CN_HEAVY_SUB threads per candidate splitting the agent list.  Results are identical to the sequential loop
+// (first free candidate, same stream position).
+__global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(CnParams p, CnState g) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int H = p.H;
+  const EnvSmemLayout L = env_layout(H, false);
+  CnEnvSh* s = reinterpret_cast<CnEnvSh*>(smem);
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem + L.per_env);
+  int* scratch = reinterpret_cast<int*>(key + 624);
+  const int count = g.defer_ctl[0];
+  const CnCoop co = {(int)threadIdx.x, (int)blockDim.x, scratch};
+  for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    const int entry = g.defer_list[idx];
+    const int e = entry & 0xffffff, evt = entry >> 24;
+    if (threadIdx.x == 0) env_view(smem, L, H, false, g, e);
+    __syncthreads();
+    if (evt == 2) {
+      cn_prepare_env(p, g, *s, e, key, co, 0);
+      for (int i = threadIdx.x; i < 624; i += blockDim.x) g.prep_mt[(size_t)e * 624 + i] = key[i];
+    } else {
+      for (int h = threadIdx.x; h < H; h += blockDim.x) cn_phase_load(p, g, *s, e, h, nullptr);
+      for (int i = threadIdx.x; i < 624; i += blockDim.x) key[i] = g.mt[(size_t)e * 624 + i];
+      __syncthreads();
+      cn_phase_goals(p, g, *s, e, key, co, 0);
+      __syncthreads();
+      for (int h = threadIdx.x; h < H; h += blockDim.x) cn_phase_store(p, g, *s, e, h);
+      for (int i = threadIdx.x; i < 624; i += blockDim.x) g.mt[(size_t)e * 624 + i] = key[i];
+    }
+    __syncthreads();
+  }
+  // the last CTA to finish clears the list for the next event kernel
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(g.defer_ctl + 1, 1) == (int)gridDim.x - 1) { g.defer_ctl[0] = 0; g.defer_ctl[1] = 0; }
   }
 }
 
@@ -319,6 +373,8 @@ struct cn_env {
   size_t smem_bytes;
   int line_cap;
   size_t reset_warp_bytes;
+  int heavy_grid;          // CTAs of cn_env_event_heavy_kernel (each loops over the deferred list)
+  size_t heavy_smem;
   int maxh;
   int64_t launches;
   std::map<std::string, Field> fields;
@@ -374,6 +430,11 @@ int event_kernel(cn_env* env, int force, cudaStream_t stream) {
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_event_kernel launch: %s", cudaGetErrorString(err));
+  // deferred (pathological) searches, one CTA each; an empty list costs one ~2 us launch on the side stream
+  cn_env_event_heavy_kernel<<<env->heavy_grid, CN_HEAVY_THREADS, env->heavy_smem, stream>>>(env->p, env->g);
+  env->launches += 1;
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return cn_set_error("cn_env_event_heavy_kernel launch: %s", cudaGetErrorString(err));
   return 0;
 }
 
@@ -502,6 +563,13 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   p.goal_change_chance = cfg->goal_change_chance;
   p.orca_safety_space = cfg->orca_safety_space; p.orca_neighbor_dist = cfg->orca_neighbor_dist;
   p.orca_time_horizon = (float)cfg->orca_time_horizon;
+  {
+    // warp-scope budget of rejection-sampling tries before an event goes to the CTA-scope kernel
+    // (CN_DEFER_TRIES=1 sends every search that needs a second candidate there: parity tests of the heavy path)
+    const char* dt = getenv("CN_DEFER_TRIES");
+    p.defer_tries = dt ? atoi(dt) : CN_DEFER_TRIES;
+    if (p.defer_tries < 1) p.defer_tries = 1;
+  }
 
   const size_t N = (size_t)p.N, NH = N * p.H;
   CnState& g = env->g;
@@ -518,7 +586,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
-  A(lp_cost, N);
+  A(lp_cost, N); A(defer_list, N); A(defer_ctl, 4);
 #undef A
   if (!rc) {
     // nd_global starts at the configured value (config.orca.neighbor_dist)
@@ -615,6 +683,17 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   err = cudaFuncSetAttribute(cn_env_event_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(CN_EVENT_WARPS * env->reset_warp_bytes));
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }
+  // heavy path: working set + MT19937 state + a few ints of scratch per CTA; half an SM-wave of CTAs (the list
+  // is short, and these CTAs share the GPU with the caller's policy kernels)
+  env->heavy_smem = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t) + 64);
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    env->heavy_grid = sms / 2 > 0 ? sms / 2 : 1;
+    if (env->heavy_grid > p.N) env->heavy_grid = p.N;
+  }
+  err = cudaFuncSetAttribute(cn_env_event_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->heavy_smem);
+  if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(heavy): %s", cudaGetErrorString(err)); }
   *out = env;
   return 0;
 }

@@ -13,23 +13,33 @@
 struct CnRng {
   uint32_t* key;   // 624 words
   int pos;
+  // Deferral of pathological rejection-sampling searches (cn_rejection_sample): a WARP-scope caller gives every
+  // search a budget of tries; a search that exhausts it sets `deferred` and the whole event of that environment is
+  // redone from scratch by a 512-thread CTA (cn_env_event_heavy_kernel).  budget 0 = unlimited.
+  int budget;
+  int deferred;
 };
 
 // Cooperative execution context.  {lane, 32}: the 32 lanes of a warp execute the same (replicated,
 // warp-uniform) control flow and split data-parallel inner loops between them; {0, 1}: a single
-// thread (the CPU test harness, where every collective degenerates to the identity).
+// thread (the CPU test harness, where every collective degenerates to the identity); {tid, blockDim, scratch}
+// with nlanes > 32: a whole CTA in replicated control flow (collectives become CTA barriers; `scratch` = a few
+// ints of shared memory).  Only the RNG / rejection-sampling path supports the CTA scope.
 struct CnCoop {
   int lane, nlanes;
+  int* scratch;
 };
 CN_HD bool cn_any(const CnCoop& c, bool pred) {
 #if defined(__CUDA_ARCH__)
+  if (c.nlanes > 32) return __syncthreads_or(pred ? 1 : 0) != 0;
   if (c.nlanes > 1) return __any_sync(0xffffffffu, pred) != 0;
 #endif
   return pred;
 }
 CN_HD void cn_coop_sync(const CnCoop& c) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) __syncwarp();
+  if (c.nlanes > 32) __syncthreads();
+  else if (c.nlanes > 1) __syncwarp();
 #endif
   (void)c;
 }
@@ -113,21 +123,22 @@ CN_HD uint32_t cn_rng_mix(uint32_t a, uint32_t b, uint32_t m) {
 }
 
 // genrand twist.  Sequential semantics: key[i] <- f(key[i], key[i+1], key[(i+397) % 624]) for i = 0..623
-// in order.  Chunks of `nlanes` consecutive i are independent (every operand a chunk reads is either
+// in order.  Chunks of up to 227 consecutive i are independent (every operand a chunk reads is either
 // not yet overwritten or was produced >= 227 positions earlier), so each chunk is read by all lanes,
-// synchronised, then written.
+// synchronised, then written.  (A CTA-scope context uses chunks of 224; its other lanes only take the barriers.)
 CN_HD void cn_rng_twist(CnRng& r, const CnCoop& c) {
-  const int nl = c.nlanes;
+  const int nl = c.nlanes < 224 ? c.nlanes : 224;
   for (int base = 0; base < 624; base += nl) {
     const int i = base + c.lane;
+    const bool mine = c.lane < nl && i < 624;
     uint32_t v = 0;
-    if (i < 624) {
+    if (mine) {
       const int i1 = (i + 1 == 624) ? 0 : i + 1;
       const int im = (i + 397 < 624) ? i + 397 : i + 397 - 624;
       v = cn_rng_mix(r.key[i], r.key[i1], r.key[im]);
     }
     cn_coop_sync(c);
-    if (i < 624) r.key[i] = v;
+    if (mine) r.key[i] = v;
     cn_coop_sync(c);
   }
   r.pos = 0;

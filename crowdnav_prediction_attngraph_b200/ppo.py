@@ -29,18 +29,26 @@ def global_advantage_normalize(adv):
     return ((adv - mean.float()) / (var.clamp_min(0).sqrt().float() + 1e-5))
 
 
-def allreduce_gradients(params):
-    """Average gradients across ranks through one flat fp32 bucket (2.5 M floats = 10 MB)."""
+def allreduce_gradients(params, events=None):
+    """Average gradients across ranks through one flat fp32 bucket (2.5 M floats = 10 MB).
+    `events`: optional list that receives (start, end) CUDA events around the collective (bench timing)."""
     if not _dist_ready():
-        return
+        return 0
     grads = [p.grad for p in params if p.grad is not None]
     flat = torch.cat([g.reshape(-1) for g in grads])
+    if events is not None and flat.is_cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     torch.distributed.all_reduce(flat)
+    if events is not None and flat.is_cuda:
+        e1.record()
+        events.append((e0, e1))
     flat.div_(torch.distributed.get_world_size())
     off = 0
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+    return flat.numel() * flat.element_size()
 
 
 class PPO(object):
@@ -50,6 +58,8 @@ class PPO(object):
         (fp32 matmuls like the reference); 'tf32' runs the update's matmuls on TF32 tensor cores
         (torch.set_float32_matmul_precision('high') for the duration of update())."""
         self.matmul_precision = matmul_precision
+        self.profile = False          # True: time the gradient all-reduces of update() -> self.last_profile
+        self.last_profile = None
         self.actor_critic = actor_critic
         self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
         self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
@@ -75,6 +85,8 @@ class PPO(object):
         advantages = global_advantage_normalize(advantages)
         v_sum = a_sum = e_sum = 0.0
         params = [p for p in self.actor_critic.parameters()]
+        events = [] if self.profile else None
+        ar_bytes = 0
         for _ in range(self.ppo_epoch):
             for sample in rollouts.recurrent_generator(advantages, self.num_mini_batch):
                 obs_b, hxs_b, act_b, vpred_b, ret_b, masks_b, old_lp_b, adv_b = sample
@@ -90,9 +102,16 @@ class PPO(object):
                     value_loss = 0.5 * (ret_b - values).pow(2).mean()
                 self.optimizer.zero_grad()
                 (value_loss * self.value_loss_coef + action_loss - entropy * self.entropy_coef).backward()
-                allreduce_gradients(params)
+                ar_bytes = allreduce_gradients(params, events) or ar_bytes
                 nn.utils.clip_grad_norm_(params, self.max_grad_norm)
                 self.optimizer.step()
                 v_sum += value_loss.item(); a_sum += action_loss.item(); e_sum += entropy.item()
         n = self.ppo_epoch * self.num_mini_batch
+        if self.profile:
+            if events:
+                torch.cuda.synchronize()
+            self.last_profile = {"optimizer_steps": n, "allreduce_calls": len(events or []),
+                                 "allreduce_ms": float(sum(a.elapsed_time(b) for a, b in (events or []))),
+                                 "allreduce_bytes_per_call": int(ar_bytes),
+                                 "world_size": torch.distributed.get_world_size() if _dist_ready() else 1}
         return v_sum / n, a_sum / n, e_sum / n

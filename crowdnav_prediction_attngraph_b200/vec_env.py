@@ -358,7 +358,8 @@ class CudaCrowdVecEnv(object):
                hpx="f8", hpy="f8", hgx="f8", hgy="f8", hrad="f8", hvpref="f8", hvx="f4", hvy="f4",
                bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
                sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",
-               last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4", evt="u1", spawn_overflow="u1")
+               last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4", evt="u1", spawn_overflow="u1",
+               defer_ctl="i4", defer_list="i4", lp_cost="i4")
 
     def get_state(self, name):
         nbytes = self.lib.cn_env_state_bytes(self._h, name.encode())

@@ -146,3 +146,49 @@ def test_host_buffer_entry_point_matches_device_path():
     for k in h_ob:
         assert np.array_equal(obs[k].cpu().numpy(), h_ob[k])
     assert np.array_equal(rew.cpu().numpy(), h_out["reward"]) and np.array_equal(done.cpu().numpy(), h_out["done"])
+
+
+@pytest.mark.parametrize("name", ["env_pred_h20_rand", "env_pred_h50_rand"])
+def test_heavy_event_path_matches_reference_golden(name, monkeypatch):
+    """CN_DEFER_TRIES=1: every rejection-sampling search that needs a second candidate is deferred to the
+    CTA-scope kernel (cn_env_event_heavy_kernel: 224-word twists, <= 104 candidates at once, 4 threads per
+    candidate) -- same goldens, same tolerances as the warp-scope path."""
+    monkeypatch.setenv("CN_DEFER_TRIES", "1")
+    g, case, over = load_env_case(name)
+    env = _engine(**over)
+
+    def step(a):
+        obs, rew, done, info = env.step_device(torch.from_numpy(a).cuda())
+        out = dict(reward=rew.cpu().numpy(), done=done.cpu().numpy(), info=info.cpu().numpy(),
+                   info_aux=env._out["info_aux"].cpu().numpy())
+        return _np_obs(obs), out
+
+    bad = replay(g, case, lambda: _np_obs(env.reset()), step, env.get_state, pos_tol=1e-9)
+    assert not bad, bad[:5]
+    assert int(env.get_state("defer_ctl")[2]) > 0          # the heavy kernel did serve events
+
+
+def test_heavy_event_path_equals_warp_path_at_config4_shape(monkeypatch):
+    """BASELINE config 4 shape (50 randomised humans, random goal changes), 256 environments, 120 steps: the run with
+    the default deferral budget, with everything deferred, and with nothing deferred end in the same state."""
+    import os
+    finals = []
+    for budget in ("320", "1", "1000000"):
+        monkeypatch.setenv("CN_DEFER_TRIES", budget)
+        env = _engine(num_envs=256, human_num=50, seed=9, randomize_attributes=1, random_goal_changing=1)
+        env.reset()
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        for _ in range(120):
+            a = torch.rand(256, 2, device="cuda", generator=gen) * 2 - 1
+            env.step_device(a)
+        torch.cuda.synchronize()
+        finals.append({k: env.get_state(k).copy() for k in ("hpx", "hpy", "hgx", "hgy", "hrad", "mt_pos", "rpx", "step_count",
+                                                           "case_counter", "spawn_overflow")})
+        finals[-1]["deferrals"] = int(env.get_state("defer_ctl")[2])
+        env.close()
+    for k in finals[0]:
+        if k == "deferrals":
+            continue
+        assert np.array_equal(finals[0][k], finals[1][k]), k
+        assert np.array_equal(finals[0][k], finals[2][k]), k
+    assert finals[1]["deferrals"] > finals[0]["deferrals"] >= 0 and finals[2]["deferrals"] == 0
