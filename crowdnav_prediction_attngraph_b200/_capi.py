@@ -49,7 +49,7 @@ class CnActPtrs(C.Structure):
 
 
 # every symbol include/crowdnav_b200.h declares (tests check the library exports all of them)
-ABI_VERSION = 2          # include/crowdnav_b200.h CN_ABI_VERSION
+ABI_VERSION = 3          # include/crowdnav_b200.h CN_ABI_VERSION
 
 EXPORTS = [
     "cn_last_error", "cn_abi_version", "cn_env_create", "cn_env_destroy", "cn_env_reset", "cn_env_step",
@@ -59,6 +59,8 @@ EXPORTS = [
     "cn_policy_stage_name", "cn_policy_stage_ms", "cn_copy_segments",
     "cn_gst_create", "cn_gst_destroy", "cn_gst_set_param", "cn_gst_finalize", "cn_gst_reset", "cn_gst_step",
     "cn_gst_launch_count",
+    "cn_update_linear_saved_bytes", "cn_update_linear_ws_bytes", "cn_update_linear_fwd", "cn_update_linear_bwd",
+    "cn_update_attn_fwd", "cn_update_attn_bwd",
 ]
 
 _lib = None
@@ -144,6 +146,14 @@ def load_library(path=None):
     lib.cn_policy_stage_name.restype = C.c_char_p
     lib.cn_policy_stage_name.argtypes = [C.c_int]
     lib.cn_policy_stage_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.cn_update_linear_saved_bytes.restype = C.c_size_t
+    lib.cn_update_linear_saved_bytes.argtypes = [C.c_int, C.c_int]
+    lib.cn_update_linear_ws_bytes.restype = C.c_size_t
+    lib.cn_update_linear_ws_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.cn_update_linear_fwd.argtypes = [C.c_void_p] * 6 + [C.c_size_t] + [C.c_int] * 5 + [C.c_void_p]
+    lib.cn_update_linear_bwd.argtypes = [C.c_void_p] * 8 + [C.c_size_t] + [C.c_int] * 5 + [C.c_void_p]
+    lib.cn_update_attn_fwd.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]
+    lib.cn_update_attn_bwd.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]
     if path is None:
         _lib = lib
     return lib

@@ -52,6 +52,12 @@ struct TcEpilogue {
   const int* m_ptr;      // optional device-side row count (compacted rows); tiles past it exit
   int dbg_nostore;       // diagnostic: run the epilogue arithmetic but skip the global stores
   const int* m0_ptr;     // optional device-side first row: the launch covers rows [*m0_ptr, *m_ptr) (row chunks)
+  // --- PPO update path (cn_update.cuh); all zero / null in the rollout ---
+  const float* inv_scale_a;   // optional device scalars: the result is also multiplied by *inv_scale_a * *inv_scale_b
+  const float* inv_scale_b;   // (dynamic power-of-two operand scales chosen from the tensors' amax)
+  int ksplit;                 // > 1: the K range is cut into `ksplit` slices, every slice is its own tile and ADDS its
+                              // partial product into a zero-initialised fp32 C with TMA reduce (bias from slice 0 only,
+                              // no activation): wgrad has K = #rows (hundreds of thousands) and a tiny output
 };
 
 namespace tc {
@@ -83,6 +89,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // TMA store of a shared-memory box to global memory (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+// TMA reduce (add) of a shared-memory fp32 box into global memory: split-K partial sums
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -202,15 +213,23 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   int m_lo = ep.m0_ptr ? *ep.m0_ptr : 0;
   if (m_lo > M) m_lo = M;
   const int n_ntiles = N / BN;
-  const int n_tiles = ((M - m_lo + TC_BM - 1) / TC_BM) * n_ntiles;   // CTAs beyond it run zero tiles and tear down
+  const int n_mn = ((M - m_lo + TC_BM - 1) / TC_BM) * n_ntiles;
+  const int ksplit = ep.ksplit > 1 ? ep.ksplit : 1;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;                 // k-blocks per slice (the last may be shorter)
+  const int n_tiles = n_mn * ksplit;                                 // CTAs beyond it run zero tiles and tear down
+  float inv_scale = ep.inv_scale;
+  if (ep.inv_scale_a) inv_scale *= __ldg(ep.inv_scale_a);
+  if (ep.inv_scale_b) inv_scale *= __ldg(ep.inv_scale_b);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;                                            // running k-block counter across tiles
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = m_lo + (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int mn = tile % n_mn, ks = tile / n_mn;
+        const int m0 = m_lo + (mn / n_ntiles) * TC_BM, n0 = (mn % n_ntiles) * TC_BN;
+        const int kb0 = ks * kb_per, kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
           tc::mbar_wait(bar_empty + 8 * s, ph ^ 1u);              // slot free (first pass returns immediately)
           const uint32_t full = bar_full + 8 * s;
@@ -233,7 +252,9 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
         tc::mbar_wait(bar_tempty + 8 * ab, aph ^ 1u);             // epilogue drained this accumulator
         tc::tcgen05_fence_after();
         const uint32_t tmem_acc = tmem_base + ab * TcCfg<BN>::kTmemCols;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int ks = tile / n_mn;
+        const int kb0 = ks * kb_per, kb1 = (kb0 + kb_per < num_kb) ? kb0 + kb_per : num_kb;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % TC_STAGES, ph = (it / TC_STAGES) & 1u;
           tc::mbar_wait(bar_full + 8 * s, ph);                    // TMA bytes landed
           tc::tcgen05_fence_after();
@@ -245,7 +266,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
             const uint32_t koff = k * 32;                         // 16 fp16 = 32 bytes inside the swizzle atom
             const uint64_t dah = tc::make_desc(a_hi + koff), dal = tc::make_desc(a_lo + koff);
             const uint64_t dbh = tc::make_desc(b_hi + koff), dbl = tc::make_desc(b_lo + koff);
-            tc::mma_f16(tmem_acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::mma_f16(tmem_acc, dah, dbh, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
             tc::mma_f16(tmem_acc, dah, dbl, idesc, 1u);
             tc::mma_f16(tmem_acc, dal, dbh, idesc, 1u);
           }
@@ -262,7 +283,8 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
     const uint32_t stage_out = base + TcCfg<BN>::kStageOutOff + (uint32_t)(warp - 2) * 4096u;   // 1024-byte aligned
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = m_lo + (tile / n_ntiles) * TC_BM, n0 = (tile % n_ntiles) * TC_BN;
+      const int mn = tile % n_mn, ks = tile / n_mn;
+      const int m0 = m_lo + (mn / n_ntiles) * TC_BM, n0 = (mn % n_ntiles) * TC_BN;
       const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
       tc::mbar_wait(bar_tfull + 8 * ab, aph);
       tc::tcgen05_fence_after();
@@ -272,7 +294,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       {
         const int et = threadIdx.x - 64;                          // index within the epilogue warps
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");   // previous tile's readers are done
-        for (int c = et; c < TC_BN; c += 32 * TC_EPI_WARPS) bias_s[c] = ep.bias ? __ldg(ep.bias + n0 + c) : 0.0f;
+        for (int c = et; c < TC_BN; c += 32 * TC_EPI_WARPS) bias_s[c] = (ep.bias && ks == 0) ? __ldg(ep.bias + n0 + c) : 0.0f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       }
       // activation is uniform over the tile unless the [act_lo, act_hi) window cuts through it
@@ -287,7 +309,7 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
         const float* bs = bias_s + c * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), ep.inv_scale, bs[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), inv_scale, bs[j]);
         if (act_mode == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -316,7 +338,11 @@ cn_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
                                __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
             tc::fence_async_smem();
             __syncwarp();
-            if (lane == 0) { tc::tma_store_2d(&map_c32, stage_out, nb, m0 + q * 32); tc::tma_store_commit(); }
+            if (lane == 0) {
+              if (ksplit > 1) tc::tma_reduce_add_2d(&map_c32, stage_out, nb, m0 + q * 32);
+              else tc::tma_store_2d(&map_c32, stage_out, nb, m0 + q * 32);
+              tc::tma_store_commit();
+            }
           }
           if (ep.out_hi) {
             if (lane == 0) tc::tma_store_wait_read();

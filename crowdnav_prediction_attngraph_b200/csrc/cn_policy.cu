@@ -214,6 +214,7 @@ void gemm_tc(cn_policy* p, cudaStream_t st, const TcMat& A, const TcMat& B, int 
              int act, const TcOut& o, const int* m_ptr = nullptr, int act_lo = 0, int act_hi = 1 << 30,
              const int* m0_ptr = nullptr) {
   TcEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
   ep.bias = bias; ep.inv_scale = 1.0f / 64.0f; ep.act = act; ep.act_lo = act_lo; ep.act_hi = act_hi;
   ep.c32 = o.c32; ep.ldc = o.ldc; ep.out_hi = o.oh; ep.out_lo = o.ol; ep.ldh = o.ldh; ep.m_ptr = m_ptr; ep.m0_ptr = m0_ptr;
   {
@@ -687,3 +688,4 @@ int cn_internal_gemm_tc(const float* dA, const float* dW, const float* dbias, fl
 }  // extern "C"
 
 #include "cn_gst_tc.cuh"
+#include "cn_update.cuh"

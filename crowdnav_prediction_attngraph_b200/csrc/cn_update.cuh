@@ -1,0 +1,554 @@
+// PPO update path (rl/ppo/ppo.py:36-101 -> Policy.evaluate_actions): the per-human linear
+// layers of the attention encoder -- 98 % of the update's FLOPs -- forward, data gradient and weight gradient on
+// the tcgen05 3xFP16 GEMM (cn_gemm_tc.cuh), in fp32-equivalent accuracy:
+//
+//   forward   Y[M,N]  = act(X[M,K] W[N,K]^T + b)
+//   dgrad     dX[M,K] = dZ[M,N] W[N,K]            dZ = dY o act'(Y)
+//   wgrad     dW[N,K] = dZ[M,N]^T X[M,K]          K-dimension of this GEMM = M rows (hundreds of thousands):
+//                                                 split-K over the CTAs, partial tiles added with TMA reduce
+//   db[N]     = column sums of dZ
+//
+// Every operand travels as a (hi, lo) fp16 pair.  Unlike the rollout (whose activations have known ranges and whose
+// weights carry a fixed 2^6 scale) gradients span many orders of magnitude, so each tensor gets a DYNAMIC
+// power-of-two scale from its amax (|x| max * scale in [2^13, 2^14)): exact to undo, keeps hi and lo in fp16's
+// normal range for everything within ~2^-24 of the tensor's largest entry.  The scales stay on the device
+// (no host synchronisation); the GEMM epilogue multiplies by 1 / (scale_a * scale_b).
+//
+// The C ABI below is stateless: the caller (crowdnav_prediction_attngraph_b200/update_ops.py, a torch.autograd
+// Function) owns every buffer, including the workspace.
+// (included at the end of cn_policy.cu: same translation unit as the GEMM kernel instantiations and the TMA helpers)
+#pragma once
+
+namespace {
+
+inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------- small kernels
+// amax of |x| (optionally of x o [y > 0]): non-negative floats order like their bit patterns
+__global__ void cn_upd_amax_kernel(const float* __restrict__ x, const float* __restrict__ relu_y, size_t count,
+                                   unsigned int* __restrict__ out) {
+  float m = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    float v = fabsf(x[i]);
+    if (relu_y && !(relu_y[i] > 0.0f)) v = 0.0f;
+    if (v == v && v < 3.0e38f) m = fmaxf(m, v);            // NaN / inf do not poison the scale (they poison the result)
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0f;
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) atomicMax(out, __float_as_uint(m));
+  }
+}
+
+// scale[0] = 2^k with amax * 2^k in [2^13, 2^14), scale[1] = 2^-k  (amax == 0: 1, 1)
+__global__ void cn_upd_scale_kernel(const unsigned int* __restrict__ amax_bits, float* __restrict__ scale) {
+  const float a = __uint_as_float(*amax_bits);
+  float s = 1.0f;
+  if (a > 0.0f) {
+    int e;
+    frexpf(a, &e);                                    // a = f * 2^e, f in [0.5, 1)
+    int k = 14 - e;
+    k = k > 100 ? 100 : (k < -100 ? -100 : k);
+    s = ldexpf(1.0f, k);
+  }
+  scale[0] = s;
+  scale[1] = 1.0f / s;
+}
+
+// (hi, lo) split of a row-major fp32 matrix src[M, C] (optionally masked by relu_y > 0), scaled by *scale:
+//   hi/lo    [M, Cp]   row-major (pitch Cp >= C, multiple of 64; padding columns zero) -- or null
+//   hiT/loT  [C, Mp]   transposed (pitch Mp >= M, multiple of 64; padding zero)       -- or null
+//   colsum   [C]       += column sums of the masked, UNscaled values (db)             -- or null
+// One 32 x 32 tile per 256-thread CTA iteration (grid-stride over tiles), transposed through shared memory.
+__global__ void __launch_bounds__(256) cn_upd_split_kernel(const float* __restrict__ src, int ld, const float* __restrict__ relu_y,
+                                                           int ldy, int M, int C, const float* __restrict__ scale,
+                                                           __half* __restrict__ hi, __half* __restrict__ lo, int Cp,
+                                                           __half* __restrict__ hiT, __half* __restrict__ loT, int Mp,
+                                                           float* __restrict__ colsum) {
+  __shared__ float tile[32][33];
+  const float sc = __ldg(scale);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const int tiles_c = (C + 31) / 32, tiles_m = (M + 31) / 32;
+  const int tiles_cp = Cp / 32 > tiles_c ? Cp / 32 : tiles_c;   // also visit the column padding of hi / lo
+  const int tiles_mp = Mp / 32 > tiles_m ? Mp / 32 : tiles_m;   // ... and the row padding of hiT / loT
+  const long long total = (long long)tiles_mp * tiles_cp;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int tm = (int)(t / tiles_cp), tcn = (int)(t - (long long)tm * tiles_cp);
+    const int r0 = tm * 32, c0 = tcn * 32;
+    float cs = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + ty + 8 * j, c = c0 + tx;
+      float v = 0.0f;
+      if (r < M && c < C) {
+        v = src[(size_t)r * ld + c];
+        if (relu_y && !(relu_y[(size_t)r * ldy + c] > 0.0f)) v = 0.0f;
+      }
+      cs += v;
+      const float x = fminf(fmaxf(v * sc, -65504.0f), 65504.0f);
+      tile[ty + 8 * j][tx] = x;
+      if (hi && r < M && c < Cp) {
+        const __half h = __float2half_rn(x);
+        hi[(size_t)r * Cp + c] = h;
+        lo[(size_t)r * Cp + c] = __float2half_rn(x - __half2float(h));
+      }
+    }
+    __shared__ float part[8][32];
+    if (colsum) {                                       // (uniform) 8 partial sums per column in this CTA
+      part[ty][tx] = cs;
+      __syncthreads();
+      if (ty == 0 && c0 + tx < C) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += part[j][tx];
+        if (s != 0.0f) atomicAdd(colsum + c0 + tx, s);
+      }
+    }
+    __syncthreads();
+    if (hiT) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, r = r0 + tx;          // transposed: this thread writes column c, row r
+        if (c < C && r < Mp) {
+          const float x = tile[tx][ty + 8 * j];
+          const __half h = __float2half_rn(x);
+          hiT[(size_t)c * Mp + r] = h;
+          loT[(size_t)c * Mp + r] = __float2half_rn(x - __half2float(h));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- attention (update)
+// Human-human multi-head self attention over COMPACTED rows, forward with soft-max statistics and backward
+// (selfAttn_srnn_temp_node.py:63-91 -> nn.MultiheadAttention core: softmax(q k^T / 8) v over the n valid humans of a
+// sample).  qkv [Mc, 1536] = (q | k | v) per row, 8 heads x 64.  One warp per row, all heads at once; lane l owns the
+// float4 #(l + 32 c), c = 0..3, of every 512-wide row = 4 elements of head 2 c + (l >= 16), so a head's dot product is
+// a butterfly over the 16 lanes of a half-warp.  The padded torch formulation this replaces materialised
+// [B, H, 1536] tensors (7.5 GB per minibatch at the bench shape); here only real rows move.
+#define CN_UPD_ATTN_WARPS 4
+#define CN_UPD_MAXKEYS 128
+
+__device__ __forceinline__ void upd_load_row(const float* __restrict__ p, int lane, float4 (&r)[4]) {
+  const float4* v = reinterpret_cast<const float4*>(p) + lane;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) r[c] = __ldg(v + 32 * c);
+}
+// per-head dot products of two 512-wide rows: s[c] = <a, b> restricted to head 2 c + (lane >= 16), on every lane of the half
+__device__ __forceinline__ void upd_dot_heads(const float4 (&a)[4], const float4 (&b)[4], float (&s)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float x = a[c].x * b[c].x;
+    x = fmaf(a[c].y, b[c].y, x); x = fmaf(a[c].z, b[c].z, x); x = fmaf(a[c].w, b[c].w, x);
+#pragma unroll
+    for (int o = 8; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    s[c] = x;
+  }
+}
+__device__ __forceinline__ void upd_axpy(float4 (&acc)[4], const float (&w)[4], const float4 (&x)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    acc[c].x = fmaf(w[c], x[c].x, acc[c].x); acc[c].y = fmaf(w[c], x[c].y, acc[c].y);
+    acc[c].z = fmaf(w[c], x[c].z, acc[c].z); acc[c].w = fmaf(w[c], x[c].w, acc[c].w);
+  }
+}
+
+// forward: out[r] = softmax_j(q_r . k_j / 8) v_j ; stats[r] = {max[8], sum[8]} (head h at index h and 8 + h)
+__global__ void __launch_bounds__(CN_UPD_ATTN_WARPS * 32) cn_upd_attn_fwd_kernel(const float* __restrict__ qkv,
+                                                                                const int* __restrict__ row_start,
+                                                                                const int* __restrict__ row_env, int Mc,
+                                                                                float* __restrict__ out, float* __restrict__ stats) {
+  __shared__ float sc[CN_UPD_ATTN_WARPS][CN_UPD_MAXKEYS][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4;
+  float (*my)[8] = sc[warp];
+  for (int r = blockIdx.x * CN_UPD_ATTN_WARPS + warp; r < Mc; r += gridDim.x * CN_UPD_ATTN_WARPS) {
+    const int e = row_env[r], row0 = row_start[e], n = row_start[e + 1] - row0;
+    float4 q[4];
+    upd_load_row(qkv + (size_t)r * 1536, lane, q);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { q[c].x *= 0.125f; q[c].y *= 0.125f; q[c].z *= 0.125f; q[c].w *= 0.125f; }
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int j = 0; j < n; ++j) {
+      float4 k[4];
+      upd_load_row(qkv + (size_t)(row0 + j) * 1536 + 512, lane, k);
+      float s[4];
+      upd_dot_heads(q, k, s);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) m[c] = fmaxf(m[c], s[c]);
+      if ((lane & 15) == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) my[j][half * 4 + c] = s[c];
+      }
+    }
+    __syncwarp();
+    float4 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < n; ++j) {
+      float4 v[4];
+      upd_load_row(qkv + (size_t)(row0 + j) * 1536 + 1024, lane, v);
+      float p[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { p[c] = expf(my[j][half * 4 + c] - m[c]); l[c] += p[c]; }
+      upd_axpy(acc, p, v);
+    }
+    float4* o = reinterpret_cast<float4*>(out + (size_t)r * 512) + lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float inv = 1.0f / l[c];
+      o[32 * c] = make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
+    }
+    if ((lane & 15) == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                    // head = 2 c + half
+        stats[(size_t)r * 16 + 2 * c + half] = m[c];
+        stats[(size_t)r * 16 + 8 + 2 * c + half] = l[c];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// backward, pass A (per query row i): delta_i = <dO_i, O_i> per head, dQ_i = (1/8) sum_j dS_ij K_j with
+// dS_ij = P_ij (dO_i . V_j - delta_i).  Writes dqkv[:, 0:512] and delta [Mc, 8].
+__global__ void __launch_bounds__(CN_UPD_ATTN_WARPS * 32) cn_upd_attn_bwd_q_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ out, const float* __restrict__ dout, const float* __restrict__ stats,
+    const int* __restrict__ row_start, const int* __restrict__ row_env, int Mc, float* __restrict__ dqkv,
+    float* __restrict__ delta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4;
+  for (int r = blockIdx.x * CN_UPD_ATTN_WARPS + warp; r < Mc; r += gridDim.x * CN_UPD_ATTN_WARPS) {
+    const int e = row_env[r], row0 = row_start[e], n = row_start[e + 1] - row0;
+    float4 q[4], dO[4], O[4];
+    upd_load_row(qkv + (size_t)r * 1536, lane, q);
+    upd_load_row(dout + (size_t)r * 512, lane, dO);
+    upd_load_row(out + (size_t)r * 512, lane, O);
+    float dl[4], m[4], linv[4];
+    upd_dot_heads(dO, O, dl);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      q[c].x *= 0.125f; q[c].y *= 0.125f; q[c].z *= 0.125f; q[c].w *= 0.125f;
+      m[c] = stats[(size_t)r * 16 + 2 * c + half];
+      linv[c] = 1.0f / stats[(size_t)r * 16 + 8 + 2 * c + half];
+    }
+    if ((lane & 15) == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) delta[(size_t)r * 8 + 2 * c + half] = dl[c];
+    }
+    float4 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+      float4 k[4], v[4];
+      upd_load_row(qkv + (size_t)(row0 + j) * 1536 + 512, lane, k);
+      upd_load_row(qkv + (size_t)(row0 + j) * 1536 + 1024, lane, v);
+      float s[4], dp[4], ds[4];
+      upd_dot_heads(q, k, s);
+      upd_dot_heads(dO, v, dp);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ds[c] = expf(s[c] - m[c]) * linv[c] * (dp[c] - dl[c]) * 0.125f;
+      upd_axpy(acc, ds, k);
+    }
+    float4* o = reinterpret_cast<float4*>(dqkv + (size_t)r * 1536) + lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[32 * c] = acc[c];
+  }
+}
+
+// backward, pass B (per key row j): dV_j = sum_i P_ij dO_i, dK_j = (1/8) sum_i dS_ij Q_i.  Writes dqkv[:, 512:1536].
+__global__ void __launch_bounds__(CN_UPD_ATTN_WARPS * 32) cn_upd_attn_bwd_kv_kernel(
+    const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ stats, const float* __restrict__ delta,
+    const int* __restrict__ row_start, const int* __restrict__ row_env, int Mc, float* __restrict__ dqkv) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4;
+  for (int r = blockIdx.x * CN_UPD_ATTN_WARPS + warp; r < Mc; r += gridDim.x * CN_UPD_ATTN_WARPS) {
+    const int e = row_env[r], row0 = row_start[e], n = row_start[e + 1] - row0;
+    float4 k[4], v[4];
+    upd_load_row(qkv + (size_t)r * 1536 + 512, lane, k);
+    upd_load_row(qkv + (size_t)r * 1536 + 1024, lane, v);
+    float4 dk[4], dv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { dk[c] = make_float4(0.f, 0.f, 0.f, 0.f); dv[c] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int i = 0; i < n; ++i) {
+      const size_t ri = (size_t)(row0 + i);
+      float4 q[4], dO[4];
+      upd_load_row(qkv + ri * 1536, lane, q);
+      upd_load_row(dout + ri * 512, lane, dO);
+      float s[4], dp[4], p[4], ds[4];
+      upd_dot_heads(q, k, s);
+      upd_dot_heads(dO, v, dp);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float mi = stats[ri * 16 + 2 * c + half], li = stats[ri * 16 + 8 + 2 * c + half];
+        p[c] = expf(s[c] * 0.125f - mi) / li;
+        ds[c] = p[c] * (dp[c] - delta[ri * 8 + 2 * c + half]) * 0.125f;
+      }
+      upd_axpy(dv, p, dO);
+      upd_axpy(dk, ds, q);
+    }
+    float4* ok = reinterpret_cast<float4*>(dqkv + (size_t)r * 1536 + 512) + lane;
+    float4* ov = reinterpret_cast<float4*>(dqkv + (size_t)r * 1536 + 1024) + lane;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { ok[32 * c] = dk[c]; ov[32 * c] = dv[c]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- TMA maps
+// operand map: fp16 [rows, K] with row pitch `pitch`, box 64 (K) x box_rows, SWIZZLE_128B; out-of-range -> zeros
+int op_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch) {
+  EncodeFn enc = get_encode();
+  if (!enc) return cn_set_error("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cn_set_error("cuTensorMapEncodeTiled(operand) failed (%d) rows=%d K=%d pitch=%d", (int)r, rows, K, pitch);
+  return 0;
+}
+// fp32 output map [rows, cols], leading dimension ld: box 32 x 32, SWIZZLE_128B (the epilogue's staging layout)
+int c_map(CUtensorMap* map, float* ptr, int rows, int cols, int ld) {
+  EncodeFn enc = get_encode();
+  if (!enc) return cn_set_error("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cn_set_error("cuTensorMapEncodeTiled(C) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+  return 0;
+}
+
+struct Dev {
+  int sms;
+  bool attrs;
+};
+Dev g_dev[64];
+
+int setup_device(int device) {
+  if (device < 0 || device >= 64) return cn_set_error("cn_update: bad device %d", device);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cn_set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  if (!g_dev[device].attrs) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = cudaFuncSetAttribute(cn_gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(cn_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
+    if (e != cudaSuccess) return cn_set_error("cudaFuncSetAttribute(update gemm): %s", cudaGetErrorString(e));
+    g_dev[device].sms = sms;
+    g_dev[device].attrs = true;
+  }
+  return 0;
+}
+
+// C[Mr, Nc] (+)= act((A_hi + A_lo)[Mr, Kd] (B_hi + B_lo)[Nc, Kd]^T * inv_a * inv_b + bias); Kd multiple of 64 in storage
+// (pitches), logical extents may be smaller (TMA zero-fills).  ksplit > 1: TMA-reduce into a zeroed C.
+int launch_gemm(int device, cudaStream_t st, const __half* ahi, const __half* alo, int a_rows, int a_pitch, const __half* bhi,
+                const __half* blo, int b_rows, int b_pitch, int Kd, float* C, int ldc, const float* bias, int act,
+                const float* inv_a, const float* inv_b, int ksplit) {
+  const int bn = (b_rows % 256 == 0) ? 256 : 64;
+  if (b_rows % bn) return cn_set_error("cn_update gemm: output columns %d not a multiple of 64", b_rows);
+  const int Kp = (int)up((size_t)Kd, TC_BK);
+  CUtensorMap mah, mal, mbh, mbl, mc;
+  int rc = op_map(&mah, ahi, a_rows, Kd, TC_BM, a_pitch);
+  if (!rc) rc = op_map(&mal, alo, a_rows, Kd, TC_BM, a_pitch);
+  if (!rc) rc = op_map(&mbh, bhi, b_rows, Kd, bn, b_pitch);
+  if (!rc) rc = op_map(&mbl, blo, b_rows, Kd, bn, b_pitch);
+  if (!rc) rc = c_map(&mc, C, a_rows, b_rows, ldc);
+  if (rc) return rc;
+  TcEpilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias; ep.inv_scale = 1.0f; ep.act = act; ep.act_lo = 0; ep.act_hi = 1 << 30;
+  ep.c32 = C; ep.ldc = ldc; ep.inv_scale_a = inv_a; ep.inv_scale_b = inv_b; ep.ksplit = ksplit;
+  const int tiles = (b_rows / bn) * ((a_rows + TC_BM - 1) / TC_BM) * (ksplit > 1 ? ksplit : 1);
+  const int grid = tiles < g_dev[device].sms ? tiles : g_dev[device].sms;
+  if (bn == 256)
+    cn_gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(mah, mal, mbh, mbl, mc, mah, mah, a_rows, b_rows, Kp, ep);
+  else
+    cn_gemm_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::kSmemBytes, st>>>(mah, mal, mbh, mbl, mc, mah, mah, a_rows, b_rows, Kp, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update gemm launch (M=%d N=%d K=%d ksplit=%d): %s", a_rows, b_rows, Kd, ksplit, cudaGetErrorString(e));
+  return 0;
+}
+
+int run_amax_scale(cudaStream_t st, const float* x, const float* relu_y, size_t count, unsigned int* amax_bits, float* scale) {
+  cudaMemsetAsync(amax_bits, 0, sizeof(unsigned int), st);
+  const int grid = (int)((count + 256 * 8 - 1) / (256 * 8)) < 1184 ? (int)((count + 256 * 8 - 1) / (256 * 8)) : 1184;
+  cn_upd_amax_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(x, relu_y, count, amax_bits);
+  cn_upd_scale_kernel<<<1, 1, 0, st>>>(amax_bits, scale);
+  return 0;
+}
+
+void run_split(cudaStream_t st, const float* src, int ld, const float* relu_y, int ldy, int M, int C, const float* scale,
+               __half* hi, __half* lo, int Cp, __half* hiT, __half* loT, int Mp, float* colsum) {
+  const long long tiles = (long long)((Mp > M ? Mp : M) + 31) / 32 * (((Cp > C ? Cp : C) + 31) / 32);
+  const int grid = tiles < 148 * 16 ? (int)tiles : 148 * 16;
+  cn_upd_split_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(src, ld, relu_y, ldy, M, C, scale, hi, lo, Cp, hiT, loT, Mp, colsum);
+}
+
+struct Carve {
+  unsigned char* p;
+  size_t off, cap;
+  void* take(size_t bytes) {
+    off = up(off, 1024);
+    void* q = p + off;
+    off += bytes;
+    return q;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// rows of padding the transposed activation copies use
+static inline int mpad(int M) { return (int)up((size_t)M, 64); }
+
+size_t cn_update_linear_saved_bytes(int M, int K) {
+  // X^T as (hi, lo) fp16 [K, Mp] + its scale {s, 1/s} (+ slack for alignment)
+  return up((size_t)2 * K * mpad(M) * sizeof(__half), 1024) + 1024;
+}
+
+size_t cn_update_linear_ws_bytes(int M, int N, int K) {
+  const size_t Mp = mpad(M), Np = up(N, 64), Kp = up(K, 64);
+  size_t fwd = 2 * (size_t)M * Kp * 2 + 2 * (size_t)N * Kp * 2;                                 // X split, W split
+  size_t bwd = 2 * (size_t)M * Np * 2 + 2 * (size_t)N * Mp * 2 + 2 * (size_t)K * Np * 2;        // dZ, dZ^T, W^T splits
+  return (fwd > bwd ? fwd : bwd) + 16 * 1024;
+}
+
+// replaces (inside Policy.evaluate_actions of the PPO update): F.linear + ReLU of one per-human layer.
+// d_saved receives X^T split for the weight gradient of the backward pass.
+int cn_update_linear_fwd(const float* d_x, const float* d_w, const float* d_b, float* d_y, void* d_saved, void* d_ws,
+                         size_t ws_bytes, int M, int N, int K, int act, int device, void* stream) {
+  if (!d_x || !d_w || !d_y || !d_saved || !d_ws) return cn_set_error("cn_update_linear_fwd: null argument");
+  if (M <= 0 || N % 64 || K % 64) return cn_set_error("cn_update_linear_fwd: need M > 0, N %% 64 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  if (ws_bytes < cn_update_linear_ws_bytes(M, N, K)) return cn_set_error("cn_update_linear_fwd: workspace too small");
+  int rc = setup_device(device);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = mpad(M);
+  Carve c{(unsigned char*)d_ws, 0, ws_bytes};
+  unsigned int* amax = (unsigned int*)c.take(64);
+  float* sw = (float*)c.take(64);
+  __half* xh = (__half*)c.take((size_t)M * K * 2);
+  __half* xl = (__half*)c.take((size_t)M * K * 2);
+  __half* wh = (__half*)c.take((size_t)N * K * 2);
+  __half* wl = (__half*)c.take((size_t)N * K * 2);
+  unsigned char* sv = (unsigned char*)d_saved;
+  __half* xTh = (__half*)sv;
+  __half* xTl = xTh + (size_t)K * Mp;
+  float* sx = (float*)(sv + up((size_t)2 * K * Mp * 2, 1024));
+  run_amax_scale(st, d_x, nullptr, (size_t)M * K, amax, sx);
+  run_split(st, d_x, K, nullptr, 0, M, K, sx, xh, xl, K, xTh, xTl, Mp, nullptr);
+  run_amax_scale(st, d_w, nullptr, (size_t)N * K, amax + 1, sw);
+  run_split(st, d_w, K, nullptr, 0, N, K, sw, wh, wl, K, nullptr, nullptr, 0, nullptr);
+  rc = launch_gemm(device, st, xh, xl, M, K, wh, wl, N, K, K, d_y, N, d_b, act, sx + 1, sw + 1, 1);
+  if (rc) return rc;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update_linear_fwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// Backward of the same layer: dZ = dY o [Y > 0] (act == ReLU), dX = dZ W, dW = dZ^T X, db = colsum(dZ).
+// d_dx may be null (first layer of a chain).  d_dw [N, K] and d_db [N] are OVERWRITTEN.
+int cn_update_linear_bwd(const float* d_dy, const float* d_y, const void* d_saved, const float* d_w, float* d_dx, float* d_dw,
+                         float* d_db, void* d_ws, size_t ws_bytes, int M, int N, int K, int act, int device, void* stream) {
+  if (!d_dy || !d_saved || !d_w || !d_dw || !d_ws) return cn_set_error("cn_update_linear_bwd: null argument");
+  if (act == 1 && !d_y) return cn_set_error("cn_update_linear_bwd: ReLU layer needs its forward output");
+  if (act != 0 && act != 1) return cn_set_error("cn_update_linear_bwd: activation %d unsupported (0 none, 1 ReLU)", act);
+  if (M <= 0 || N % 64 || K % 64) return cn_set_error("cn_update_linear_bwd: need M > 0, N %% 64 == 0, K %% 64 == 0");
+  if (ws_bytes < cn_update_linear_ws_bytes(M, N, K)) return cn_set_error("cn_update_linear_bwd: workspace too small");
+  int rc = setup_device(device);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Mp = mpad(M);
+  Carve c{(unsigned char*)d_ws, 0, ws_bytes};
+  unsigned int* amax = (unsigned int*)c.take(64);
+  float* sdz = (float*)c.take(64);
+  float* sw = (float*)c.take(64);
+  __half* zh = (__half*)c.take((size_t)M * N * 2);
+  __half* zl = (__half*)c.take((size_t)M * N * 2);
+  __half* zTh = (__half*)c.take((size_t)N * Mp * 2);
+  __half* zTl = (__half*)c.take((size_t)N * Mp * 2);
+  __half* wTh = (__half*)c.take((size_t)K * N * 2);
+  __half* wTl = (__half*)c.take((size_t)K * N * 2);
+  const unsigned char* sv = (const unsigned char*)d_saved;
+  const __half* xTh = (const __half*)sv;
+  const __half* xTl = xTh + (size_t)K * Mp;
+  const float* sx = (const float*)(sv + up((size_t)2 * K * Mp * 2, 1024));
+  const float* mask = act == 1 ? d_y : nullptr;
+  run_amax_scale(st, d_dy, mask, (size_t)M * N, amax, sdz);
+  if (d_db) cudaMemsetAsync(d_db, 0, (size_t)N * sizeof(float), st);
+  run_split(st, d_dy, N, mask, N, M, N, sdz, d_dx ? zh : nullptr, d_dx ? zl : nullptr, N, zTh, zTl, Mp, d_db);
+  if (d_dx) {
+    run_amax_scale(st, d_w, nullptr, (size_t)N * K, amax + 1, sw);
+    run_split(st, d_w, K, nullptr, 0, N, K, sw, nullptr, nullptr, 0, wTh, wTl, N, nullptr);     // W^T [K, N]
+    rc = launch_gemm(device, st, zh, zl, M, N, wTh, wTl, K, N, N, d_dx, K, nullptr, 0, sdz + 1, sw + 1, 1);
+    if (rc) return rc;
+  }
+  // wgrad: dW[N, K] = dZ^T[N, Mp] . X^T[K, Mp]^T, reduction over the rows, split across CTAs
+  cudaMemsetAsync(d_dw, 0, (size_t)N * K * sizeof(float), st);
+  {
+    const int bn = (K % 256 == 0) ? 256 : 64;
+    const int mn = ((N + TC_BM - 1) / TC_BM) * (K / bn);
+    const int kblocks = Mp / TC_BK;
+    int ksplit = (g_dev[device].sms + mn - 1) / mn;
+    if (ksplit > kblocks) ksplit = kblocks;
+    if (ksplit < 1) ksplit = 1;
+    // every slice must own at least one k-block (an empty slice would add an uninitialised accumulator):
+    // ksplit = ceil(kblocks / ceil(kblocks / ksplit)) has that property; C is zeroed above for the reduce path
+    const int kb_per = (kblocks + ksplit - 1) / ksplit;
+    ksplit = (kblocks + kb_per - 1) / kb_per;
+    rc = launch_gemm(device, st, zTh, zTl, N, Mp, xTh, xTl, K, Mp, M, d_dw, K, nullptr, 0, sdz + 1, sx + 1, ksplit);
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update_linear_bwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// replaces (update path): the nn.MultiheadAttention core over the valid humans of every sample.
+// d_qkv [Mc,1536]; d_row_start [B+1] (prefix sums of the per-sample human counts), d_row_env [Mc] (sample of a row);
+// outputs d_out [Mc,512], d_stats [Mc,16] (soft-max max / sum per head, consumed by the backward).
+int cn_update_attn_fwd(const float* d_qkv, const int* d_row_start, const int* d_row_env, int Mc, float* d_out, float* d_stats,
+                       int device, void* stream) {
+  if (!d_qkv || !d_row_start || !d_row_env || !d_out || !d_stats) return cn_set_error("cn_update_attn_fwd: null argument");
+  if (Mc <= 0) return 0;
+  int rc = setup_device(device);
+  if (rc) return rc;
+  int grid = (Mc + CN_UPD_ATTN_WARPS - 1) / CN_UPD_ATTN_WARPS;
+  if (grid > g_dev[device].sms * 16) grid = g_dev[device].sms * 16;
+  cn_upd_attn_fwd_kernel<<<grid, CN_UPD_ATTN_WARPS * 32, 0, (cudaStream_t)stream>>>(d_qkv, d_row_start, d_row_env, Mc, d_out, d_stats);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update_attn_fwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// d_dqkv [Mc,1536] = gradient w.r.t. (q | k | v) given d_dout [Mc,512]; d_delta [Mc,8] is scratch.
+int cn_update_attn_bwd(const float* d_qkv, const float* d_out, const float* d_dout, const float* d_stats, const int* d_row_start,
+                       const int* d_row_env, int Mc, float* d_dqkv, float* d_delta, int device, void* stream) {
+  if (!d_qkv || !d_out || !d_dout || !d_stats || !d_row_start || !d_row_env || !d_dqkv || !d_delta)
+    return cn_set_error("cn_update_attn_bwd: null argument");
+  if (Mc <= 0) return 0;
+  int rc = setup_device(device);
+  if (rc) return rc;
+  int grid = (Mc + CN_UPD_ATTN_WARPS - 1) / CN_UPD_ATTN_WARPS;
+  if (grid > g_dev[device].sms * 16) grid = g_dev[device].sms * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  cn_upd_attn_bwd_q_kernel<<<grid, CN_UPD_ATTN_WARPS * 32, 0, st>>>(d_qkv, d_out, d_dout, d_stats, d_row_start, d_row_env, Mc, d_dqkv, d_delta);
+  cn_upd_attn_bwd_kv_kernel<<<grid, CN_UPD_ATTN_WARPS * 32, 0, st>>>(d_qkv, d_dout, d_stats, d_delta, d_row_start, d_row_env, Mc, d_dqkv);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update_attn_bwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

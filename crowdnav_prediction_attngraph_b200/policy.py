@@ -281,7 +281,15 @@ class Policy(nn.Module):
             # (masked_fill(-1e9)), so they contribute neither to the outputs nor to any gradient.  The per-row
             # layers (98 % of the FLOPs) run on the valid rows only; the tiny H x H attention runs padded.
             sp_p = sp[valid]                                             # [Mc, W]
-            e = sa.embedding_layer(sp_p)
+            # update kernels: the three 128/512-wide per-row layers forward + backward on the tcgen05
+            # 3xFP16 GEMM and the attention core over compacted rows; plain torch ops on CPU or with CN_UPDATE_KERNELS=0
+            use_tc = sp.is_cuda and getattr(self, "update_kernels", os.environ.get("CN_UPDATE_KERNELS", "1") == "1")
+            if use_tc:
+                from . import update_ops as uo
+                e1 = torch.relu(F.linear(sp_p, sa.embedding_layer[0].weight, sa.embedding_layer[0].bias))   # K = 12: torch
+                e = uo.linear_tc(e1, sa.embedding_layer[2].weight, sa.embedding_layer[2].bias, 1)
+            else:
+                e = sa.embedding_layer(sp_p)
 
             def pad(x):
                 out = x.new_zeros(B, H, x.shape[-1])
@@ -296,14 +304,22 @@ class Policy(nn.Module):
             win = mha.in_proj_weight.reshape(3, 512, 512)
             w_qkv = torch.bmm(win, wl).reshape(1536, 512)
             b_qkv = (torch.bmm(win, bl.unsqueeze(-1)).squeeze(-1) + mha.in_proj_bias.reshape(3, 512)).reshape(1536)
-            qkv = F.linear(e, w_qkv, b_qkv)
-            q, k, v = [heads(pad(t)) for t in qkv.chunk(3, -1)]
-            o = _hh_attention(q, k, v, valid)
-            o = o.transpose(1, 2).reshape(B, H, 512)[valid]
             sl = b.spatial_linear[0]
             w_os = sl.weight @ mha.out_proj.weight
             b_os = sl.weight @ mha.out_proj.bias + sl.bias
-            hs = pad(torch.relu(F.linear(o, w_os, b_os)))
+            if use_tc:
+                qkv = uo.linear_tc(e, w_qkv, b_qkv, 0)
+                row_start = torch.zeros(B + 1, dtype=torch.int32, device=sp.device)
+                row_start[1:] = torch.cumsum(n, 0)
+                row_env = torch.repeat_interleave(torch.arange(B, device=sp.device, dtype=torch.int32), n)
+                o = uo.hh_attention_rows(qkv, row_start, row_env)
+                hs = pad(uo.linear_tc(o, w_os, b_os, 1))
+            else:
+                qkv = F.linear(e, w_qkv, b_qkv)
+                q, k, v = [heads(pad(t)) for t in qkv.chunk(3, -1)]
+                o = _hh_attention(q, k, v, valid)
+                o = o.transpose(1, 2).reshape(B, H, 512)[valid]
+                hs = pad(torch.relu(F.linear(o, w_os, b_os)))
         else:
             e = sa.embedding_layer(sp)
             q = heads(F.linear(sa.q_linear(e), wq, bq))

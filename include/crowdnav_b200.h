@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CN_ABI_VERSION 2
+#define CN_ABI_VERSION 3
 
 /* info codes — crowd_sim/envs/utils/info.py (Nothing, Timeout, Collision, ReachGoal, Danger) */
 #define CN_INFO_NOTHING_C 0
@@ -193,6 +193,33 @@ int cn_policy_profile(cn_policy *pol, int enable);
 int cn_policy_stage_count(void);
 const char *cn_policy_stage_name(int i);
 int cn_policy_stage_ms(cn_policy *pol, float *out, int n);
+
+/* ------------------------------------------------------------------------------------------ */
+/* PPO update path (rl/ppo/ppo.py:36-101 -> Policy.evaluate_actions, selfAttn_srnn_temp_node.py:63-91): the
+ * per-human linear layers forward / backward on the tcgen05 3xFP16 GEMM in fp32-equivalent accuracy.
+ * Stateless: every buffer (outputs, `d_saved` = what the backward needs from the forward, workspace) is caller-owned
+ * device memory; sizes from the *_bytes functions.  Dimensions: N and K multiples of 64, M arbitrary.
+ * act: 0 none, 1 ReLU.  replaces: torch F.linear(+ReLU) and its autograd backward for these layers.            */
+size_t cn_update_linear_saved_bytes(int M, int K);
+size_t cn_update_linear_ws_bytes(int M, int N, int K);
+/* Y[M,N] = act(X[M,K] W[N,K]^T + b[N])                                                                         */
+int cn_update_linear_fwd(const float *d_x, const float *d_w, const float *d_b, float *d_y, void *d_saved, void *d_ws,
+                         size_t ws_bytes, int M, int N, int K, int act, int device, void *stream);
+/* dZ = dY o [Y > 0] (ReLU); dX[M,K] = dZ W (d_dx may be NULL); dW[N,K] = dZ^T X; db[N] = colsum(dZ) (may be NULL) */
+int cn_update_linear_bwd(const float *d_dy, const float *d_y, const void *d_saved, const float *d_w, float *d_dx,
+                         float *d_dw, float *d_db, void *d_ws, size_t ws_bytes, int M, int N, int K, int act, int device,
+                         void *stream);
+
+/* Human-human multi-head attention core (softmax(q k^T / 8) v, 8 heads x 64) over COMPACTED rows: only the valid
+ * humans of every sample have rows.  d_qkv [Mc,1536] = (q | k | v); d_row_start [B+1] prefix sums of the per-sample
+ * human counts; d_row_env [Mc] sample index of a row; d_stats [Mc,16] soft-max max / sum per head (forward -> backward);
+ * d_delta [Mc,8] scratch.  replaces: nn.MultiheadAttention's attention product with key_padding_mask
+ * (rl/networks/selfAttn_srnn_temp_node.py:83-87) and its autograd backward.                                      */
+int cn_update_attn_fwd(const float *d_qkv, const int *d_row_start, const int *d_row_env, int Mc, float *d_out,
+                       float *d_stats, int device, void *stream);
+int cn_update_attn_bwd(const float *d_qkv, const float *d_out, const float *d_dout, const float *d_stats,
+                       const int *d_row_start, const int *d_row_env, int Mc, float *d_dqkv, float *d_delta, int device,
+                       void *stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cn_abi_version() == 2
+    assert lib.cn_abi_version() == 3
 
 
 def test_struct_layout_matches_header():
