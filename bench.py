@@ -133,7 +133,25 @@ def reference_rollout_rate(steps, warmup, num_processes=None, humans=HUMANS):
     sys.path[:0] = [os.path.join(REPO, "oracle", "shims"), root]
     cores = len(os.sched_getaffinity(0)) or (os.cpu_count() or 1)
     n = num_processes or cores
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # The fork workers must be single-threaded: they inherit the parent's OpenMP / BLAS pools, and on a 128-core box
+    # 128 workers x 128 spinning threads each never finish a step (the first version of this arm timed out after 600 s
+    # there).  So the pools are limited to 1 thread BEFORE the workers are forked and only the parent's torch pool is
+    # widened afterwards (the policy forward and the env steps alternate, they never compete for the cores).
+    pol_threads = min(cores, 32)
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    verbose = os.environ.get("CN_BENCH_VERBOSE", "0") == "1"
+    t_start = time.perf_counter()
+
+    def note(msg):
+        if verbose:
+            sys.stderr.write("[reference arm %.1fs] %s\n" % (time.perf_counter() - t_start, msg))
+            sys.stderr.flush()
     argv, sys.argv = sys.argv, ["x", "--no-cuda", "--env-name", "CrowdSimPred-v0", "--num-processes", str(n)]
     cwd = os.getcwd()
     os.chdir(root)
@@ -141,6 +159,7 @@ def reference_rollout_rate(steps, warmup, num_processes=None, humans=HUMANS):
         import numpy as np
         import torch
         import rvo2
+        torch.set_num_threads(1)
         rvo2.ONLY_AGENT0 = False                     # the reference's full doStep (H agents per cached simulator)
         from arguments import get_args
         from crowd_nav.configs.config import Config
@@ -157,10 +176,12 @@ def reference_rollout_rate(steps, warmup, num_processes=None, humans=HUMANS):
         with contextlib.redirect_stdout(io.StringIO()):          # make_env prints one Monitor repr per environment
             envs = make_vec_envs("CrowdSimPred-v0", 425, n, args.gamma, None, torch.device("cpu"), False, config=config,
                                  pretext_wrapper=False)
+        note("make_vec_envs done (%d workers)" % n)
         torch.manual_seed(425)
-        torch.set_num_threads(cores)
+        torch.set_num_threads(pol_threads)
         pol = Policy(envs.observation_space.spaces, envs.action_space, base_kwargs=args, base='selfAttn_merge_srnn')
         obs = envs.reset()
+        note("reset done")
         hx = {'human_node_rnn': torch.zeros(n, 1, 128), 'human_human_edge_rnn': torch.zeros(n, humans + 1, 256)}
         masks = torch.ones(n, 1)
         t_env, t_pol = [], []
@@ -175,12 +196,14 @@ def reference_rollout_rate(steps, warmup, num_processes=None, humans=HUMANS):
             if s >= warmup:
                 t_pol.append(t1 - t0)
                 t_env.append(t2 - t1)
+            if s < 3 or s % 50 == 0:
+                note("step %d: policy %.1f ms, env %.1f ms" % (s, 1e3 * (t1 - t0), 1e3 * (t2 - t1)))
         envs.close()
     finally:
         os.chdir(cwd)
         sys.argv = argv
     tot = sum(t_env) + sum(t_pol)
-    return dict(rate=n * steps / tot, workers=n, cores=cores, steps=steps,
+    return dict(rate=n * steps / tot, workers=n, cores=cores, steps=steps, pol_threads=pol_threads,
                 env_ms_median=1e3 * float(np.median(t_env)), env_ms_max=1e3 * float(np.max(t_env)),
                 policy_ms_median=1e3 * float(np.median(t_pol)), policy_ms_max=1e3 * float(np.max(t_pol)),
                 env_only_rate=n * steps / sum(t_env), root=os.path.relpath(root, REPO) if root.startswith(REPO) else root)
@@ -197,7 +220,7 @@ def cpu_arm(steps, warmup, seconds=None):
                   "the reference's design), reference Policy.act on CPU (%d torch threads), CrowdSimPred-v0 const_vel H=%d, "
                   "%d rollout steps after %d warm-up; per step: env %.1f ms median / %.1f ms max, policy %.1f ms median / "
                   "%.1f ms max; env-only %.0f env-steps/s; behind oracle/shims (gym, baselines, rvo2 = oracle/rvo2_ref.cpp)"
-                  % (r["root"], r["workers"], r["cores"], HUMANS, r["steps"], warmup, r["env_ms_median"], r["env_ms_max"],
+                  % (r["root"], r["workers"], r["pol_threads"], HUMANS, r["steps"], warmup, r["env_ms_median"], r["env_ms_max"],
                      r["policy_ms_median"], r["policy_ms_max"], r["env_only_rate"]))
         return r["rate"], {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": sample,
                            "workers": r["workers"], "detail": {k: r[k] for k in (

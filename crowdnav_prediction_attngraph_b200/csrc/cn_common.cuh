@@ -23,7 +23,10 @@ enum { CN_INFO_NOTHING = 0, CN_INFO_TIMEOUT = 1, CN_INFO_COLLISION = 2, CN_INFO_
 // Device-side mirror of cn_config (include/crowdnav_b200.h) with derived constants.
 struct CnParams {
   int N;            // environments in this shard
-  int H;            // humans per environment (sim.human_num, human_num_range == 0)
+  int H;            // human SLOTS per environment = sim.human_num + sim.human_num_range (max_human_num); the live
+                    // count of an environment is CnState::hn[e] (== H when hrange == 0)
+  int hrange;       // sim.human_num_range: humans join / leave every 5 s (crowd_sim_pred.py:165-194)
+  int hbase;        // sim.human_num
   int P;            // sim.predict_steps
   int W;            // spatial_edges row width: 2*(P+1) (CrowdSimPred) or 2 (CrowdSimVarNum)
   int const_vel;    // 1: CrowdSimPred-v0 'const_vel'; 0: CrowdSimVarNum-v0 'none'
@@ -61,6 +64,8 @@ struct CnState {
   double *ep_ret;                    // bench.Monitor episode return
   int *ep_len;
   int *step_count;                   // global_time = step_count * time_step
+  int *hn;                           // [N] live humans (slots [hn, H) are empty), constant H unless hrange > 0
+  int *prep_hn;                      // [N] live humans of the prepared next episode
   uint32_t *case_counter;            // case_counter[phase]
   int32_t *seed_off;                 // thisSeed - seed_base of every environment (default: its index; a batched
                                      // evaluation replays the single-env test protocol with all zeros)
@@ -72,6 +77,7 @@ struct CnState {
   uint8_t *vis;                      // human_visibility (to the robot)
   // per-human cached rvo2 simulator parameters (crowd_nav/policy/orca.py:79-95): frozen at creation
   uint8_t *sim_exists;               // [N][H]
+  uint8_t *sim_n;                    // [N][H] live human count when the simulator was created (human_num_range > 0)
   float *sim_nd, *sim_rself, *sim_vmax;   // [N][H]
   float *sim_rother;                 // [N][H][H] (only when randomize)
   // legacy numpy MT19937 per environment

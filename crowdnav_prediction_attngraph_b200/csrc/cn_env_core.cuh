@@ -73,6 +73,7 @@ struct CnEnvSh {
   double reward;
   int done, info, reset_flag;
   int nvis;
+  int hn;                // live humans of this environment (slots [hn, H) are empty; == H unless sim.human_num_range > 0)
   int goal_flag;         // some human is within its radius of its goal (respawn pending)
   int lp3_cost;          // humans of this environment whose solve fell through to linearProgram3 (balancing)
   int lean;              // step kernel: gx / gy / rad / vpref point straight into HBM (read-only there)
@@ -112,6 +113,7 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
     s.rpx = g.rpx[e]; s.rpy = g.rpy[e]; s.rgx = g.rgx[e]; s.rgy = g.rgy[e];
     s.rvx = g.rvx[e]; s.rvy = g.rvy[e];
     s.done = 0; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0; s.lp3_cost = 0;
+    s.hn = g.hn[e];
     if (action) {
       float ax = action[2 * e], ay = action[2 * e + 1];
       const float nrm = sqrtf(ax * ax + ay * ay);          // np.linalg.norm(float32[2])
@@ -128,18 +130,21 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
 template <int MAXH>
 CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnLineStore lines, int& nl_out,
                          float& vmax_out, CnF2& pref_out, bool use_fov = true) {
-  const int H = p.H;
+  const int H = p.H;            // slots (row pitch of the [N][H] arrays)
+  const int hn = s.hn;          // live humans: the simulator of human h holds the other hn - 1 (orca.py:80-95)
   const size_t i = cn_idx(p, e, h);
   const double fov = p.human_fov;
   float nd, rself, vmax;
   const double pad = 0.01;
   // --- cached simulator parameters (frozen at creation; orca.py:80-95 only updates pos/vel)
   if (p.randomize) {
-    if (!g.sim_exists[i]) {
+    // (re)created when missing or when humans joined / left since its creation (orca.py:80-82: agent count mismatch)
+    if (!g.sim_exists[i] || (p.hrange > 0 && g.sim_n[i] != (uint8_t)hn)) {
+      g.sim_n[i] = (uint8_t)hn;
       g.sim_nd[i] = (float)g.nd_global[e];
       g.sim_rself[i] = (float)(s.rad[h] + pad + p.orca_safety_space);
       g.sim_vmax[i] = (float)s.vpref[h];
-      for (int j = 0; j < H; ++j) {
+      for (int j = 0; j < hn; ++j) {
         if (j == h) continue;
         const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
         g.sim_rother[i * H + j] = (float)((v ? s.rad[j] : 0.3) + pad + p.orca_safety_space);
@@ -172,7 +177,7 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   float vd[MAXH];
   uint8_t vj[MAXH];          // bit 7 = dummy (invisible) neighbour, bits 0..6 = human index
   int nl = 0;
-  for (int j = 0; j < H; ++j) {
+  for (int j = 0; j < hn; ++j) {
     if (j == h) continue;
     // use_fov = false: act_joint_state of the ground-truth look-ahead passes every other human as is
     const bool v = !use_fov || cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
@@ -236,7 +241,7 @@ CN_HD void cn_orca_finish(const CnParams& p, const CnState& g, CnEnvSh& s, int e
 // ------------------------------------------------------------------------------------------
 // Phase REWARD (leader): calc_reward + robot integration + time.
 CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int e, const CnStepOut& out) {
-  const int H = p.H;
+  const int H = s.hn;           // live humans
   double dmin = INFINITY;
   bool collision = false;
   for (int i = 0; i < H; ++i) {
@@ -478,7 +483,9 @@ CN_HD bool cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   }
   cn_coop_sync(co);
   double nd = g.nd_global[e];
-  for (int i = 0; i < H; ++i) {
+  // human_num = randint(human_num - range, human_num + range + 1) (crowd_sim_var_num.py:103-104; no draw when range == 0)
+  const int hn = p.hrange > 0 ? cn_rng_randint(rng, co, p.hbase - p.hrange, p.hbase + p.hrange + 1) : H;
+  for (int i = 0; i < hn; ++i) {
     const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, i, nd, g.spawn_overflow + e);
     if (rng.deferred) return true;
     if (co.lane == 0) {
@@ -488,12 +495,15 @@ CN_HD bool cn_prepare_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   }
   for (int i = co.lane; i < H; i += co.nlanes) {
     const size_t gi = cn_idx(p, e, i);
-    g.prep_hpx[gi] = s.px[i]; g.prep_hpy[gi] = s.py[i]; g.prep_hrad[gi] = s.rad[i]; g.prep_hvpref[gi] = s.vpref[i];
+    const bool live = i < hn;       // empty slots: zeros
+    g.prep_hpx[gi] = live ? s.px[i] : 0.0; g.prep_hpy[gi] = live ? s.py[i] : 0.0;
+    g.prep_hrad[gi] = live ? s.rad[i] : 0.0; g.prep_hvpref[gi] = live ? s.vpref[i] : 0.0;
   }
   if (co.lane == 0) {
     double* r = g.prep_robot + (size_t)e * 4;
     r[0] = s.rpx; r[1] = s.rpy; r[2] = s.rgx; r[3] = s.rgy;
     g.prep_nd[e] = nd;
+    g.prep_hn[e] = hn;
     g.prep_mt_pos[e] = rng.pos;
   }
   cn_coop_sync(co);
@@ -523,7 +533,58 @@ CN_HD void cn_install_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
     g.mt_pos[e] = g.prep_mt_pos[e];
     if (p.randomize) g.nd_global[e] = g.prep_nd[e];
     s.reset_flag = 1; s.nvis = 0; s.goal_flag = 0;
+    s.hn = g.prep_hn[e]; g.hn[e] = s.hn;
   }
+}
+
+// Humans join / leave every 5 s of simulation (sim.human_num_range > 0): CrowdSimPred.step (crowd_sim_pred.py:165-194)
+// and CrowdSimVarNum.step (crowd_sim_var_num.py:404-437), AFTER the agents moved and BEFORE the observation.
+// Single thread (the environment's leader), generator state used in place (`key` = g.mt row of the environment):
+// it runs once per 20 steps and environment, so it is not worth a cooperative version.  The LAST humans leave
+// (never one the robot currently observes: CrowdSimVarNum only -- CrowdSimPred never refreshes observed_human_ids),
+// joining humans spawn on the circle like at reset and are unknown to the robot (belief (15, 15, 0, 0, 0.3)).
+CN_HD void cn_phase_add_remove(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
+  const CnCoop co = {0, 1, nullptr};
+  CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = g.mt_pos[e]; rng.budget = 0; rng.deferred = 0;
+  const int hn = s.hn, hmin = p.hbase - p.hrange;
+  int hnew = hn;
+  if (cn_rng_double(rng, co) < 0.5) {
+    int max_seen = -1;
+    if (!p.const_vel)
+      for (int k = 0; k < hn; ++k) if (g.vis[cn_idx(p, e, k)]) max_seen = k;
+    int remove_num;
+    if (p.const_vel) {
+      const int max_remove = max_seen < 0 ? hn - 1 : (hn - 1) - max_seen;
+      remove_num = cn_rng_randint(rng, co, 0, (p.hrange < max_remove ? p.hrange : max_remove) + 1);
+    } else {
+      int max_remove = hn - hmin;
+      if (max_seen >= 0 && (hn - 1) - max_seen < max_remove) max_remove = (hn - 1) - max_seen;
+      remove_num = cn_rng_randint(rng, co, 0, max_remove + 1);
+    }
+    hnew = hn - remove_num;
+  } else {
+    const int add_num = cn_rng_randint(rng, co, 0, p.hrange + 1);
+    double nd = g.nd_global[e];
+    for (int i = hn; i < hn + add_num && i < p.H; ++i) {
+      s.hn = i;                                   // the spawn checks the robot and humans [0, i)
+      const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, i, nd, g.spawn_overflow + e);
+      s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
+      s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.fx[i] = (float)sp.px; s.fy[i] = (float)sp.py;
+      const size_t gi = cn_idx(p, e, i);
+      g.bpx[gi] = 15.; g.bpy[gi] = 15.; g.bvx[gi] = 0.; g.bvy[gi] = 0.; g.brad[gi] = 0.3;
+      g.vis[gi] = 0; g.sim_exists[gi] = 0;
+      hnew = i + 1;
+    }
+    if (p.randomize) g.nd_global[e] = nd;
+  }
+  // departed humans take their simulators with them; the survivors' simulators are rebuilt lazily at their next solve
+  // (agent-count mismatch, cn_orca_build), exactly when the reference does it
+  for (int k = hnew; k < hn; ++k) g.sim_exists[cn_idx(p, e, k)] = 0;
+  s.hn = hnew; g.hn[e] = hnew;
+  g.mt_pos[e] = rng.pos;
+}
+CN_HD bool cn_add_remove_due(const CnParams& p, const CnState& g, const CnEnvSh& s, int e) {
+  return p.hrange > 0 && !s.done && fmod(g.step_count[e] * p.time_step, 5.0) == 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -532,6 +593,10 @@ CN_HD void cn_install_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
 template <int MAXW>
 CN_HD void cn_phase_obs_a(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, float* row) {
   const size_t i = cn_idx(p, e, h);
+  if (h >= s.hn) {           // empty slot: an all-inf row of the reference's max_human_num storage (sorts last, reads 15)
+    s.visr[h] = 0; g.vis[i] = 0; s.t0[h] = INFINITY; s.t1[h] = 0.0;
+    return;
+  }
   const double dist = cn_norm_dot(s.rpx - s.px[h], s.rpy - s.py[h]) - p.robot_radius - s.rad[h];
   const bool in_fov = cn_in_fov(s.rpx, s.rpy, s.rvx, s.rvy, s.px[h], s.py[h], p.robot_fov);
   const bool vis = in_fov && (dist <= p.sensor_range);
@@ -622,7 +687,7 @@ CN_HD void cn_phase_obs_c(const CnParams& p, CnEnvSh& s, int e, int h, const CnO
 // Returns true when a search exhausted `budget` tries (see cn_prepare_env): the caller must NOT store the working set.
 CN_HD bool cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e, uint32_t* key, const CnCoop& co,
                           int budget = 0) {
-  const int H = p.H;
+  const int H = s.hn;           // live humans
   CnRng rng; rng.key = key; rng.pos = g.mt_pos[e]; rng.budget = budget; rng.deferred = 0;
   double nd = g.nd_global[e];
   const int step = g.step_count[e];

@@ -99,14 +99,16 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   unsigned char* lp3_q = reinterpret_cast<unsigned char*>(lines_smem + (size_t)line_cap * blockDim.x +
                                                           (size_t)(blockDim.x >> 5) * MAXH);
   if (threadIdx.x == 0) { reinterpret_cast<int*>(lp3_q)[0] = 0; reinterpret_cast<int*>(lp3_q)[1] = 0; }
-  const CnCoop co = {lane, 32};
+  const CnCoop co = {lane, 32, nullptr};
 
   if (mode == 1) {
-    if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; s->lp3_cost = 0; }
+    if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; s->lp3_cost = 0; s->hn = 0; }
   } else if (active) {
     cn_phase_load(p, g, *s, e, h, action);
   }
   __syncthreads();
+  // live = this thread's slot holds a human (slots [hn, H) are empty when sim.human_num_range > 0)
+  const bool live = active && h < s->hn;
   // One ORCA solve of every human of the CTA on the joint state currently in shared memory (CTA-uniform
   // call: contains barriers).  linearProgram3 (needed by ~30 % of the humans in steady state) is
   // balanced across the whole CTA: failed humans are queued in shared memory and every warp pops tasks
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
     float vmax = 0.0f;
     CnF2 pref = f2(0.0f, 0.0f);
     result = f2(0.0f, 0.0f);
-    if (active) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref, use_fov);
+    if (live) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref, use_fov);
     __syncwarp();
     cn_orca_lp2_warp(co, W, nl, vmax, pref, result, fail);            // all 32 lanes, idle ones with nl = 0
     if (fail >= 0) {
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   if (mode != 1) {
     CnF2 result; int nl, fail;
     orca_solve(true, result, nl, fail);                               // get_human_actions (crowd_sim.py:680-703)
-    if (active && fail >= 0) atomicAdd(&s->lp3_cost, 1);              // cost estimate for the next step's balancing
+    if (live && fail >= 0) atomicAdd(&s->lp3_cost, 1);              // cost estimate for the next step's balancing
     if (p.test_phase) {
       // phase 'test': ground-truth look-ahead (crowd_sim_pred.py:136-138 -> crowd_sim_var_num.py:180-206):
       // lookahead_steps nested solves on a scratch copy of the joint state kept in the same shared arrays
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
       double spx = 0, spy = 0, lx = 0, ly = 0;
       float svx = 0, svy = 0, lvx = 0, lvy = 0;
       bool vis_prev = false;
-      if (active) {
+      if (live) {
         spx = s->px[h]; spy = s->py[h]; svx = s->vx[h]; svy = s->vy[h];
         lx = spx; ly = spy; lvx = svx; lvy = svy;
         vis_prev = g.vis[cn_idx(p, e, h)] != 0;
@@ -171,26 +173,26 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
       CnF2 lres = f2(0.0f, 0.0f); int lnl = 0, lfail = -1;
       for (int t = 1; t <= p.lookahead_steps; ++t) {
         __syncthreads();
-        if (active) {
+        if (live) {
           s->px[h] = lx; s->py[h] = ly; s->fx[h] = (float)lx; s->fy[h] = (float)ly; s->vx[h] = lvx; s->vy[h] = lvy;
         }
         __syncthreads();
         orca_solve(false, lres, lnl, lfail);
         lx = lx + (double)lres.x * p.time_step; ly = ly + (double)lres.y * p.time_step;
         lvx = lres.x; lvy = lres.y;
-        if (active && t % p.pred_interval == 0) cn_lookahead_accumulate(p, *s, vis_prev, lx, ly, t / p.pred_interval, la);
+        if (live && t % p.pred_interval == 0) cn_lookahead_accumulate(p, *s, vis_prev, lx, ly, t / p.pred_interval, la);
       }
       __syncthreads();
-      if (active) {
+      if (live) {
         s->px[h] = spx; s->py[h] = spy; s->fx[h] = (float)spx; s->fy[h] = (float)spy; s->vx[h] = svx; s->vy[h] = svy;
       }
       __syncthreads();
-      if (active) {
+      if (live) {
         cn_orca_finish(p, g, *s, e, h, result, nl, fail);
         cn_orca_diag(p, g, e, h, lres, lnl, lfail);                   // the simulators' LAST solve
         s->t0[h] = la.min_rd; s->t1[h] = la.pen;                      // reward inputs (test phase)
       }
-    } else if (active) {
+    } else if (live) {
       cn_orca_finish(p, g, *s, e, h, result, nl, fail);
     }
   }
@@ -199,9 +201,13 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   __syncthreads();
   if (active) {
     if (s->done) cn_install_env(p, g, *s, e, h);      // finished: the prepared next episode takes over
-    else cn_phase_integrate(p, *s, h);
+    else if (live) cn_phase_integrate(p, *s, h);
   }
   __syncthreads();
+  if (p.hrange > 0) {                                 // humans join / leave every 5 s, before the observation (leader)
+    if (mode != 1 && active && h == 0 && cn_add_remove_due(p, g, *s, e)) cn_phase_add_remove(p, g, *s, e);
+    __syncthreads();
+  }
   float row[MAXW];
   if (active) cn_phase_obs_a<MAXW>(p, g, *s, e, h, row);
   __syncthreads();
@@ -497,9 +503,10 @@ int cn_abi_version(void) { return CN_ABI_VERSION; }
 int cn_env_create(const cn_config* cfg, cn_env** out) {
   if (!cfg || !out) return cn_set_error("cn_env_create: null argument");
   *out = nullptr;
-  if (cfg->num_envs <= 0 || cfg->human_num <= 0 || cfg->human_num > 128)
-    return cn_set_error("cn_env_create: need num_envs > 0 and 1 <= human_num <= 128 (got %d, %d)", cfg->num_envs,
-                        cfg->human_num);
+  if (cfg->num_envs <= 0 || cfg->human_num <= 0 || cfg->human_num_range < 0 || cfg->human_num_range >= cfg->human_num ||
+      cfg->human_num + cfg->human_num_range > 128)
+    return cn_set_error("cn_env_create: need num_envs > 0, 0 <= human_num_range < human_num and human_num + range <= 128 "
+                        "(got %d, %d, %d)", cfg->num_envs, cfg->human_num, cfg->human_num_range);
   if (cfg->const_vel && (cfg->predict_steps < 0 || 2 * (cfg->predict_steps + 1) > 16))
     return cn_set_error("cn_env_create: predict_steps %d unsupported (row width > 16)", cfg->predict_steps);
   {
@@ -537,7 +544,8 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("side stream: %s", cudaGetErrorString(err)); }
   CnParams& p = env->p;
   memset(&p, 0, sizeof(p));
-  p.N = cfg->num_envs; p.H = cfg->human_num; p.P = cfg->predict_steps;
+  p.hbase = cfg->human_num; p.hrange = cfg->human_num_range;
+  p.N = cfg->num_envs; p.H = cfg->human_num + cfg->human_num_range; p.P = cfg->predict_steps;
   p.const_vel = cfg->const_vel ? 1 : 0;
   p.W = p.const_vel ? 2 * (p.P + 1) : 2;
   p.randomize = cfg->randomize_attributes; p.goal_changing = cfg->random_goal_changing;
@@ -586,7 +594,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
-  A(lp_cost, N); A(defer_list, N); A(defer_ctl, 4);
+  A(lp_cost, N); A(defer_list, N); A(defer_ctl, 4); A(hn, N); A(prep_hn, N); A(sim_n, NH);
 #undef A
   if (!rc) {
     // nd_global starts at the configured value (config.orca.neighbor_dist)

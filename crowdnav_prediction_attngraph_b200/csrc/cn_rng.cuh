@@ -191,3 +191,15 @@ CN_HD double cn_rng_uniform(CnRng& r, const CnCoop& c, double lo, double hi) {
   return lo + scale * u;
 #endif
 }
+
+// np.random.randint(low, high) of the legacy RandomState (int64 path, range < 2^32): rng = high - 1 - low;
+// rng == 0 consumes NO draw; otherwise masked rejection on 32-bit outputs (smallest 2^k - 1 >= rng).
+CN_HD int cn_rng_randint(CnRng& r, const CnCoop& c, int low, int high) {
+  const uint32_t rng = (uint32_t)(high - 1 - low);
+  if (rng == 0) return low;
+  uint32_t mask = rng;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  uint32_t v;
+  do { v = cn_rng_u32(r, c) & mask; } while (v > rng);
+  return low + (int)v;
+}

@@ -89,8 +89,6 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
         phase = "test" if (nenv_total or num_envs) == 1 else "train"
     if phase not in ("train", "test"):
         raise NotImplementedError("phase %r: the engine covers 'train' and 'test'" % (phase,))
-    if config.sim.human_num_range != 0:
-        raise NotImplementedError("sim.human_num_range > 0 is outside the engine's scope (SURVEY.md §8f row 4)")
     if config.action_space.kinematics != "holonomic" or config.humans.policy != "orca" or config.robot.visible:
         raise NotImplementedError("engine covers holonomic robot, ORCA humans, robot.visible=False")
     if env_name == "CrowdSimPred-v0":
@@ -108,7 +106,8 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
         raise NotImplementedError("args.sort_humans=False is covered only behind the GST wrapper (pretext_wrapper=True)")
     return _capi.default_config_dict(
         num_envs=num_envs, nenv_total=nenv_total or num_envs, rank_offset=rank_offset, seed=seed,
-        human_num=config.sim.human_num, predict_steps=config.sim.predict_steps, const_vel=const_vel,
+        human_num=config.sim.human_num, human_num_range=int(config.sim.human_num_range),
+        predict_steps=config.sim.predict_steps, const_vel=const_vel,
         randomize_attributes=int(bool(config.env.randomize_attributes)),
         random_goal_changing=int(bool(config.humans.random_goal_changing)),
         end_goal_changing=int(bool(config.humans.end_goal_changing)), sort_humans=int(bool(sort_humans)),
@@ -208,7 +207,7 @@ class CudaCrowdVecEnv(object):
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):       # the C entry point calls cudaSetDevice: keep the caller's current device
             _capi.check(self.lib, self.lib.cn_env_create(C.byref(self._cfg), C.byref(self._h)), "cn_env_create")
-        N, H = d["num_envs"], d["human_num"]
+        N, H = d["num_envs"], d["human_num"] + d["human_num_range"]          # rows = max_human_num
         W = 2 * (d["predict_steps"] + 1) if d["const_vel"] else 2
         self.num_envs, self.human_num, self.row_width = N, H, W
         spaces = {
@@ -359,7 +358,7 @@ class CudaCrowdVecEnv(object):
                bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
                sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",
                last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4", evt="u1", spawn_overflow="u1",
-               defer_ctl="i4", defer_list="i4", lp_cost="i4")
+               defer_ctl="i4", defer_list="i4", lp_cost="i4", hn="i4", prep_hn="i4")
 
     def get_state(self, name):
         nbytes = self.lib.cn_env_state_bytes(self._h, name.encode())

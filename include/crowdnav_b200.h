@@ -42,7 +42,7 @@ typedef struct cn_config {
   int32_t nenv_total;        /* env.nenv: total environments of the job (case_counter stride)   */
   int32_t rank_offset;       /* global index of this shard's env 0 (thisSeed = seed + rank)     */
   int32_t seed;              /* --seed (arguments.py:47)                                        */
-  int32_t human_num;         /* sim.human_num (sim.human_num_range must be 0)                   */
+  int32_t human_num;         /* sim.human_num                                                    */
   int32_t predict_steps;     /* sim.predict_steps                                               */
   int32_t const_vel;         /* 1: CrowdSimPred-v0 / 'const_vel'; 0: CrowdSimVarNum-v0 / 'none' */
   int32_t randomize_attributes;   /* env.randomize_attributes                                   */
@@ -53,7 +53,8 @@ typedef struct cn_config {
   int32_t phase;                  /* env.phase: 0 'train', 2 'test' (ground-truth look-ahead, 'future'
                                    * danger zone, test seeds; crowd_sim_pred.py:136-138)          */
   int32_t val_size, test_size;    /* env.val_size / env.test_size: case_counter wrap of the phase */
-  int32_t reserved0;
+  int32_t human_num_range;        /* sim.human_num_range: humans join / leave every 5 s; observations are padded to
+                                   * human_num + human_num_range rows (crowd_sim_pred.py:165-194)             */
   double time_step, time_limit, pred_timestep;
   double circle_radius, arena_size;
   double discomfort_dist, discomfort_penalty_factor, success_reward, collision_penalty;

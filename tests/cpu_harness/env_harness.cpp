@@ -49,16 +49,17 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     s.vx = f.data(); s.vy = s.vx + H; s.fx = s.vy + H; s.fy = s.fx + H; s.nvx = s.fy + H; s.nvy = s.nvx + H;
     s.visr = u.data();
     s.lean = 0;
-    const CnCoop co = {0, 1};
+    const CnCoop co = {0, 1, nullptr};
     uint32_t* prep_key = g.prep_mt + (size_t)e * 624;
     if (mode == 1) {
       // full reset = prepare (event kernel, forced) -> install + first observation (step kernel, mode 1)
       cn_prepare_env(p, g, s, e, prep_key, co);
-      s.done = 1; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0;
+      s.done = 1; s.info = 0; s.reward = 0.0; s.reset_flag = 0; s.nvis = 0; s.goal_flag = 0; s.hn = 0;
       for (int h = H - 1; h >= 0; --h) cn_install_env(p, g, s, e, h);
     } else {
       for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, action);
-      for (int h = 0; h < H; ++h) {
+      const int hn = s.hn;                       // live humans (slots [hn, H) are empty)
+      for (int h = 0; h < hn; ++h) {
         // single-lane "warp": the cooperative solver degenerates to the sequential RVO2 order
         CnWarpLines W; W.smem0 = lines.data() + (size_t)h * H; W.stride = 1; W.cap = 3;    // exercise both tiers
         W.ovf0 = lines.data() + (size_t)h * H + 3; W.ovf_stride = 0;
@@ -77,13 +78,13 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
         std::vector<CnLookahead> la(H);
         std::vector<CnF2> res(H);
         std::vector<int> nls(H), fails(H);
-        for (int h = 0; h < H; ++h) { la[h].min_rd = INFINITY; la[h].pen = 0.0; }
+        for (int h = 0; h < hn; ++h) { la[h].min_rd = INFINITY; la[h].pen = 0.0; }
         for (int t = 1; t <= p.lookahead_steps; ++t) {
-          for (int h = 0; h < H; ++h) {
+          for (int h = 0; h < hn; ++h) {
             s.px[h] = lx[h]; s.py[h] = ly[h]; s.fx[h] = (float)lx[h]; s.fy[h] = (float)ly[h];
             s.vx[h] = lvx[h]; s.vy[h] = lvy[h];
           }
-          for (int h = 0; h < H; ++h) {
+          for (int h = 0; h < hn; ++h) {
             CnWarpLines W; W.smem0 = lines.data() + (size_t)h * H; W.stride = 1; W.cap = 3;
             W.ovf0 = lines.data() + (size_t)h * H + 3; W.ovf_stride = 0;
             CnLineStore proj; proj.base = projbuf.data(); proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
@@ -93,7 +94,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
             cn_orca_lp3_warp(co, W, nl, vmax, proj, result, fail);
             res[h] = result; nls[h] = nl; fails[h] = fail;
           }
-          for (int h = 0; h < H; ++h) {
+          for (int h = 0; h < hn; ++h) {
             lx[h] = lx[h] + (double)res[h].x * p.time_step; ly[h] = ly[h] + (double)res[h].y * p.time_step;
             lvx[h] = res[h].x; lvy[h] = res[h].y;
             if (t % p.pred_interval == 0)
@@ -101,7 +102,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
             if (t == p.lookahead_steps) cn_orca_diag(p, g, e, h, res[h], nls[h], fails[h]);
           }
         }
-        for (int h = 0; h < H; ++h) {
+        for (int h = 0; h < hn; ++h) {
           s.px[h] = sx[h]; s.py[h] = sy[h]; s.fx[h] = (float)sx[h]; s.fy[h] = (float)sy[h];
           s.vx[h] = svx[h]; s.vy[h] = svy[h];
           s.t0[h] = la[h].min_rd; s.t1[h] = la[h].pen;
@@ -109,7 +110,8 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
       }
       cn_phase_reward(p, g, s, e, out);
       if (s.done) { for (int h = H - 1; h >= 0; --h) cn_install_env(p, g, s, e, h); }   // prepared next episode
-      else { for (int h = 0; h < H; ++h) cn_phase_integrate(p, s, h); }
+      else { for (int h = 0; h < hn; ++h) cn_phase_integrate(p, s, h); }
+      if (cn_add_remove_due(p, g, s, e)) cn_phase_add_remove(p, g, s, e);
     }
     for (int h = 0; h < H; ++h) cn_phase_obs_a<16>(p, g, s, e, h, rows.data() + (size_t)h * 16);
     for (int h = 0; h < H; ++h) cn_phase_obs_b(p, g, s, e, h, rows.data() + (size_t)h * 16, ob);
@@ -128,7 +130,8 @@ void* harness_create(const cn_config* cfg) {
   Harness* hn = new Harness();
   CnParams& p = hn->p;
   memset(&p, 0, sizeof(p));
-  p.N = cfg->num_envs; p.H = cfg->human_num; p.P = cfg->predict_steps;
+  p.hbase = cfg->human_num; p.hrange = cfg->human_num_range;
+  p.N = cfg->num_envs; p.H = cfg->human_num + cfg->human_num_range; p.P = cfg->predict_steps;
   p.const_vel = cfg->const_vel ? 1 : 0;
   p.W = p.const_vel ? 2 * (p.P + 1) : 2;
   p.randomize = cfg->randomize_attributes; p.goal_changing = cfg->random_goal_changing;
@@ -157,7 +160,7 @@ void* harness_create(const cn_config* cfg) {
   A(mt, N * 624); A(mt_pos, N);
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
-  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N); A(lp_cost, N);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N); A(lp_cost, N); A(hn, N); A(prep_hn, N); A(sim_n, NH);
 #undef A
   for (size_t e = 0; e < N; ++e) { g.nd_global[e] = cfg->orca_neighbor_dist; g.seed_off[e] = (int32_t)e; }
   return hn;
@@ -196,7 +199,7 @@ int harness_state_copy(void* h, const char* name, void* buf, size_t bytes, int d
 void harness_rng_doubles(uint32_t seed, int n, double* out) {
   uint32_t key[624];
   CnRng r; r.key = key; r.pos = 624;
-  const CnCoop co = {0, 1};
+  const CnCoop co = {0, 1, nullptr};
   cn_rng_seed(r, seed, co);
   for (int i = 0; i < n; ++i) out[i] = cn_rng_double(r, co);
 }

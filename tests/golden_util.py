@@ -8,7 +8,9 @@ import numpy as np
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ENV_CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5", "env_pred_h20_test",
-             "env_pred_h10_test_rand", "env_varnum_h5_test"]
+             "env_pred_h10_test_rand", "env_varnum_h5_test",
+             # sim.human_num_range > 0: humans join / leave every 5 s, observations padded to max_human_num
+             "env_varnum_h5_range2", "env_pred_h6_range3"]
 
 
 def load_env_case(name):
@@ -17,14 +19,14 @@ def load_env_case(name):
     over = dict(num_envs=g["actions"].shape[1], nenv_total=case["nenv"], seed=case["seed"],
                 human_num=case["human_num"], const_vel=1 if case["predict_method"] == "const_vel" else 0,
                 randomize_attributes=int(case["randomize"]), random_goal_changing=int(case["goal_changing"]),
-                phase=2 if case.get("phase", "train") == "test" else 0)
+                phase=2 if case.get("phase", "train") == "test" else 0, human_num_range=int(case.get("human_num_range", 0)))
     return g, case, over
 
 
 def replay(g, case, reset_fn, step_fn, get_fn, pos_tol=1e-9, obs_tol=1e-5, exact_orca=True):
     """Returns a list of human-readable mismatch strings (empty = parity)."""
     T, N = g["actions"].shape[:2]
-    H = case["human_num"]
+    H = case["human_num"] + int(case.get("human_num_range", 0))      # slots = max_human_num; absent humans are NaN in the goldens
     bad = []
     ob = reset_fn()
     for k in ob:
@@ -75,6 +77,8 @@ def replay(g, case, reset_fn, step_fn, get_fn, pos_tol=1e-9, obs_tol=1e-5, exact
             msg.append("potential")
         if np.abs(get_fn("nd_global") - g["st_nd_global"][t + 1]).max() > pos_tol:
             msg.append("nd_global")
+        if "st_count" in g.files and not np.array_equal(get_fn("hn"), g["st_count"][t + 1]):
+            msg.append("human count")
         if not np.array_equal(get_fn("sim_exists").reshape(N, H).astype(bool), g["st_sim_exists"][t + 1]):
             msg.append("sim_exists")
         if msg:

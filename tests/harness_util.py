@@ -19,7 +19,7 @@ STATE_DTYPES = dict(
     hpx="f8", hpy="f8", hgx="f8", hgy="f8", hrad="f8", hvpref="f8", hvx="f4", hvy="f4",
     bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
     sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",
-    last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4", evt="u1", spawn_overflow="u1")
+    last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4", evt="u1", spawn_overflow="u1", hn="i4", prep_hn="i4")
 
 
 def build():
@@ -47,7 +47,7 @@ class HarnessEnv(object):
         self.cfgd = _capi.default_config_dict(**cfg_over)
         self.cfg = _capi.config_from_dict(self.cfgd)
         self.h = self.lib.harness_create(C.byref(self.cfg))
-        N, H = self.cfgd["num_envs"], self.cfgd["human_num"]
+        N, H = self.cfgd["num_envs"], self.cfgd["human_num"] + self.cfgd["human_num_range"]
         W = 2 * (self.cfgd["predict_steps"] + 1) if self.cfgd["const_vel"] else 2
         self.N, self.H, self.W = N, H, W
         self.ob = dict(robot_node=np.zeros((N, 1, 7), np.float32), temporal_edges=np.zeros((N, 1, 2), np.float32),
