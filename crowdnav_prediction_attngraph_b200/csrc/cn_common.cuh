@@ -49,6 +49,8 @@ struct CnParams {
   double goal_change_chance;
   double orca_safety_space, orca_neighbor_dist;   // neighbor_dist: initial value of the global
   float orca_time_horizon;
+  int social_force;       // humans.policy == 'social_force' (crowd_nav/policy/social_force.py) instead of ORCA
+  double sf_A, sf_B, sf_KI;   // config.sf
   int defer_tries;        // warp-scope rejection-sampling budget (cn_env_event_kernel -> cn_env_event_heavy_kernel)
 };
 
@@ -72,6 +74,8 @@ struct CnState {
   // humans [N][H]
   double *hpx, *hpy, *hgx, *hgy, *hrad, *hvpref;
   float *hvx, *hvy;
+  double *hwx, *hwy;                 // fp64 velocities of social-force humans (the reference keeps Python floats;
+                                     // ORCA velocities are fp32-valued and live in hvx / hvy)
   // robot belief (last_human_states) [N][H]
   double *bpx, *bpy, *bvx, *bvy, *brad;
   uint8_t *vis;                      // human_visibility (to the robot)

@@ -61,6 +61,7 @@ struct CnEnvSh {
   // human arrays, length H
   double *px, *py, *gx, *gy, *rad, *vpref;
   float *vx, *vy;        // current velocities (fp32-valued)
+  double *wx, *wy, *nwx, *nwy;   // social-force humans only: current / new velocity in fp64 (null otherwise)
   float *fx, *fy;        // positions narrowed to fp32 (what the Cython boundary hands to rvo2)
   float *nvx, *nvy;      // ORCA output
   double *t0;            // scratch: closest distance / sort key
@@ -108,6 +109,7 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   s.px[h] = g.hpx[i]; s.py[h] = g.hpy[i];
   if (!s.lean) { s.gx[h] = g.hgx[i]; s.gy[h] = g.hgy[i]; s.rad[h] = g.hrad[i]; s.vpref[h] = g.hvpref[i]; }
   s.vx[h] = g.hvx[i]; s.vy[h] = g.hvy[i];
+  if (p.social_force) { s.wx[h] = g.hwx[i]; s.wy[h] = g.hwy[i]; }
   s.fx[h] = (float)s.px[h]; s.fy[h] = (float)s.py[h];
   if (h == 0) {
     s.rpx = g.rpx[e]; s.rpy = g.rpy[e]; s.rgx = g.rgx[e]; s.rgy = g.rgy[e];
@@ -198,6 +200,40 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
     lines.set(rank, cn_orca_line(pos, vel, rself, op, ov, orad, invTimeHorizon, timeStep));
   }
   nl_out = nl; vmax_out = vmax; pref_out = pref;
+}
+
+// Social-force humans (humans.policy = 'social_force', crowd_nav/policy/social_force.py:11-49): pull towards the goal
+// with relaxation K_I, exponential push A exp((r_i + r_j - d) / B) from every other human (the ones outside the FOV are
+// replaced by the dummy at (7, 7), crowd_sim.py:680-703), explicit Euler step, speed clipped to v_pref.  fp64 like the
+// reference's Python floats, same expression order.  Writes s.nwx / s.nwy and the robot-collision distance.
+CN_HD void cn_sf_action(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, bool use_fov = true) {
+  const int hn = s.hn;
+  const double px = s.px[h], py = s.py[h], vx = s.wx[h], vy = s.wy[h];
+  const double dx = s.gx[h] - px, dy = s.gy[h] - py;
+  const double dist = sqrt(dx * dx + dy * dy);
+  const double dvx = p.sf_KI * ((dx / dist) * s.vpref[h] - vx);
+  const double dvy = p.sf_KI * ((dy / dist) * s.vpref[h] - vy);
+  double ivx = 0.0, ivy = 0.0;
+  for (int j = 0; j < hn; ++j) {
+    if (j == h) continue;
+    const bool v = !use_fov || cn_in_fov(px, py, vx, vy, s.px[j], s.py[j], p.human_fov);
+    const double ox = v ? s.px[j] : 7.0, oy = v ? s.py[j] : 7.0, orad = v ? s.rad[j] : 0.3;
+    const double ex = px - ox, ey = py - oy;
+    const double d = sqrt(ex * ex + ey * ey);
+    const double w = p.sf_A * exp((s.rad[h] + orad - d) / p.sf_B);
+    ivx += w * (ex / d);
+    ivy += w * (ey / d);
+  }
+  double nvx = vx + (dvx + ivx) * p.time_step;
+  double nvy = vy + (dvy + ivy) * p.time_step;
+  const double nrm = cn_norm_dot(nvx, nvy);                  // np.linalg.norm([new_vx, new_vy])
+  if (nrm > s.vpref[h]) { nvx = nvx / nrm * s.vpref[h]; nvy = nvy / nrm * s.vpref[h]; }
+  s.nwx[h] = nvx; s.nwy[h] = nvy;
+  s.nvx[h] = (float)nvx; s.nvy[h] = (float)nvy;
+  const size_t i = cn_idx(p, e, h);
+  g.last_hvx[i] = (float)nvx; g.last_hvy[i] = (float)nvy; g.orca_nlines[i] = 0; g.orca_fail[i] = -1;
+  const double rx = px - s.rpx, ry = py - s.rpy;
+  s.t0[h] = sqrt(rx * rx + ry * ry) - s.rad[h] - p.robot_radius;
 }
 
 // Diagnostics of the LAST ORCA solve of a human's simulator (what reading the reference's rvo2 sims after a
@@ -305,9 +341,16 @@ CN_HD void cn_phase_reward(const CnParams& p, const CnState& g, CnEnvSh& s, int 
 
 // Phase INTEGRATE (per human): humans[i].step(human_action).
 CN_HD void cn_phase_integrate(const CnParams& p, CnEnvSh& s, int h) {
-  s.px[h] = s.px[h] + (double)s.nvx[h] * p.time_step;
-  s.py[h] = s.py[h] + (double)s.nvy[h] * p.time_step;
-  s.vx[h] = s.nvx[h]; s.vy[h] = s.nvy[h];
+  if (p.social_force) {
+    s.px[h] = s.px[h] + s.nwx[h] * p.time_step;
+    s.py[h] = s.py[h] + s.nwy[h] * p.time_step;
+    s.wx[h] = s.nwx[h]; s.wy[h] = s.nwy[h];
+    s.vx[h] = (float)s.nwx[h]; s.vy[h] = (float)s.nwy[h];
+  } else {
+    s.px[h] = s.px[h] + (double)s.nvx[h] * p.time_step;
+    s.py[h] = s.py[h] + (double)s.nvy[h] * p.time_step;
+    s.vx[h] = s.nvx[h]; s.vy[h] = s.nvy[h];
+  }
   // end-goal respawn is due when a human is within its radius of its goal (crowd_sim_pred.py:207-211);
   // the RNG-consuming work itself runs in the event kernel.  (benign race: all writers store 1)
   if (p.end_goal_changing && cn_norm_dot(s.gx[h] - s.px[h], s.gy[h] - s.py[h]) < s.rad[h]) s.goal_flag = 1;
@@ -519,6 +562,7 @@ CN_HD void cn_install_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   s.px[h] = px; s.py[h] = py; s.gx[h] = -px; s.gy[h] = -py;        // lean: gx / gy / rad / vpref alias HBM
   s.rad[h] = g.prep_hrad[i]; s.vpref[h] = g.prep_hvpref[i];
   s.vx[h] = 0.0f; s.vy[h] = 0.0f; s.fx[h] = (float)px; s.fy[h] = (float)py;
+  if (p.social_force) { s.wx[h] = 0.0; s.wy[h] = 0.0; }
   g.sim_exists[i] = 0;
   g.bpx[i] = 0; g.bpy[i] = 0; g.bvx[i] = 0; g.bvy[i] = 0; g.brad[i] = 0;   // last_human_states = zeros
   for (int w = h; w < 624; w += H) g.mt[(size_t)e * 624 + w] = g.prep_mt[(size_t)e * 624 + w];
@@ -570,6 +614,7 @@ CN_HD void cn_phase_add_remove(const CnParams& p, const CnState& g, CnEnvSh& s, 
       const CnSpawn sp = cn_circle_crossing_human(p, s, rng, co, i, nd, g.spawn_overflow + e);
       s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
       s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.fx[i] = (float)sp.px; s.fy[i] = (float)sp.py;
+      if (p.social_force) { s.wx[i] = 0.0; s.wy[i] = 0.0; }
       const size_t gi = cn_idx(p, e, i);
       g.bpx[gi] = 15.; g.bpy[gi] = 15.; g.bvx[gi] = 0.; g.bvy[gi] = 0.; g.brad[gi] = 0.3;
       g.vis[gi] = 0; g.sim_exists[gi] = 0;
@@ -606,7 +651,8 @@ CN_HD void cn_phase_obs_a(const CnParams& p, const CnState& g, CnEnvSh& s, int e
   const double pvx = g.bvx[i], pvy = g.bvy[i];
   double bx, by;
   if (vis) {
-    g.bpx[i] = s.px[h]; g.bpy[i] = s.py[h]; g.bvx[i] = (double)s.vx[h]; g.bvy[i] = (double)s.vy[h];
+    g.bpx[i] = s.px[h]; g.bpy[i] = s.py[h]; g.bvx[i] = p.social_force ? s.wx[h] : (double)s.vx[h];
+    g.bvy[i] = p.social_force ? s.wy[h] : (double)s.vy[h];
     g.brad[i] = s.rad[h];
     bx = s.px[h]; by = s.py[h];
   } else if (s.reset_flag) {
@@ -716,6 +762,7 @@ CN_HD bool cn_phase_goals(const CnParams& p, const CnState& g, CnEnvSh& s, int e
         if (co.lane == 0) {
           s.px[i] = sp.px; s.py[i] = sp.py; s.gx[i] = -sp.px; s.gy[i] = -sp.py;
           s.vx[i] = 0.0f; s.vy[i] = 0.0f; s.rad[i] = sp.rad; s.vpref[i] = sp.vpref;
+          if (p.social_force) { s.wx[i] = 0.0; s.wy[i] = 0.0; }
           g.sim_exists[cn_idx(p, e, i)] = 0;       // new Human => new ORCA policy => new rvo2 sim
         }
         cn_coop_sync(co);
@@ -732,6 +779,7 @@ CN_HD void cn_phase_store(const CnParams& p, const CnState& g, const CnEnvSh& s,
   g.hpx[i] = s.px[h]; g.hpy[i] = s.py[h];
   if (!s.lean) { g.hgx[i] = s.gx[h]; g.hgy[i] = s.gy[h]; g.hrad[i] = s.rad[h]; g.hvpref[i] = s.vpref[h]; }
   g.hvx[i] = s.vx[h]; g.hvy[i] = s.vy[h];
+  if (p.social_force) { g.hwx[i] = s.wx[h]; g.hwy[i] = s.wy[h]; }
   if (h == 0) {
     g.rpx[e] = s.rpx; g.rpy[e] = s.rpy; g.rgx[e] = s.rgx; g.rgy[e] = s.rgy;
     g.rvx[e] = s.rvx; g.rvy[e] = s.rvy;

@@ -32,10 +32,10 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 
 // lean = step kernel: goals / radii / preferred speeds are read-only there and stay in HBM, only what
 // other threads read or what changes lives in shared memory (px, py, t0, t1 + 6 float arrays)
-__host__ __device__ inline EnvSmemLayout env_layout(int H, bool lean) {
+__host__ __device__ inline EnvSmemLayout env_layout(int H, bool lean, bool sf = false) {
   EnvSmemLayout L;
   size_t o = align16(sizeof(CnEnvSh));
-  L.off_dbl = o; o += (size_t)(lean ? 4 : 8) * H * sizeof(double);
+  L.off_dbl = o; o += (size_t)((lean ? 4 : 8) + (sf ? 4 : 0)) * H * sizeof(double);   // sf: + wx, wy, nwx, nwy
   L.off_flt = o; o += (size_t)6 * H * sizeof(float);
   L.off_u8 = o; o += (size_t)H;
   L.per_env = align16(o);
@@ -43,7 +43,7 @@ __host__ __device__ inline EnvSmemLayout env_layout(int H, bool lean) {
 }
 
 __device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L, int H, bool lean, const CnState& g,
-                                    int e) {
+                                    int e, bool sf = false) {
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
   double* d = reinterpret_cast<double*>(base + L.off_dbl);
   float* f = reinterpret_cast<float*>(base + L.off_flt);
@@ -55,6 +55,10 @@ __device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L,
     s->gx = d + 4 * H; s->gy = d + 5 * H; s->rad = d + 6 * H; s->vpref = d + 7 * H;
   }
   s->lean = lean ? 1 : 0;
+  {
+    double* w = d + (lean ? 4 : 8) * H;
+    s->wx = sf ? w : nullptr; s->wy = sf ? w + H : nullptr; s->nwx = sf ? w + 2 * H : nullptr; s->nwy = sf ? w + 3 * H : nullptr;
+  }
   s->vx = f; s->vy = f + H; s->fx = f + 2 * H; s->fy = f + 3 * H; s->nvx = f + 4 * H; s->nvy = f + 5 * H;
   s->visr = base + L.off_u8;
   return s;
@@ -74,11 +78,11 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   // similar total linear-programming cost; results do not depend on the assignment
   const int e = (le < epb) ? g.perm[blockIdx.x * epb + le] : p.N;
   const bool active = (le < epb) && (e < p.N);
-  const EnvSmemLayout L = env_layout(H, true);
+  const EnvSmemLayout L = env_layout(H, true, p.social_force != 0);
   CnEnvSh* s = nullptr;
   if (le < epb) {
     s = reinterpret_cast<CnEnvSh*>(smem + (size_t)le * L.per_env);
-    if (h == 0 && e < p.N) env_view(smem + (size_t)le * L.per_env, L, H, true, g, e);
+    if (h == 0 && e < p.N) env_view(smem + (size_t)le * L.per_env, L, H, true, g, e, p.social_force != 0);
   }
   __syncthreads();
   // ORCA line storage of this warp: first `line_cap` lines of every thread in shared memory
@@ -153,7 +157,9 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
     if (fail >= 0) result = f2(s->nvx[h], s->nvy[h]);
     if (threadIdx.x == 0) { *lp3_count = 0; *lp3_head = 0; }          // ready for the next solve (a barrier follows)
   };
-  if (mode != 1) {
+  if (mode != 1 && p.social_force) {
+    if (live) cn_sf_action(p, g, *s, e, h);                           // social-force humans: no linear programs
+  } else if (mode != 1) {
     CnF2 result; int nl, fail;
     orca_solve(true, result, nl, fail);                               // get_human_actions (crowd_sim.py:680-703)
     if (live && fail >= 0) atomicAdd(&s->lp3_cost, 1);              // cost estimate for the next step's balancing
@@ -240,10 +246,10 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
   const int evt = force ? 2 : g.evt[e];
   if (evt == 0) return;
   const int H = p.H;
-  const EnvSmemLayout L = env_layout(H, false);
+  const EnvSmemLayout L = env_layout(H, false, p.social_force != 0);
   unsigned char* base = smem + (size_t)warp * per_warp_bytes;
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(base);
-  if (lane == 0) env_view(base, L, H, false, g, e);
+  if (lane == 0) env_view(base, L, H, false, g, e, p.social_force != 0);
   __syncwarp();
   uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
   const CnCoop co = {lane, 32, nullptr};
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
 __global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(CnParams p, CnState g) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.H;
-  const EnvSmemLayout L = env_layout(H, false);
+  const EnvSmemLayout L = env_layout(H, false, p.social_force != 0);
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(smem);
   uint32_t* key = reinterpret_cast<uint32_t*>(smem + L.per_env);
   int* scratch = reinterpret_cast<int*>(key + 624);
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(Cn
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int entry = g.defer_list[idx];
     const int e = entry & 0xffffff, evt = entry >> 24;
-    if (threadIdx.x == 0) env_view(smem, L, H, false, g, e);
+    if (threadIdx.x == 0) env_view(smem, L, H, false, g, e, p.social_force != 0);
     __syncthreads();
     if (evt == 2) {
       cn_prepare_env(p, g, *s, e, key, co, 0);
@@ -557,6 +563,15 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     const double q = floor(cfg->pred_timestep / cfg->time_step);
     p.pred_dt = cfg->time_step * (double)(int)q;
   }
+  if (cfg->human_policy != 0 && cfg->human_policy != 1) {
+    cn_env_destroy(env);
+    return cn_set_error("cn_env_create: human_policy %d unsupported (0 = 'orca', 1 = 'social_force')", cfg->human_policy);
+  }
+  if (cfg->human_policy == 1 && cfg->phase == 2) {
+    cn_env_destroy(env);
+    return cn_set_error("cn_env_create: social-force humans are covered in phase 'train' only (the test phase's "
+                        "ground-truth look-ahead runs the ORCA solver)");
+  }
   if (cfg->phase != 0 && cfg->phase != 2) {
     cn_env_destroy(env);
     return cn_set_error("cn_env_create: phase %d unsupported (0 = 'train', 2 = 'test')", cfg->phase);
@@ -571,6 +586,8 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   p.goal_change_chance = cfg->goal_change_chance;
   p.orca_safety_space = cfg->orca_safety_space; p.orca_neighbor_dist = cfg->orca_neighbor_dist;
   p.orca_time_horizon = (float)cfg->orca_time_horizon;
+  p.social_force = cfg->human_policy == 1 ? 1 : 0;
+  p.sf_A = cfg->sf_A; p.sf_B = cfg->sf_B; p.sf_KI = cfg->sf_KI;
   {
     // warp-scope budget of rejection-sampling tries before an event goes to the CTA-scope kernel
     // (CN_DEFER_TRIES=1 sends every search that needs a second candidate there: parity tests of the heavy path)
@@ -595,6 +612,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
   A(lp_cost, N); A(defer_list, N); A(defer_ctl, 4); A(hn, N); A(prep_hn, N); A(sim_n, NH);
+  A(hwx, cfg->human_policy ? NH : (size_t)4); A(hwy, cfg->human_policy ? NH : (size_t)4);
 #undef A
   if (!rc) {
     // nd_global starts at the configured value (config.orca.neighbor_dist)
@@ -630,7 +648,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   // of every thread live in shared memory.  Search (epb, cap) for the largest cap whose launch is
   // resident in ONE wave (shared memory is the occupancy limiter; a 1.16-wave launch costs 2x).
   env->maxh = p.H <= 32 ? 32 : (p.H <= 64 ? 64 : 128);
-  const EnvSmemLayout L = env_layout(p.H, true);
+  const EnvSmemLayout L = env_layout(p.H, true, p.social_force != 0);
   int nsm = 0;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, cfg->device);
   KernelFn fn = pick_kernel(env->maxh);
@@ -687,13 +705,13 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     env->balance = !(nb && nb[0] == '1') && env->use_side;
   }
   // event kernel: per-warp working set + MT19937 state
-  env->reset_warp_bytes = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t));
+  env->reset_warp_bytes = align16(env_layout(p.H, false, p.social_force != 0).per_env + 624 * sizeof(uint32_t));
   err = cudaFuncSetAttribute(cn_env_event_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(CN_EVENT_WARPS * env->reset_warp_bytes));
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }
   // heavy path: working set + MT19937 state + a few ints of scratch per CTA; half an SM-wave of CTAs (the list
   // is short, and these CTAs share the GPU with the caller's policy kernels)
-  env->heavy_smem = align16(env_layout(p.H, false).per_env + 624 * sizeof(uint32_t) + 64);
+  env->heavy_smem = align16(env_layout(p.H, false, p.social_force != 0).per_env + 624 * sizeof(uint32_t) + 64);
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);

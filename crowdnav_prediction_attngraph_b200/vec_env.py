@@ -89,8 +89,10 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
         phase = "test" if (nenv_total or num_envs) == 1 else "train"
     if phase not in ("train", "test"):
         raise NotImplementedError("phase %r: the engine covers 'train' and 'test'" % (phase,))
-    if config.action_space.kinematics != "holonomic" or config.humans.policy != "orca" or config.robot.visible:
-        raise NotImplementedError("engine covers holonomic robot, ORCA humans, robot.visible=False")
+    if config.action_space.kinematics != "holonomic" or config.robot.visible:
+        raise NotImplementedError("engine covers the holonomic robot with robot.visible=False")
+    if config.humans.policy not in ("orca", "social_force"):
+        raise NotImplementedError("humans.policy %r: the engine covers 'orca' and 'social_force'" % (config.humans.policy,))
     if env_name == "CrowdSimPred-v0":
         if config.sim.predict_method != "const_vel":
             raise NotImplementedError("CrowdSimPred-v0 is covered for predict_method='const_vel'")
@@ -122,6 +124,8 @@ def config_dict_from_reference(config, num_envs, seed, env_name, nenv_total=None
         sensor_range=float(config.robot.sensor_range), goal_change_chance=float(config.humans.goal_change_chance),
         orca_neighbor_dist=float(config.orca.neighbor_dist), orca_safety_space=float(config.orca.safety_space),
         orca_time_horizon=float(config.orca.time_horizon),
+        human_policy=1 if config.humans.policy == "social_force" else 0,
+        sf_A=float(config.sf.A), sf_B=float(config.sf.B), sf_KI=float(config.sf.KI),
         phase=2 if phase == "test" else 0, val_size=int(getattr(config.env, "val_size", 100)),
         test_size=int(getattr(config.env, "test_size", 500)))
 
@@ -358,7 +362,7 @@ class CudaCrowdVecEnv(object):
                bpx="f8", bpy="f8", bvx="f8", bvy="f8", brad="f8", vis="u1", sim_exists="u1",
                sim_nd="f4", sim_rself="f4", sim_vmax="f4", sim_rother="f4", mt="u4", mt_pos="i4",
                last_hvx="f4", last_hvy="f4", orca_nlines="i4", orca_fail="i4", evt="u1", spawn_overflow="u1",
-               defer_ctl="i4", defer_list="i4", lp_cost="i4", hn="i4", prep_hn="i4")
+               defer_ctl="i4", defer_list="i4", lp_cost="i4", hn="i4", prep_hn="i4", hwx="f8", hwy="f8")
 
     def get_state(self, name):
         nbytes = self.lib.cn_env_state_bytes(self._h, name.encode())

@@ -55,6 +55,8 @@ typedef struct cn_config {
   int32_t val_size, test_size;    /* env.val_size / env.test_size: case_counter wrap of the phase */
   int32_t human_num_range;        /* sim.human_num_range: humans join / leave every 5 s; observations are padded to
                                    * human_num + human_num_range rows (crowd_sim_pred.py:165-194)             */
+  int32_t human_policy;           /* humans.policy: 0 'orca', 1 'social_force' (crowd_nav/policy/social_force.py) */
+  int32_t reserved1;
   double time_step, time_limit, pred_timestep;
   double circle_radius, arena_size;
   double discomfort_dist, discomfort_penalty_factor, success_reward, collision_penalty;
@@ -62,6 +64,7 @@ typedef struct cn_config {
   double robot_radius, robot_v_pref, robot_fov, sensor_range;
   double goal_change_chance;
   double orca_neighbor_dist, orca_safety_space, orca_time_horizon;
+  double sf_A, sf_B, sf_KI;       /* config.sf (social-force humans)                                          */
 } cn_config;
 
 /* Observation buffers: the dict rl/networks/shmem_vec_env.py:109-116 returns, float32.       */

@@ -36,7 +36,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
   CnStepOut out;
   memset(&out, 0, sizeof(out));
   if (r) out = CnStepOut{r->reward, r->done, r->info, r->info_aux, r->ep_ret, r->ep_len, r->not_done};
-  std::vector<double> d(8 * H);
+  std::vector<double> d(12 * H);
   std::vector<float> f(6 * H);
   std::vector<uint8_t> u(H);
   std::vector<float4> lines((size_t)H * H);
@@ -46,6 +46,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     CnEnvSh s;
     s.px = d.data(); s.py = s.px + H; s.gx = s.py + H; s.gy = s.gx + H; s.rad = s.gy + H; s.vpref = s.rad + H;
     s.t0 = s.vpref + H; s.t1 = s.t0 + H;
+    s.wx = s.t1 + H; s.wy = s.wx + H; s.nwx = s.wy + H; s.nwy = s.nwx + H;      // social-force humans only
     s.vx = f.data(); s.vy = s.vx + H; s.fx = s.vy + H; s.fy = s.fx + H; s.nvx = s.fy + H; s.nvy = s.nvx + H;
     s.visr = u.data();
     s.lean = 0;
@@ -59,7 +60,8 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     } else {
       for (int h = H - 1; h >= 0; --h) cn_phase_load(p, g, s, e, h, action);
       const int hn = s.hn;                       // live humans (slots [hn, H) are empty)
-      for (int h = 0; h < hn; ++h) {
+      if (p.social_force) for (int h = 0; h < hn; ++h) cn_sf_action(p, g, s, e, h);
+      for (int h = 0; h < hn && !p.social_force; ++h) {
         // single-lane "warp": the cooperative solver degenerates to the sequential RVO2 order
         CnWarpLines W; W.smem0 = lines.data() + (size_t)h * H; W.stride = 1; W.cap = 3;    // exercise both tiers
         W.ovf0 = lines.data() + (size_t)h * H + 3; W.ovf_stride = 0;
@@ -149,6 +151,7 @@ void* harness_create(const cn_config* cfg) {
   p.goal_change_chance = cfg->goal_change_chance;
   p.orca_safety_space = cfg->orca_safety_space; p.orca_neighbor_dist = cfg->orca_neighbor_dist;
   p.orca_time_horizon = (float)cfg->orca_time_horizon;
+  p.social_force = cfg->human_policy == 1 ? 1 : 0; p.sf_A = cfg->sf_A; p.sf_B = cfg->sf_B; p.sf_KI = cfg->sf_KI;
   const size_t N = p.N, NH = N * p.H;
   CnState& g = hn->g;
 #define A(field, count) halloc(hn, #field, &g.field, (count))
@@ -160,7 +163,7 @@ void* harness_create(const cn_config* cfg) {
   A(mt, N * 624); A(mt_pos, N);
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
-  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N); A(lp_cost, N); A(hn, N); A(prep_hn, N); A(sim_n, NH);
+  A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N); A(lp_cost, N); A(hn, N); A(prep_hn, N); A(sim_n, NH); A(hwx, NH); A(hwy, NH);
 #undef A
   for (size_t e = 0; e < N; ++e) { g.nd_global[e] = cfg->orca_neighbor_dist; g.seed_off[e] = (int32_t)e; }
   return hn;

@@ -10,7 +10,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ENV_CASES = ["env_pred_h20", "env_pred_h20_rand", "env_pred_h50_rand", "env_varnum_h5", "env_pred_h20_test",
              "env_pred_h10_test_rand", "env_varnum_h5_test",
              # sim.human_num_range > 0: humans join / leave every 5 s, observations padded to max_human_num
-             "env_varnum_h5_range2", "env_pred_h6_range3"]
+             "env_varnum_h5_range2", "env_pred_h6_range3",
+             # humans.policy = 'social_force' (crowd_nav/policy/social_force.py), randomised attributes + goal changes
+             "env_pred_h8_sf"]
 
 
 def load_env_case(name):
@@ -19,7 +21,8 @@ def load_env_case(name):
     over = dict(num_envs=g["actions"].shape[1], nenv_total=case["nenv"], seed=case["seed"],
                 human_num=case["human_num"], const_vel=1 if case["predict_method"] == "const_vel" else 0,
                 randomize_attributes=int(case["randomize"]), random_goal_changing=int(case["goal_changing"]),
-                phase=2 if case.get("phase", "train") == "test" else 0, human_num_range=int(case.get("human_num_range", 0)))
+                phase=2 if case.get("phase", "train") == "test" else 0, human_num_range=int(case.get("human_num_range", 0)),
+                human_policy=1 if case.get("human_policy", "orca") == "social_force" else 0)
     return g, case, over
 
 
