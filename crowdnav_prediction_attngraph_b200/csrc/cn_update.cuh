@@ -62,13 +62,14 @@ __global__ void cn_upd_scale_kernel(const unsigned int* __restrict__ amax_bits, 
 // (hi, lo) split of a row-major fp32 matrix src[M, C] (optionally masked by relu_y > 0), scaled by *scale:
 //   hi/lo    [M, Cp]   row-major (pitch Cp >= C, multiple of 64; padding columns zero) -- or null
 //   hiT/loT  [C, Mp]   transposed (pitch Mp >= M, multiple of 64; padding zero)       -- or null
-//   colsum   [C]       += column sums of the masked, UNscaled values (db)             -- or null
+//   colsum   [C]       += column sums of the masked, UNscaled values (db), fp64 accumulators (the partial sums of
+//                         ~M/32 CTAs arrive in arbitrary order: in fp32 that costs ~1e-5 relative)  -- or null
 // One 32 x 32 tile per 256-thread CTA iteration (grid-stride over tiles), transposed through shared memory.
 __global__ void __launch_bounds__(256) cn_upd_split_kernel(const float* __restrict__ src, int ld, const float* __restrict__ relu_y,
                                                            int ldy, int M, int C, const float* __restrict__ scale,
                                                            __half* __restrict__ hi, __half* __restrict__ lo, int Cp,
                                                            __half* __restrict__ hiT, __half* __restrict__ loT, int Mp,
-                                                           float* __restrict__ colsum) {
+                                                           double* __restrict__ colsum) {
   __shared__ float tile[32][33];
   const float sc = __ldg(scale);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) cn_upd_split_kernel(const float* __restri
         float s = 0.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += part[j][tx];
-        if (s != 0.0f) atomicAdd(colsum + c0 + tx, s);
+        if (s != 0.0f) atomicAdd(colsum + c0 + tx, (double)s);
       }
     }
     __syncthreads();
@@ -123,6 +124,11 @@ __global__ void __launch_bounds__(256) cn_upd_split_kernel(const float* __restri
     }
     __syncthreads();
   }
+}
+
+__global__ void cn_upd_d2f_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
 }
 
 // ---------------------------------------------------------------------------------------------- attention (update)
@@ -389,7 +395,7 @@ int run_amax_scale(cudaStream_t st, const float* x, const float* relu_y, size_t 
 }
 
 void run_split(cudaStream_t st, const float* src, int ld, const float* relu_y, int ldy, int M, int C, const float* scale,
-               __half* hi, __half* lo, int Cp, __half* hiT, __half* loT, int Mp, float* colsum) {
+               __half* hi, __half* lo, int Cp, __half* hiT, __half* loT, int Mp, double* colsum) {
   const long long tiles = (long long)((Mp > M ? Mp : M) + 31) / 32 * (((Cp > C ? Cp : C) + 31) / 32);
   const int grid = tiles < 148 * 16 ? (int)tiles : 148 * 16;
   cn_upd_split_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(src, ld, relu_y, ldy, M, C, scale, hi, lo, Cp, hiT, loT, Mp, colsum);
@@ -422,7 +428,7 @@ size_t cn_update_linear_ws_bytes(int M, int N, int K) {
   const size_t Mp = mpad(M), Np = up(N, 64), Kp = up(K, 64);
   size_t fwd = 2 * (size_t)M * Kp * 2 + 2 * (size_t)N * Kp * 2;                                 // X split, W split
   size_t bwd = 2 * (size_t)M * Np * 2 + 2 * (size_t)N * Mp * 2 + 2 * (size_t)K * Np * 2;        // dZ, dZ^T, W^T splits
-  return (fwd > bwd ? fwd : bwd) + 16 * 1024;
+  return (fwd > bwd ? fwd : bwd) + 16 * 1024 + (size_t)N * 8;
 }
 
 // replaces (inside Policy.evaluate_actions of the PPO update): F.linear + ReLU of one per-human layer.
@@ -487,8 +493,10 @@ int cn_update_linear_bwd(const float* d_dy, const float* d_y, const void* d_save
   const float* sx = (const float*)(sv + up((size_t)2 * K * Mp * 2, 1024));
   const float* mask = act == 1 ? d_y : nullptr;
   run_amax_scale(st, d_dy, mask, (size_t)M * N, amax, sdz);
-  if (d_db) cudaMemsetAsync(d_db, 0, (size_t)N * sizeof(float), st);
-  run_split(st, d_dy, N, mask, N, M, N, sdz, d_dx ? zh : nullptr, d_dx ? zl : nullptr, N, zTh, zTl, Mp, d_db);
+  double* db64 = (double*)c.take((size_t)N * sizeof(double));
+  if (d_db) cudaMemsetAsync(db64, 0, (size_t)N * sizeof(double), st);
+  run_split(st, d_dy, N, mask, N, M, N, sdz, d_dx ? zh : nullptr, d_dx ? zl : nullptr, N, zTh, zTl, Mp, d_db ? db64 : nullptr);
+  if (d_db) cn_upd_d2f_kernel<<<(N + 255) / 256, 256, 0, st>>>(db64, d_db, N);
   if (d_dx) {
     run_amax_scale(st, d_w, nullptr, (size_t)N * K, amax + 1, sw);
     run_split(st, d_w, K, nullptr, 0, N, K, sw, nullptr, nullptr, 0, wTh, wTl, N, nullptr);     // W^T [K, N]

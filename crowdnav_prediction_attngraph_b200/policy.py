@@ -261,11 +261,12 @@ class Policy(nn.Module):
     def _features(self, inputs, h0, masks, T, N):
         b = self.base
         H = self.human_num
-        sp = inputs['spatial_edges'].reshape(T * N, H, -1).float()
+        dt = b.robot_linear[0].weight.dtype            # fp32; fp64 when a test runs the module in double as its reference
+        sp = inputs['spatial_edges'].reshape(T * N, H, -1).to(dt)
         n = inputs['detected_human_num'].reshape(T * N).long().clamp(1, H)
         valid = torch.arange(H, device=sp.device)[None, :] < n[:, None]
         rs = b.robot_linear(torch.cat([inputs['temporal_edges'].reshape(T * N, 2),
-                                       inputs['robot_node'].reshape(T * N, 7)], -1).float())
+                                       inputs['robot_node'].reshape(T * N, 7)], -1).to(dt))
         sa = b.spatial_attn
         mha = sa.multihead_attn
         wq, wk, wv = mha.in_proj_weight.chunk(3, 0)
@@ -283,7 +284,7 @@ class Policy(nn.Module):
             sp_p = sp[valid]                                             # [Mc, W]
             # update kernels: the three 128/512-wide per-row layers forward + backward on the tcgen05
             # 3xFP16 GEMM and the attention core over compacted rows; plain torch ops on CPU or with CN_UPDATE_KERNELS=0
-            use_tc = sp.is_cuda and getattr(self, "update_kernels", os.environ.get("CN_UPDATE_KERNELS", "1") == "1")
+            use_tc = sp.is_cuda and dt == torch.float32 and getattr(self, "update_kernels", os.environ.get("CN_UPDATE_KERNELS", "1") == "1")
             if use_tc:
                 from . import update_ops as uo
                 e1 = torch.relu(F.linear(sp_p, sa.embedding_layer[0].weight, sa.embedding_layer[0].bias))   # K = 12: torch

@@ -173,7 +173,7 @@ def test_heavy_event_path_equals_warp_path_at_config4_shape(monkeypatch):
     the default deferral budget, with everything deferred, and with nothing deferred end in the same state."""
     import os
     finals = []
-    for budget in ("320", "1", "1000000"):
+    for budget in ("136", "1", "1000000"):
         monkeypatch.setenv("CN_DEFER_TRIES", budget)
         env = _engine(num_envs=256, human_num=50, seed=9, randomize_attributes=1, random_goal_changing=1)
         env.reset()

@@ -39,10 +39,12 @@ def test_linear_tc_matches_fp64_reference(M, K, N, act, gscale):
         # the ReLU mask of the kernel path comes from ITS forward output; use the fp64 mask for both references
         yy.backward(dy.to(dt))
         outs[dt] = [yy.detach(), xx.grad, ww.grad, bb.grad]
-    for name, a, r64, r32 in zip(("y", "dx", "dw", "db"), got, outs[torch.float64], outs[torch.float32]):
-        e_tc, e_32 = _rel(a, r64), _rel(r32, r64)
+    errs = {name: (_rel(a, r64), _rel(r32, r64)) for name, a, r64, r32 in
+            zip(("y", "dx", "dw", "db"), got, outs[torch.float64], outs[torch.float32])}
+    print("linear_tc M=%d K=%d N=%d act=%d: (kernel error, torch fp32 error) vs fp64" % (M, K, N, act), errs)
+    for name, (e_tc, e_32) in errs.items():
         # fp32-equivalent: within 4x of torch's own fp32 error, or below 2e-6 of the tensor's largest entry
-        assert e_tc <= max(4 * e_32, 2e-6), (name, e_tc, e_32)
+        assert e_tc <= max(4 * e_32, 2e-6), (name, errs)
 
 
 def _segments(B, H, seed):
@@ -98,18 +100,27 @@ def test_evaluate_actions_kernels_on_equals_off():
     hx = {'human_node_rnn': torch.randn(N, 1, 128, device=DEV, generator=g) * 0.3}
     masks = (torch.rand(B, 1, device=DEV, generator=g) > 0.05).float()
     act = torch.randn(B, 2, device=DEV, generator=g)
+    import copy
     res = {}
-    for on in (True, False):
-        pol.update_kernels = on
-        pol.zero_grad()
-        v, lp, ent, h = pol.evaluate_actions(obs, hx, masks, act)
+    for tag, module, on in (("tc", pol, True), ("torch32", pol, False), ("fp64", copy.deepcopy(pol).double(), False)):
+        module.update_kernels = on
+        module.zero_grad()
+        dt = torch.float64 if tag == "fp64" else torch.float32
+        v, lp, ent, h = module.evaluate_actions(obs, {'human_node_rnn': hx['human_node_rnn'].to(dt)}, masks.to(dt), act.to(dt))
         (0.5 * v.pow(2).mean() - lp.mean() + 0.01 * ent).backward()
-        res[on] = (v.detach().clone(), lp.detach().clone(), float(ent), {k: p.grad.clone() for k, p in pol.named_parameters()
-                                                                         if p.grad is not None})
-    assert torch.allclose(res[True][0], res[False][0], rtol=1e-5, atol=1e-5)
-    assert torch.allclose(res[True][1], res[False][1], rtol=1e-5, atol=1e-5)
-    assert abs(res[True][2] - res[False][2]) <= 1e-6
-    for k, gref in res[False][3].items():
-        gk = res[True][3][k]
-        # both paths are fp32: agreement to 1e-4 of the gradient tensor's largest entry (measured noise ~1e-6)
-        assert float((gk - gref).abs().max()) <= 1e-4 * float(gref.abs().max()) + 1e-9, k
+        res[tag] = (v.detach().double(), lp.detach().double(), float(ent.detach()),
+                    {k: p.grad.double().clone() for k, p in module.named_parameters() if p.grad is not None})
+    assert torch.allclose(res["tc"][0], res["fp64"][0], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(res["tc"][1], res["fp64"][1], rtol=1e-5, atol=1e-5)
+    assert abs(res["tc"][2] - res["fp64"][2]) <= 1e-6
+    worst = []
+    for k, g64 in res["fp64"][3].items():
+        sc = float(g64.abs().max()) + 1e-30
+        e_tc = float((res["tc"][3][k] - g64).abs().max()) / sc
+        e_32 = float((res["torch32"][3][k] - g64).abs().max()) / sc
+        worst.append((e_tc, e_32, k))
+    worst.sort(reverse=True)
+    print("gradient errors vs fp64 (kernels, torch fp32), worst five:", worst[:5])
+    for e_tc, e_32, k in worst:
+        # fp32-equivalent: the kernel path is no further from the fp64 gradient than 4x torch's own fp32 path (or 2e-5)
+        assert e_tc <= max(4 * e_32, 2e-5), (k, e_tc, e_32)
