@@ -24,23 +24,39 @@ namespace {
 inline size_t up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------- small kernels
-// amax of |x| (optionally of x o [y > 0]): non-negative floats order like their bit patterns
-__global__ void cn_upd_amax_kernel(const float* __restrict__ x, const float* __restrict__ relu_y, size_t count,
-                                   unsigned int* __restrict__ out) {
+// amax of |x| (optionally of x o [y > 0]): non-negative floats order like their bit patterns.  16-byte loads.
+__global__ void __launch_bounds__(256) cn_upd_amax_kernel(const float* __restrict__ x, const float* __restrict__ relu_y,
+                                                          size_t count, unsigned int* __restrict__ out) {
   float m = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t n4 = count / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* y4 = reinterpret_cast<const float4*>(relu_y);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(x4 + i);
+    if (relu_y) {
+      const float4 y = __ldg(y4 + i);
+      if (!(y.x > 0.0f)) v.x = 0.0f;
+      if (!(y.y > 0.0f)) v.y = 0.0f;
+      if (!(y.z > 0.0f)) v.z = 0.0f;
+      if (!(y.w > 0.0f)) v.w = 0.0f;
+    }
+    const float a = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));   // fmaxf drops NaNs
+    if (a < 3.0e38f) m = fmaxf(m, a);                     // inf does not poison the scale (it poisons the result)
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {      // tail
+    const size_t i = n4 * 4 + threadIdx.x;
     float v = fabsf(x[i]);
     if (relu_y && !(relu_y[i] > 0.0f)) v = 0.0f;
-    if (v == v && v < 3.0e38f) m = fmaxf(m, v);            // NaN / inf do not poison the scale (they poison the result)
+    if (v == v && v < 3.0e38f) m = fmaxf(m, v);
   }
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __shared__ float sm[32];
+  __shared__ float sm[8];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0f;
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) atomicMax(out, __float_as_uint(m));
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    atomicMax(out, __float_as_uint(m));
   }
 }
 
@@ -59,66 +75,83 @@ __global__ void cn_upd_scale_kernel(const unsigned int* __restrict__ amax_bits, 
   scale[1] = 1.0f / s;
 }
 
-// (hi, lo) split of a row-major fp32 matrix src[M, C] (optionally masked by relu_y > 0), scaled by *scale:
+// (hi, lo) split of a row-major fp32 matrix src[M, C] (C and ld multiples of 4; optionally masked by relu_y > 0),
+// scaled by *scale:
 //   hi/lo    [M, Cp]   row-major (pitch Cp >= C, multiple of 64; padding columns zero) -- or null
 //   hiT/loT  [C, Mp]   transposed (pitch Mp >= M, multiple of 64; padding zero)       -- or null
 //   colsum   [C]       += column sums of the masked, UNscaled values (db), fp64 accumulators (the partial sums of
-//                         ~M/32 CTAs arrive in arbitrary order: in fp32 that costs ~1e-5 relative)  -- or null
-// One 32 x 32 tile per 256-thread CTA iteration (grid-stride over tiles), transposed through shared memory.
+//                         ~M/64 CTAs arrive in arbitrary order: in fp32 that costs ~1e-5 relative)  -- or null
+// One 64 x 64 tile per CTA iteration (grid-stride): 16-byte loads, 8-byte row-major stores, and the transposed copy
+// leaves through shared memory as 4-byte (two rows) stores, 128 contiguous bytes per warp.
 __global__ void __launch_bounds__(256) cn_upd_split_kernel(const float* __restrict__ src, int ld, const float* __restrict__ relu_y,
                                                            int ldy, int M, int C, const float* __restrict__ scale,
                                                            __half* __restrict__ hi, __half* __restrict__ lo, int Cp,
                                                            __half* __restrict__ hiT, __half* __restrict__ loT, int Mp,
                                                            double* __restrict__ colsum) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][65];
+  __shared__ float colpart[64];
   const float sc = __ldg(scale);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
-  const int tiles_c = (C + 31) / 32, tiles_m = (M + 31) / 32;
-  const int tiles_cp = Cp / 32 > tiles_c ? Cp / 32 : tiles_c;   // also visit the column padding of hi / lo
-  const int tiles_mp = Mp / 32 > tiles_m ? Mp / 32 : tiles_m;   // ... and the row padding of hiT / loT
-  const long long total = (long long)tiles_mp * tiles_cp;
+  const int tid = threadIdx.x;
+  const int lx = tid & 15, ly = tid >> 4;                       // load layout: 16 float4 per row, 16 rows per pass
+  const int tiles_c = ((Cp > C ? Cp : C) + 63) / 64, tiles_m = ((Mp > M ? Mp : M) + 63) / 64;
+  const long long total = (long long)tiles_m * tiles_c;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-    const int tm = (int)(t / tiles_cp), tcn = (int)(t - (long long)tm * tiles_cp);
-    const int r0 = tm * 32, c0 = tcn * 32;
-    float cs = 0.0f;
+    const int tm = (int)(t / tiles_c), tcn = (int)(t - (long long)tm * tiles_c);
+    const int r0 = tm * 64, c0 = tcn * 64;
+    if (colsum && tid < 64) colpart[tid] = 0.0f;
+    if (colsum) __syncthreads();
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = r0 + ty + 8 * j, c = c0 + tx;
-      float v = 0.0f;
+      const int r = r0 + ly + 16 * j, c = c0 + 4 * lx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < M && c < C) {
-        v = src[(size_t)r * ld + c];
-        if (relu_y && !(relu_y[(size_t)r * ldy + c] > 0.0f)) v = 0.0f;
+        v = *reinterpret_cast<const float4*>(src + (size_t)r * ld + c);
+        if (relu_y) {
+          const float4 y = *reinterpret_cast<const float4*>(relu_y + (size_t)r * ldy + c);
+          if (!(y.x > 0.0f)) v.x = 0.0f;
+          if (!(y.y > 0.0f)) v.y = 0.0f;
+          if (!(y.z > 0.0f)) v.z = 0.0f;
+          if (!(y.w > 0.0f)) v.w = 0.0f;
+        }
       }
-      cs += v;
-      const float x = fminf(fmaxf(v * sc, -65504.0f), 65504.0f);
-      tile[ty + 8 * j][tx] = x;
+      cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+      float x[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+      uint32_t ph[2], pl[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float x0 = fminf(fmaxf(x[2 * q], -65504.0f), 65504.0f), x1 = fminf(fmaxf(x[2 * q + 1], -65504.0f), 65504.0f);
+        x[2 * q] = x0; x[2 * q + 1] = x1;
+        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+        const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+        ph[q] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        pl[q] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      float* trow = &tile[ly + 16 * j][4 * lx];
+      trow[0] = x[0]; trow[1] = x[1]; trow[2] = x[2]; trow[3] = x[3];
       if (hi && r < M && c < Cp) {
-        const __half h = __float2half_rn(x);
-        hi[(size_t)r * Cp + c] = h;
-        lo[(size_t)r * Cp + c] = __float2half_rn(x - __half2float(h));
+        *reinterpret_cast<uint2*>(hi + (size_t)r * Cp + c) = make_uint2(ph[0], ph[1]);
+        *reinterpret_cast<uint2*>(lo + (size_t)r * Cp + c) = make_uint2(pl[0], pl[1]);
       }
     }
-    __shared__ float part[8][32];
-    if (colsum) {                                       // (uniform) 8 partial sums per column in this CTA
-      part[ty][tx] = cs;
-      __syncthreads();
-      if (ty == 0 && c0 + tx < C) {
-        float s = 0.0f;
+    if (colsum) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += part[j][tx];
-        if (s != 0.0f) atomicAdd(colsum + c0 + tx, (double)s);
-      }
+      for (int q = 0; q < 4; ++q) if (cs[q] != 0.0f) atomicAdd(&colpart[4 * lx + q], cs[q]);
     }
     __syncthreads();
+    if (colsum && tid < 64 && c0 + tid < C && colpart[tid] != 0.0f) atomicAdd(colsum + c0 + tid, (double)colpart[tid]);
     if (hiT) {
+      const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c0 + ty + 8 * j, r = r0 + tx;          // transposed: this thread writes column c, row r
+      for (int j = 0; j < 8; ++j) {
+        const int cl = warp + 8 * j;                               // column of the tile handled by this warp
+        const int c = c0 + cl, r = r0 + 2 * lane;                  // this lane writes rows r, r + 1
         if (c < C && r < Mp) {
-          const float x = tile[tx][ty + 8 * j];
-          const __half h = __float2half_rn(x);
-          hiT[(size_t)c * Mp + r] = h;
-          loT[(size_t)c * Mp + r] = __float2half_rn(x - __half2float(h));
+          const float x0 = tile[2 * lane][cl], x1 = tile[2 * lane + 1][cl];
+          const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+          const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+          *reinterpret_cast<uint32_t*>(hiT + (size_t)c * Mp + r) = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          *reinterpret_cast<uint32_t*>(loT + (size_t)c * Mp + r) = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
         }
       }
     }
@@ -388,7 +421,8 @@ int launch_gemm(int device, cudaStream_t st, const __half* ahi, const __half* al
 
 int run_amax_scale(cudaStream_t st, const float* x, const float* relu_y, size_t count, unsigned int* amax_bits, float* scale) {
   cudaMemsetAsync(amax_bits, 0, sizeof(unsigned int), st);
-  const int grid = (int)((count + 256 * 8 - 1) / (256 * 8)) < 1184 ? (int)((count + 256 * 8 - 1) / (256 * 8)) : 1184;
+  const size_t want = (count / 4 + 255) / 256;
+  const int grid = want < 148 * 16 ? (int)want : 148 * 16;
   cn_upd_amax_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(x, relu_y, count, amax_bits);
   cn_upd_scale_kernel<<<1, 1, 0, st>>>(amax_bits, scale);
   return 0;
@@ -396,8 +430,8 @@ int run_amax_scale(cudaStream_t st, const float* x, const float* relu_y, size_t 
 
 void run_split(cudaStream_t st, const float* src, int ld, const float* relu_y, int ldy, int M, int C, const float* scale,
                __half* hi, __half* lo, int Cp, __half* hiT, __half* loT, int Mp, double* colsum) {
-  const long long tiles = (long long)((Mp > M ? Mp : M) + 31) / 32 * (((Cp > C ? Cp : C) + 31) / 32);
-  const int grid = tiles < 148 * 16 ? (int)tiles : 148 * 16;
+  const long long tiles = (long long)((Mp > M ? Mp : M) + 63) / 64 * (((Cp > C ? Cp : C) + 63) / 64);
+  const int grid = tiles < 148 * 8 ? (int)tiles : 148 * 8;
   cn_upd_split_kernel<<<grid > 0 ? grid : 1, 256, 0, st>>>(src, ld, relu_y, ldy, M, C, scale, hi, lo, Cp, hiT, loT, Mp, colsum);
 }
 

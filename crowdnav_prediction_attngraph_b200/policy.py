@@ -314,7 +314,8 @@ class Policy(nn.Module):
                 row_start[1:] = torch.cumsum(n, 0)
                 row_env = torch.repeat_interleave(torch.arange(B, device=sp.device, dtype=torch.int32), n)
                 o = uo.hh_attention_rows(qkv, row_start, row_env)
-                hs = pad(uo.linear_tc(o, w_os, b_os, 1))
+                hs_c = uo.linear_tc(o, w_os, b_os, 1)          # [Mc, 256]: stays compact through the robot-human attention
+                hs = None
             else:
                 qkv = F.linear(e, w_qkv, b_qkv)
                 q, k, v = [heads(pad(t)) for t in qkv.chunk(3, -1)]
@@ -329,17 +330,39 @@ class Policy(nn.Module):
             o = F.scaled_dot_product_attention(q, k, v, attn_mask=amask)
             o = mha.out_proj(o.transpose(1, 2).reshape(B, H, 512))
             hs = b.spatial_linear(o)
-        te = b.attn.temporal_edge_layer[0](rs)
-        se = b.attn.spatial_edge_layer[0](hs)
-        att = (te[:, None, :] * se).sum(-1) * (H / 8.0)
-        att = torch.softmax(att.masked_fill(~valid, -1e9), dim=-1)
-        wvv = torch.bmm(hs.transpose(1, 2), att.unsqueeze(-1)).squeeze(-1)
+        tc_rows = hs is None                       # update kernels: per-sample layers on the tensor cores as well
+        if tc_rows:
+            def lin(x, layer, act=0):
+                return uo.linear_tc(x, layer.weight, layer.bias, act)
+        else:
+            def lin(x, layer, act=0):
+                y = F.linear(x, layer.weight, layer.bias)
+                return torch.relu(y) if act else y
+        te = lin(rs, b.attn.temporal_edge_layer[0])
+        if tc_rows:
+            # robot-human attention over the compact rows: scores of the valid humans, soft-max per sample on a padded
+            # [B, H] score table only, weighted sum by index_add (the padded [B, H, 256] feature tensor never exists)
+            renv = row_env.long()
+            se_c = lin(hs_c, b.attn.spatial_edge_layer[0])
+            sc_c = (te.index_select(0, renv) * se_c).sum(-1) * (H / 8.0)
+            scores = sc_c.new_full((B, H), -1e9)
+            scores[valid] = sc_c
+            att_c = torch.softmax(scores, dim=-1)[valid]
+            wvv = hs_c.new_zeros(B, hs_c.shape[-1]).index_add_(0, renv, hs_c * att_c.unsqueeze(-1))
+        else:
+            se = b.attn.spatial_edge_layer[0](hs)
+            att = (te[:, None, :] * se).sum(-1) * (H / 8.0)
+            att = torch.softmax(att.masked_fill(~valid, -1e9), dim=-1)
+            wvv = torch.bmm(hs.transpose(1, 2), att.unsqueeze(-1)).squeeze(-1)
         r = b.humanNodeRNN
-        x = torch.cat([torch.relu(r.encoder_linear(rs)), torch.relu(r.edge_attention_embed(wvv))], -1).reshape(T, N, 128)
+        x = torch.cat([lin(rs, r.encoder_linear, 1), lin(wvv, r.edge_attention_embed, 1)], -1)
         g = r.gru
         h = h0.reshape(N, HIDDEN)
         m = masks.reshape(T, N, 1)
-        gi_all = F.linear(x, g.weight_ih_l0, g.bias_ih_l0)
+        if tc_rows:
+            gi_all = uo.linear_tc(x, g.weight_ih_l0, g.bias_ih_l0, 0).reshape(T, N, 3 * HIDDEN)
+        else:
+            gi_all = F.linear(x.reshape(T, N, 128), g.weight_ih_l0, g.bias_ih_l0)
         outs = []
         for t in range(T):
             h = h * m[t]
@@ -351,8 +374,10 @@ class Policy(nn.Module):
             ng = torch.tanh(inn + rg * hn)
             h = (1 - zg) * ng + zg * h
             outs.append(h)
-        y = r.output_linear(torch.stack(outs, 0)).reshape(T * N, 256)
-        return b.critic_linear(b.critic(y)), b.actor(y), h.reshape(N, 1, HIDDEN)
+        y = lin(torch.stack(outs, 0).reshape(T * N, HIDDEN), r.output_linear)
+        hc = torch.tanh(lin(torch.tanh(lin(y, b.critic[0])), b.critic[2]))
+        ha = torch.tanh(lin(torch.tanh(lin(y, b.actor[0])), b.actor[2]))
+        return b.critic_linear(hc), ha, h.reshape(N, 1, HIDDEN)
 
     def evaluate_actions(self, inputs, rnn_hxs, masks, action):
         """inputs flattened [T*N, ...] (storage.py recurrent_generator), rnn_hxs['human_node_rnn'] [N,1,128]."""
