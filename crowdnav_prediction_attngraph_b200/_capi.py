@@ -60,7 +60,7 @@ EXPORTS = [
     "cn_gst_create", "cn_gst_destroy", "cn_gst_set_param", "cn_gst_finalize", "cn_gst_reset", "cn_gst_step",
     "cn_gst_launch_count",
     "cn_update_linear_saved_bytes", "cn_update_linear_ws_bytes", "cn_update_linear_fwd", "cn_update_linear_bwd",
-    "cn_update_attn_fwd", "cn_update_attn_bwd",
+    "cn_update_attn_fwd", "cn_update_attn_bwd", "cn_update_gru_fwd", "cn_update_gru_bwd",
 ]
 
 _lib = None
@@ -154,6 +154,8 @@ def load_library(path=None):
     lib.cn_update_linear_bwd.argtypes = [C.c_void_p] * 8 + [C.c_size_t] + [C.c_int] * 5 + [C.c_void_p]
     lib.cn_update_attn_fwd.argtypes = [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]
     lib.cn_update_attn_bwd.argtypes = [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]
+    lib.cn_update_gru_fwd.argtypes = [C.c_void_p] * 5 + [C.c_int] * 2 + [C.c_void_p] * 2 + [C.c_int, C.c_void_p]
+    lib.cn_update_gru_bwd.argtypes = [C.c_void_p] * 7 + [C.c_int] * 2 + [C.c_void_p] * 3 + [C.c_int, C.c_void_p]
     if path is None:
         _lib = lib
     return lib

@@ -337,6 +337,159 @@ __global__ void __launch_bounds__(CN_UPD_ATTN_WARPS * 32) cn_upd_attn_bwd_kv_ker
   }
 }
 
+// ---------------------------------------------------------------------------------------------- GRU over a rollout (update)
+// EndRNN's GRU cell over the T steps of a minibatch with done-mask resets (rl/networks/srnn_model.py:35-103,
+// selfAttn_srnn_temp_node.py:262-285), forward and backward in ONE launch each.  The eager formulation costs ~40
+// tiny kernels and autograd nodes per step and made the update launch-bound on the host.  gi = W_ih x + b_ih comes in
+// precomputed for all steps (one GEMM); here, per step:  h <- h * mask_t;  gh = W_hh h + b_hh;  r = s(gi_r + gh_r),
+// z = s(gi_z + gh_z), n = tanh(gi_n + r gh_n), h <- (1 - z) n + z h   (PyTorch gate order r, z, n).
+// A CTA owns 16 environments for the whole sequence; W_hh (384 x 128 fp32 = 192 KB) stays in shared memory.
+#define CN_GRU_ROWS 16
+#define CN_GRU_THREADS 256
+#define CN_GRU_SMEM (384 * 128 * 4 + CN_GRU_ROWS * 384 * 4 + 384 * 4)
+
+__device__ __forceinline__ float upd_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// saved [T, N, 4, 128] = (r, z, n, gh_n) per step; out [T, N, 128] = h after each step
+__global__ void __launch_bounds__(CN_GRU_THREADS, 1) cn_upd_gru_fwd_kernel(
+    const float* __restrict__ gi, const float* __restrict__ h0, const float* __restrict__ masks, const float* __restrict__ whh,
+    const float* __restrict__ bhh, int T, int N, float* __restrict__ out, float* __restrict__ saved) {
+  extern __shared__ __align__(16) float gsm[];
+  float* wt = gsm;                              // [128][384]: W_hh transposed (k-major) -> conflict-free over the gate columns
+  float* hs = wt + 128 * 384;                   // [16][128] current (masked) hidden state  (tile is 16 x 384 floats: reused below)
+  float* bs = hs + CN_GRU_ROWS * 384;           // [384]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 384 * 128; i += CN_GRU_THREADS) { const int j = i / 128, k = i - j * 128; wt[k * 384 + j] = whh[i]; }
+  for (int i = tid; i < 384; i += CN_GRU_THREADS) bs[i] = bhh[i];
+  const int row0 = blockIdx.x * CN_GRU_ROWS;
+  const int r0 = 2 * warp, r1 = 2 * warp + 1;                    // this warp's two rows; lane owns columns lane + 32 j
+  const int e0 = row0 + r0, e1 = row0 + r1;
+  float h[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[0][j] = e0 < N ? h0[(size_t)e0 * 128 + lane + 32 * j] : 0.0f;
+    h[1][j] = e1 < N ? h0[(size_t)e1 * 128 + lane + 32 * j] : 0.0f;
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const float m0 = e0 < N ? masks[(size_t)t * N + e0] : 0.0f, m1 = e1 < N ? masks[(size_t)t * N + e1] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[0][j] *= m0; h[1][j] *= m1;
+      hs[r0 * 128 + lane + 32 * j] = h[0][j]; hs[r1 * 128 + lane + 32 * j] = h[1][j];
+    }
+    __syncwarp();                                                 // rows r0, r1 are private to this warp
+    float acc[2][12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) { acc[0][q] = 0.0f; acc[1][q] = 0.0f; }
+#pragma unroll 4
+    for (int k = 0; k < 128; ++k) {
+      const float a0 = hs[r0 * 128 + k], a1 = hs[r1 * 128 + k];
+      const float* w = wt + k * 384 + lane;
+#pragma unroll
+      for (int q = 0; q < 12; ++q) {                              // q = gate * 4 + j -> column gate * 128 + lane + 32 j
+        const float wv = w[32 * q];
+        acc[0][q] = fmaf(a0, wv, acc[0][q]); acc[1][q] = fmaf(a1, wv, acc[1][q]);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int e = rr ? e1 : e0;
+      if (e < N) {
+        const float* g = gi + ((size_t)t * N + e) * 384;
+        float* sv = saved + ((size_t)t * N + e) * 512;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = lane + 32 * j;
+          const float ghr = acc[rr][j] + bs[c], ghz = acc[rr][4 + j] + bs[128 + c], ghn = acc[rr][8 + j] + bs[256 + c];
+          const float r = upd_sigmoid(g[c] + ghr), z = upd_sigmoid(g[128 + c] + ghz);
+          const float n = tanhf(g[256 + c] + r * ghn);
+          const float hn = (1.0f - z) * n + z * h[rr][j];
+          h[rr][j] = hn;
+          out[((size_t)t * N + e) * 128 + c] = hn;
+          sv[c] = r; sv[128 + c] = z; sv[256 + c] = n; sv[384 + c] = ghn;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// backward: d_out [T, N, 128] (gradient w.r.t. every step's output), optional d_hT [N, 128] (gradient w.r.t. the final state).
+// Writes d_gi [T, N, 384] (= gradient w.r.t. gi, and the r / z parts of gh), d_ghn [T, N, 128] (n part of gh) and d_h0 [N, 128];
+// dW_hh = [d_gi_r | d_gi_z | d_ghn]^T hm and db_hh follow from these by one GEMM / column sum in the caller.
+__global__ void __launch_bounds__(CN_GRU_THREADS, 1) cn_upd_gru_bwd_kernel(
+    const float* __restrict__ d_out, const float* __restrict__ d_hT, const float* __restrict__ out, const float* __restrict__ h0,
+    const float* __restrict__ masks, const float* __restrict__ saved, const float* __restrict__ whh, int T, int N,
+    float* __restrict__ d_gi, float* __restrict__ d_ghn, float* __restrict__ d_h0) {
+  extern __shared__ __align__(16) float gsm[];
+  float* ws = gsm;                              // [384][128] W_hh as stored: row j contiguous over the hidden columns
+  float* ds = ws + 384 * 128;                   // [16][384] gradient w.r.t. gh of the current step
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 384 * 128; i += CN_GRU_THREADS) ws[i] = whh[i];
+  const int row0 = blockIdx.x * CN_GRU_ROWS;
+  const int r0 = 2 * warp, r1 = 2 * warp + 1;
+  const int e0 = row0 + r0, e1 = row0 + r1;
+  float dh[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    dh[0][j] = (d_hT && e0 < N) ? d_hT[(size_t)e0 * 128 + lane + 32 * j] : 0.0f;
+    dh[1][j] = (d_hT && e1 < N) ? d_hT[(size_t)e1 * 128 + lane + 32 * j] : 0.0f;
+  }
+  __syncthreads();
+  for (int t = T - 1; t >= 0; --t) {
+    float dhm[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int e = rr ? e1 : e0, rl = rr ? r1 : r0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        float gr = 0.0f, gz = 0.0f, gn = 0.0f, ghn_g = 0.0f, carry = 0.0f;
+        if (e < N) {
+          const float m = masks[(size_t)t * N + e];
+          const float hprev = (t > 0 ? out[((size_t)(t - 1) * N + e) * 128 + c] : h0[(size_t)e * 128 + c]) * m;
+          const float* sv = saved + ((size_t)t * N + e) * 512;
+          const float r = sv[c], z = sv[128 + c], n = sv[256 + c], ghn = sv[384 + c];
+          const float d = dh[rr][j] + d_out[((size_t)t * N + e) * 128 + c];
+          const float dn = d * (1.0f - z), dz = d * (hprev - n);
+          carry = d * z;
+          const float dpn = dn * (1.0f - n * n);
+          gn = dpn; ghn_g = dpn * r;
+          gr = dpn * ghn * r * (1.0f - r);
+          gz = dz * z * (1.0f - z);
+          float* gg = d_gi + ((size_t)t * N + e) * 384;
+          gg[c] = gr; gg[128 + c] = gz; gg[256 + c] = gn;
+          d_ghn[((size_t)t * N + e) * 128 + c] = ghn_g;
+        }
+        ds[rl * 384 + c] = gr; ds[rl * 384 + 128 + c] = gz; ds[rl * 384 + 256 + c] = ghn_g;
+        dhm[rr][j] = carry;
+      }
+    }
+    __syncwarp();
+    // dhm += d_gh W_hh  ([2 rows, 384] x [384, 128]) for this warp's rows
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[0][j] = 0.0f; acc[1][j] = 0.0f; }
+#pragma unroll 4
+    for (int q = 0; q < 384; ++q) {
+      const float a0 = ds[r0 * 384 + q], a1 = ds[r1 * 384 + q];
+      const float* w = ws + q * 128 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float wv = w[32 * j]; acc[0][j] = fmaf(a0, wv, acc[0][j]); acc[1][j] = fmaf(a1, wv, acc[1][j]); }
+    }
+    const float m0 = e0 < N ? masks[(size_t)t * N + e0] : 0.0f, m1 = e1 < N ? masks[(size_t)t * N + e1] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dh[0][j] = (dhm[0][j] + acc[0][j]) * m0; dh[1][j] = (dhm[1][j] + acc[1][j]) * m1; }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (e0 < N) d_h0[(size_t)e0 * 128 + lane + 32 * j] = dh[0][j];
+    if (e1 < N) d_h0[(size_t)e1 * 128 + lane + 32 * j] = dh[1][j];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- TMA maps
 // operand map: fp16 [rows, K] with row pitch `pitch`, box 64 (K) x box_rows, SWIZZLE_128B; out-of-range -> zeros
 int op_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch) {
@@ -590,6 +743,46 @@ int cn_update_attn_bwd(const float* d_qkv, const float* d_out, const float* d_do
   cn_upd_attn_bwd_kv_kernel<<<grid, CN_UPD_ATTN_WARPS * 32, 0, st>>>(d_qkv, d_dout, d_stats, d_delta, d_row_start, d_row_env, Mc, d_dqkv);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cn_set_error("cn_update_attn_bwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// replaces (update path): the per-step GRU loop of EndRNN / RNNBase._forward_gru with done-mask resets
+// (rl/networks/srnn_model.py:49-103) over a [T, N] minibatch.  gi [T,N,384] = W_ih x + b_ih, h0 [N,128], masks [T,N],
+// whh [384,128], bhh [384]; out [T,N,128], saved [T,N,512] (r, z, n, gh_n for the backward).
+int cn_update_gru_fwd(const float* d_gi, const float* d_h0, const float* d_masks, const float* d_whh, const float* d_bhh, int T, int N,
+                      float* d_out, float* d_saved, int device, void* stream) {
+  if (!d_gi || !d_h0 || !d_masks || !d_whh || !d_bhh || !d_out || !d_saved) return cn_set_error("cn_update_gru_fwd: null argument");
+  if (T <= 0 || N <= 0) return 0;
+  int rc = setup_device(device);
+  if (rc) return rc;
+  static bool attr[64];
+  if (!attr[device]) {
+    cudaError_t e = cudaFuncSetAttribute(cn_upd_gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_GRU_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cn_upd_gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CN_GRU_SMEM);
+    if (e != cudaSuccess) return cn_set_error("cudaFuncSetAttribute(gru): %s", cudaGetErrorString(e));
+    attr[device] = true;
+  }
+  const int grid = (N + CN_GRU_ROWS - 1) / CN_GRU_ROWS;
+  cn_upd_gru_fwd_kernel<<<grid, CN_GRU_THREADS, CN_GRU_SMEM, (cudaStream_t)stream>>>(d_gi, d_h0, d_masks, d_whh, d_bhh, T, N, d_out, d_saved);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update_gru_fwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// d_out [T,N,128] (+ optional d_hT [N,128]) -> d_gi [T,N,384], d_ghn [T,N,128], d_h0 [N,128]  (see the kernel comment)
+int cn_update_gru_bwd(const float* d_dout, const float* d_dhT, const float* d_out, const float* d_h0, const float* d_masks,
+                      const float* d_saved, const float* d_whh, int T, int N, float* d_dgi, float* d_dghn, float* d_dh0, int device,
+                      void* stream) {
+  if (!d_dout || !d_out || !d_h0 || !d_masks || !d_saved || !d_whh || !d_dgi || !d_dghn || !d_dh0)
+    return cn_set_error("cn_update_gru_bwd: null argument");
+  if (T <= 0 || N <= 0) return 0;
+  int rc = setup_device(device);
+  if (rc) return rc;
+  const int grid = (N + CN_GRU_ROWS - 1) / CN_GRU_ROWS;
+  cn_upd_gru_bwd_kernel<<<grid, CN_GRU_THREADS, CN_GRU_SMEM, (cudaStream_t)stream>>>(d_dout, d_dhT, d_out, d_h0, d_masks, d_saved, d_whh,
+                                                                                     T, N, d_dgi, d_dghn, d_dh0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cn_set_error("cn_update_gru_bwd: %s", cudaGetErrorString(e));
   return 0;
 }
 

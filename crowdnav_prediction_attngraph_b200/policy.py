@@ -363,18 +363,23 @@ class Policy(nn.Module):
             gi_all = uo.linear_tc(x, g.weight_ih_l0, g.bias_ih_l0, 0).reshape(T, N, 3 * HIDDEN)
         else:
             gi_all = F.linear(x.reshape(T, N, 128), g.weight_ih_l0, g.bias_ih_l0)
-        outs = []
-        for t in range(T):
-            h = h * m[t]
-            gh = F.linear(h, g.weight_hh_l0, g.bias_hh_l0)
-            ir, iz, inn = gi_all[t].chunk(3, -1)
-            hr, hz, hn = gh.chunk(3, -1)
-            rg = torch.sigmoid(ir + hr)
-            zg = torch.sigmoid(iz + hz)
-            ng = torch.tanh(inn + rg * hn)
-            h = (1 - zg) * ng + zg * h
-            outs.append(h)
-        y = lin(torch.stack(outs, 0).reshape(T * N, HIDDEN), r.output_linear)
+        if tc_rows:
+            hseq = uo.gru_sequence(gi_all, h, m.reshape(T, N), g.weight_hh_l0, g.bias_hh_l0)    # one launch for the T steps
+            h = hseq[-1]
+        else:
+            outs = []
+            for t in range(T):
+                h = h * m[t]
+                gh = F.linear(h, g.weight_hh_l0, g.bias_hh_l0)
+                ir, iz, inn = gi_all[t].chunk(3, -1)
+                hr, hz, hn = gh.chunk(3, -1)
+                rg = torch.sigmoid(ir + hr)
+                zg = torch.sigmoid(iz + hz)
+                ng = torch.tanh(inn + rg * hn)
+                h = (1 - zg) * ng + zg * h
+                outs.append(h)
+            hseq = torch.stack(outs, 0)
+        y = lin(hseq.reshape(T * N, HIDDEN), r.output_linear)
         hc = torch.tanh(lin(torch.tanh(lin(y, b.critic[0])), b.critic[2]))
         ha = torch.tanh(lin(torch.tanh(lin(y, b.actor[0])), b.actor[2]))
         return b.critic_linear(hc), ha, h.reshape(N, 1, HIDDEN)

@@ -113,3 +113,43 @@ class _HHAttentionRows(torch.autograd.Function):
 def hh_attention_rows(qkv, row_start, row_env):
     """qkv [Mc, 1536] fp32 CUDA, row_start int32 [B + 1], row_env int32 [Mc] -> [Mc, 512]."""
     return _HHAttentionRows.apply(qkv, row_start, row_env)
+
+
+class _GruSeq(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gi, h0, masks, whh, bhh):
+        lib = _capi.load_library()
+        T, N = gi.shape[0], gi.shape[1]
+        dev = gi.device
+        gi, h0, masks, whh, bhh = [t.contiguous() for t in (gi, h0, masks, whh, bhh)]
+        out = torch.empty(T, N, 128, device=dev, dtype=torch.float32)
+        saved = torch.empty(T, N, 512, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _capi.check(lib, lib.cn_update_gru_fwd(_p(gi), _p(h0), _p(masks), _p(whh), _p(bhh), T, N, _p(out), _p(saved), dev.index,
+                                                   _stream(dev)), "cn_update_gru_fwd")
+        ctx.save_for_backward(out, h0, masks, saved, whh)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _capi.load_library()
+        out, h0, masks, saved, whh = ctx.saved_tensors
+        T, N = out.shape[0], out.shape[1]
+        dev = out.device
+        dout = dout.contiguous()
+        dgi = torch.empty(T, N, 384, device=dev, dtype=torch.float32)
+        dghn = torch.empty(T, N, 128, device=dev, dtype=torch.float32)
+        dh0 = torch.empty(N, 128, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _capi.check(lib, lib.cn_update_gru_bwd(_p(dout), None, _p(out), _p(h0), _p(masks), _p(saved), _p(whh), T, N, _p(dgi),
+                                                   _p(dghn), _p(dh0), dev.index, _stream(dev)), "cn_update_gru_bwd")
+        # recurrent weight / bias gradients: one GEMM over all steps (gh = hm W_hh^T + b_hh, hm = masked previous state)
+        dgh = torch.cat([dgi[..., :256], dghn], -1).reshape(T * N, 384)
+        hm = (torch.cat([h0.unsqueeze(0), out[:-1]], 0) * masks.unsqueeze(-1)).reshape(T * N, 128)
+        return dgi, dh0, None, dgh.t() @ hm, dgh.sum(0)
+
+
+def gru_sequence(gi, h0, masks, whh, bhh):
+    """GRU cell over T steps with done-mask resets: gi [T, N, 384] (= x W_ih^T + b_ih), h0 [N, 128], masks [T, N] ->
+    hidden state after every step [T, N, 128]."""
+    return _GruSeq.apply(gi, h0, masks, whh, bhh)

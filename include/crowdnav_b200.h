@@ -225,6 +225,17 @@ int cn_update_attn_bwd(const float *d_qkv, const float *d_out, const float *d_do
                        const int *d_row_start, const int *d_row_env, int Mc, float *d_dqkv, float *d_delta, int device,
                        void *stream);
 
+/* EndRNN's GRU over the T steps of a [T, N] minibatch with done-mask resets, one launch forward, one backward.
+ * d_gi [T,N,384] = W_ih x + b_ih (precomputed), d_h0 [N,128], d_masks [T,N], d_whh [384,128], d_bhh [384];
+ * d_out [T,N,128] hidden state after every step; d_saved [T,N,512] gates for the backward.  Backward: d_dout [T,N,128]
+ * (+ optional d_dhT [N,128]) -> d_dgi [T,N,384], d_dghn [T,N,128] (n-gate part of the recurrent pre-activation; its r / z
+ * parts equal d_dgi's), d_dh0 [N,128].  replaces: RNNBase._forward_gru (rl/networks/srnn_model.py:35-103).        */
+int cn_update_gru_fwd(const float *d_gi, const float *d_h0, const float *d_masks, const float *d_whh, const float *d_bhh,
+                      int T, int N, float *d_out, float *d_saved, int device, void *stream);
+int cn_update_gru_bwd(const float *d_dout, const float *d_dhT, const float *d_out, const float *d_h0, const float *d_masks,
+                      const float *d_saved, const float *d_whh, int T, int N, float *d_dgi, float *d_dghn, float *d_dh0,
+                      int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
