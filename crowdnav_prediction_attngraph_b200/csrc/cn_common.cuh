@@ -106,7 +106,7 @@ struct CnState {
   uint8_t *spawn_overflow;           // [N] set when a rejection-sampling loop hit CN_MAX_SPAWN_TRIES
   // events whose rejection sampling exceeded the warp-scope budget, redone by cn_env_event_heavy_kernel:
   int *defer_list;                   // [N] env | event kind << 24
-  int *defer_ctl;                    // [4] {count, finished-CTA ticket, total deferrals (diagnostic), unused}
+  int *defer_ctl;                    // [8] {count, finished-CTA ticket, total deferrals, total CTA batches, max batches of one CTA launch, ..}
   // overflow ORCA lines (k >= line_cap) of every step-kernel thread: [grid * block][ovf_stride] float4
   void *line_ovf;
   int ovf_stride;

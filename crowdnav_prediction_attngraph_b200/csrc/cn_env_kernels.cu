@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(Cn
   uint32_t* key = reinterpret_cast<uint32_t*>(smem + L.per_env);
   int* scratch = reinterpret_cast<int*>(key + 624);
   const int count = g.defer_ctl[0];
+  if (threadIdx.x == 0) scratch[1] = 0;
   const CnCoop co = {(int)threadIdx.x, (int)blockDim.x, scratch};
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int entry = g.defer_list[idx];
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(Cn
   }
   // the last CTA to finish clears the list for the next event kernel
   if (threadIdx.x == 0) {
+    if (scratch[1]) { atomicAdd(g.defer_ctl + 3, scratch[1]); atomicMax(g.defer_ctl + 4, scratch[1]); }   // diagnostics: total / max batches per CTA
     __threadfence();
     if (atomicAdd(g.defer_ctl + 1, 1) == (int)gridDim.x - 1) { g.defer_ctl[0] = 0; g.defer_ctl[1] = 0; }
   }
@@ -611,7 +613,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(prep_robot, N * 4); A(prep_hpx, NH); A(prep_hpy, NH); A(prep_hrad, NH); A(prep_hvpref, NH); A(prep_nd, N);
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
-  A(lp_cost, N); A(defer_list, N); A(defer_ctl, 4); A(hn, N); A(prep_hn, N); A(sim_n, NH);
+  A(lp_cost, N); A(defer_list, N); A(defer_ctl, 8); A(hn, N); A(prep_hn, N); A(sim_n, NH);
   A(hwx, cfg->human_policy ? NH : (size_t)4); A(hwy, cfg->human_policy ? NH : (size_t)4);
 #undef A
   if (!rc) {

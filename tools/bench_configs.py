@@ -70,7 +70,7 @@ def run(name, steps, warmup):
     overflow = int(env.get_state("spawn_overflow").sum())
     print(json.dumps({"config": name, "env_kwargs": kw, "envs": N, "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3,
                       "env_only_ms_per_step": ms_env, "valid_human_rows": int(eng.lib.cn_policy_last_rows(eng._h)),
-                      "spawn_overflow_envs": overflow}))
+                      "spawn_overflow_envs": overflow, "defer_ctl": [int(x) for x in env.get_state("defer_ctl")]}))
     del eng, policy, env
 
 
