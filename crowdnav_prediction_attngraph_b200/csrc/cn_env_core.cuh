@@ -28,8 +28,8 @@
 #define CN_PI 3.141592653589793
 #define CN_MAX_SPAWN_TRIES 20000
 // heavy (CTA-scope) rejection sampling: threads per try, and the warp-scope budget of tries before an event is deferred
-#define CN_HEAVY_SUB 8
-#define CN_HEAVY_THREADS 1024
+#define CN_HEAVY_SUB 4
+#define CN_HEAVY_THREADS 512
 #define CN_DEFER_TRIES 136
 
 CN_HD double cn_fma(double a, double b, double c) {
@@ -434,6 +434,7 @@ CN_HD CnCand cn_cand_point(const CnParams& p, double u0, double u1, double u2, i
 CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng, const CnCoop& co, int goal_kind, int n,
                                  int skip, double rad_i, double vp, uint8_t* overflow) {
   CnCand c; c.x = 0; c.y = 0;
+  bool tab_ready = false;       // CTA scope: fp32 agent table of this search built
   for (int tries = 0;;) {
     // warp scope: a search that has used up its budget is handed to cn_env_event_heavy_kernel (warp-uniform exit)
     if (rng.budget > 0 && tries >= rng.budget) { rng.deferred = 1; return c; }
@@ -442,14 +443,52 @@ CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng
     if (nb > CN_MAX_SPAWN_TRIES - tries + 1) nb = CN_MAX_SPAWN_TRIES - tries + 1;
 #if defined(__CUDA_ARCH__)
     if (co.nlanes > 32 && nb >= 1) {
-      // CTA scope (heavy path): all <= 104 tries up to the next twist at once, CN_HEAVY_SUB consecutive threads
-      // share one try and split the agent list; the FIRST free try wins, exactly like the sequential loop.
+      // CTA scope (heavy path): all <= 104 tries up to the next twist at once, CN_HEAVY_SUB consecutive threads share
+      // one try and split the agent list; the FIRST free try wins, exactly like the sequential loop.
+      // These searches are mostly doomed (the crowd has filled the goal ring; the reference would spin forever, the
+      // engine gives up after CN_MAX_SPAWN_TRIES), so what matters is the latency of one batch.  Measured with
+      // clock64: 5 400 cycles per batch when every thread ran the fp64 path (fp64 sincos + dependent shared-memory
+      // loads through the CnEnvSh pointers + early-exit loop).  Now an fp32 SCREEN runs first: candidate from sincosf,
+      // agents from a flat fp32 table in shared memory (built once per search), no early exit (independent loads),
+      // "surely collides" only when the fp32 squared distance is below the threshold by 1e-3 (1 + d2) -- 50x the
+      // fp32 error.  Only candidates the screen cannot reject take the exact path.
       const int t = co.lane / CN_HEAVY_SUB, sub = co.lane - t * CN_HEAVY_SUB;
       if (nb > co.nlanes / CN_HEAVY_SUB) nb = co.nlanes / CN_HEAVY_SUB;
+      float* tab = co.ftab;
+      if (!tab_ready) {                                         // (first batch of this search) agent table: index k + 1
+        tab_ready = true;
+        for (int k = -1 + co.lane; k < n; k += co.nlanes) {
+          double ax, ay, agx, agy, ar;
+          if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
+          else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
+          const double md = rad_i + ar + p.discomfort_dist;
+          tab[k + 1] = (float)ax; tab[CN_FTAB + k + 1] = (float)ay; tab[2 * CN_FTAB + k + 1] = (float)agx;
+          tab[3 * CN_FTAB + k + 1] = (float)agy;
+          tab[4 * CN_FTAB + k + 1] = (k == skip) ? -1.0f : (float)(md * md);     // skipped agent: can never collide
+        }
+      }
       if (co.lane == 0) { co.scratch[0] = 0x7fffffff; co.scratch[1] += 1; }      // scratch[1]: batches of this CTA (diagnostic)
+      const long long tq0 = clock64();
       __syncthreads();
-      bool collide = false;
+      bool sure = false;
       if (t < nb) {
+        const int off = 6 * t;
+        const double u0 = cn_rng_peek_double(rng, off), u1 = cn_rng_peek_double(rng, off + 2), u2 = cn_rng_peek_double(rng, off + 4);
+        float sn, cs;
+        sincosf((float)(u0 * CN_PI * 2), &sn, &cs);
+        const float fx = (float)p.circle_radius * cs + (goal_kind ? ((float)u1 - 0.5f) * (float)vp : (float)u1 * 2.0f);
+        const float fy = (float)p.circle_radius * sn + (goal_kind ? ((float)u2 - 0.5f) * (float)vp : (float)u2 * 2.0f);
+        for (int k = sub; k < n + 1; k += CN_HEAVY_SUB) {
+          const float dx = fx - tab[k], dy = fy - tab[CN_FTAB + k], ex = fx - tab[2 * CN_FTAB + k], ey = fy - tab[3 * CN_FTAB + k];
+          const float m2 = tab[4 * CN_FTAB + k];
+          const float d2 = dx * dx + dy * dy, e2 = ex * ex + ey * ey;
+          sure = sure || (d2 < m2 - 1e-3f * (1.0f + d2)) || (e2 < m2 - 1e-3f * (1.0f + e2));
+        }
+      }
+      const uint32_t gmask = ((1u << CN_HEAVY_SUB) - 1u) << ((threadIdx.x & 31) / CN_HEAVY_SUB * CN_HEAVY_SUB);
+      const bool try_sure = (__ballot_sync(0xffffffffu, sure) & gmask) != 0;
+      bool collide = false;
+      if (t < nb && !try_sure) {                                // exact path for the few candidates the screen let through
         const int off = 6 * t;
         const CnCand cc = cn_cand_point(p, cn_rng_peek_double(rng, off), cn_rng_peek_double(rng, off + 2),
                                         cn_rng_peek_double(rng, off + 4), goal_kind, vp);
@@ -457,11 +496,11 @@ CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng
           if (k != skip) collide = cn_cand_collides(p, s, cc.x, cc.y, rad_i, k);
       }
       const uint32_t m = __ballot_sync(0xffffffffu, collide);
-      const uint32_t gmask = ((1u << CN_HEAVY_SUB) - 1u) << ((threadIdx.x & 31) / CN_HEAVY_SUB * CN_HEAVY_SUB);
-      if (t < nb && sub == 0 && !(m & gmask)) atomicMin(co.scratch, t);
+      if (t < nb && sub == 0 && !try_sure && !(m & gmask)) atomicMin(co.scratch, t);
       __syncthreads();
       const int first = co.scratch[0];
       __syncthreads();
+      if (co.lane == 0) co.scratch[2] += (int)((clock64() - tq0) >> 4);          // diagnostic: cycles / 16 in candidate batches
       const bool last = (tries + nb - 1 >= CN_MAX_SPAWN_TRIES);
       if (first != 0x7fffffff || last) {
         const int j = (first != 0x7fffffff) ? first : nb - 1;
@@ -483,8 +522,46 @@ CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng
       const int sub = (tries < 8) ? 8 : 1;                     // lanes per candidate
       const int nbt = (nb < co.nlanes / sub) ? nb : co.nlanes / sub;
       const int t = co.lane / sub, j = co.lane - t * sub;
-      bool collide = false;
-      if (t < nbt) {
+      const uint32_t gmask = (sub == 32 ? 0xffffffffu : ((1u << sub) - 1u)) << (t * sub);
+      bool try_sure = false;
+#if defined(__CUDA_ARCH__)
+      if (co.ftab) {
+        // fp32 screen first (see the CTA-scope branch): flat agent table in shared memory, candidate from sincosf,
+        // no early exit; only candidates it cannot reject run the exact fp64 path below
+        float* tab = co.ftab;
+        if (!tab_ready) {
+          tab_ready = true;
+          for (int k = -1 + co.lane; k < n; k += co.nlanes) {
+            double ax, ay, agx, agy, ar;
+            if (k < 0) { ax = s.rpx; ay = s.rpy; agx = s.rgx; agy = s.rgy; ar = p.robot_radius; }
+            else { ax = s.px[k]; ay = s.py[k]; agx = s.gx[k]; agy = s.gy[k]; ar = s.rad[k]; }
+            const double md = rad_i + ar + p.discomfort_dist;
+            tab[k + 1] = (float)ax; tab[CN_FTAB + k + 1] = (float)ay; tab[2 * CN_FTAB + k + 1] = (float)agx;
+            tab[3 * CN_FTAB + k + 1] = (float)agy;
+            tab[4 * CN_FTAB + k + 1] = (k == skip) ? -1.0f : (float)(md * md);
+          }
+          __syncwarp();
+        }
+        bool sure = false;
+        if (t < nbt) {
+          const int off = 6 * t;
+          const double u0 = cn_rng_peek_double(rng, off), u1 = cn_rng_peek_double(rng, off + 2), u2 = cn_rng_peek_double(rng, off + 4);
+          float sn, cs;
+          sincosf((float)(u0 * CN_PI * 2), &sn, &cs);
+          const float fx = (float)p.circle_radius * cs + (goal_kind ? ((float)u1 - 0.5f) * (float)vp : (float)u1 * 2.0f);
+          const float fy = (float)p.circle_radius * sn + (goal_kind ? ((float)u2 - 0.5f) * (float)vp : (float)u2 * 2.0f);
+          for (int k = j; k < n + 1; k += sub) {
+            const float dx = fx - tab[k], dy = fy - tab[CN_FTAB + k], ex = fx - tab[2 * CN_FTAB + k], ey = fy - tab[3 * CN_FTAB + k];
+            const float m2 = tab[4 * CN_FTAB + k];
+            const float d2 = dx * dx + dy * dy, e2 = ex * ex + ey * ey;
+            sure = sure || (d2 < m2 - 1e-3f * (1.0f + d2)) || (e2 < m2 - 1e-3f * (1.0f + e2));
+          }
+        }
+        try_sure = (__ballot_sync(0xffffffffu, sure) & gmask) != 0;
+      }
+#endif
+      bool collide = try_sure;
+      if (t < nbt && !try_sure) {
         const int off = 6 * t;
         c = cn_cand_point(p, cn_rng_peek_double(rng, off), cn_rng_peek_double(rng, off + 2),
                           cn_rng_peek_double(rng, off + 4), goal_kind, vp);
@@ -492,7 +569,6 @@ CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng
           if (k != skip) collide = cn_cand_collides(p, s, c.x, c.y, rad_i, k);
       }
       const uint32_t cm = cn_ballot(co, collide);
-      const uint32_t gmask = (sub == 32 ? 0xffffffffu : ((1u << sub) - 1u)) << (t * sub);
       const uint32_t free_mask = cn_ballot(co, t < nbt && j == 0 && !(cm & gmask));      // bit = first lane of a free try
       const bool last = (tries + nbt - 1 >= CN_MAX_SPAWN_TRIES);
       if (free_mask || last) {
@@ -616,7 +692,7 @@ CN_HD void cn_install_env(const CnParams& p, const CnState& g, CnEnvSh& s, int e
 // (never one the robot currently observes: CrowdSimVarNum only -- CrowdSimPred never refreshes observed_human_ids),
 // joining humans spawn on the circle like at reset and are unknown to the robot (belief (15, 15, 0, 0, 0.3)).
 CN_HD void cn_phase_add_remove(const CnParams& p, const CnState& g, CnEnvSh& s, int e) {
-  const CnCoop co = {0, 1, nullptr};
+  const CnCoop co = {0, 1, nullptr, nullptr};
   CnRng rng; rng.key = g.mt + (size_t)e * 624; rng.pos = g.mt_pos[e]; rng.budget = 0; rng.deferred = 0;
   const int hn = s.hn, hmin = p.hbase - p.hrange;
   int hnew = hn;

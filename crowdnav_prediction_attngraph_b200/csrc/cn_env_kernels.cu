@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g,
   unsigned char* lp3_q = reinterpret_cast<unsigned char*>(lines_smem + (size_t)line_cap * blockDim.x +
                                                           (size_t)(blockDim.x >> 5) * MAXH);
   if (threadIdx.x == 0) { reinterpret_cast<int*>(lp3_q)[0] = 0; reinterpret_cast<int*>(lp3_q)[1] = 0; }
-  const CnCoop co = {lane, 32, nullptr};
+  const CnCoop co = {lane, 32, nullptr, nullptr};
 
   if (mode == 1) {
     if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; s->lp3_cost = 0; s->hn = 0; }
@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(CN_EVENT_WARPS * 32) cn_env_event_kernel(CnPar
   if (lane == 0) env_view(base, L, H, false, g, e, p.social_force != 0);
   __syncwarp();
   uint32_t* key = reinterpret_cast<uint32_t*>(base + L.per_env);
-  const CnCoop co = {lane, 32, nullptr};
+  // per-warp fp32 agent table of the rejection sampler, behind the MT19937 state
+  const CnCoop co = {lane, 32, nullptr, reinterpret_cast<float*>(key + 624)};
   bool deferred;
   if (evt == 2) {
     deferred = cn_prepare_env(p, g, *s, e, key, co, p.defer_tries);
@@ -293,10 +294,12 @@ __global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(Cn
   const EnvSmemLayout L = env_layout(H, false, p.social_force != 0);
   CnEnvSh* s = reinterpret_cast<CnEnvSh*>(smem);
   uint32_t* key = reinterpret_cast<uint32_t*>(smem + L.per_env);
-  int* scratch = reinterpret_cast<int*>(key + 624);
+  int* scratch = reinterpret_cast<int*>(key + 624);                    // 16 ints
+  float* ftab = reinterpret_cast<float*>(scratch + 16);               // 5 x CN_FTAB floats
   const int count = g.defer_ctl[0];
-  if (threadIdx.x == 0) scratch[1] = 0;
-  const CnCoop co = {(int)threadIdx.x, (int)blockDim.x, scratch};
+  if (threadIdx.x == 0) { scratch[1] = 0; scratch[2] = 0; }
+  const long long tk0 = clock64();
+  const CnCoop co = {(int)threadIdx.x, (int)blockDim.x, scratch, ftab};
   for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
     const int entry = g.defer_list[idx];
     const int e = entry & 0xffffff, evt = entry >> 24;
@@ -318,7 +321,11 @@ __global__ void __launch_bounds__(CN_HEAVY_THREADS) cn_env_event_heavy_kernel(Cn
   }
   // the last CTA to finish clears the list for the next event kernel
   if (threadIdx.x == 0) {
-    if (scratch[1]) { atomicAdd(g.defer_ctl + 3, scratch[1]); atomicMax(g.defer_ctl + 4, scratch[1]); }   // diagnostics: total / max batches per CTA
+    if (scratch[1]) {
+      atomicAdd(g.defer_ctl + 3, scratch[1]); atomicMax(g.defer_ctl + 4, scratch[1]);
+      atomicAdd(g.defer_ctl + 5, scratch[2] >> 6);                               // kilo-cycles in candidate batches
+      atomicAdd(g.defer_ctl + 6, (int)((clock64() - tk0) >> 10));               // kilo-cycles of working CTAs in total
+    }   // diagnostics: total / max batches per CTA
     __threadfence();
     if (atomicAdd(g.defer_ctl + 1, 1) == (int)gridDim.x - 1) { g.defer_ctl[0] = 0; g.defer_ctl[1] = 0; }
   }
@@ -707,13 +714,13 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     env->balance = !(nb && nb[0] == '1') && env->use_side;
   }
   // event kernel: per-warp working set + MT19937 state
-  env->reset_warp_bytes = align16(env_layout(p.H, false, p.social_force != 0).per_env + 624 * sizeof(uint32_t));
+  env->reset_warp_bytes = align16(env_layout(p.H, false, p.social_force != 0).per_env + 624 * sizeof(uint32_t) + 5 * CN_FTAB * sizeof(float));
   err = cudaFuncSetAttribute(cn_env_event_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(CN_EVENT_WARPS * env->reset_warp_bytes));
   if (err != cudaSuccess) { cn_env_destroy(env); return cn_set_error("cudaFuncSetAttribute(reset): %s", cudaGetErrorString(err)); }
   // heavy path: working set + MT19937 state + a few ints of scratch per CTA; half an SM-wave of CTAs (the list
   // is short, and these CTAs share the GPU with the caller's policy kernels)
-  env->heavy_smem = align16(env_layout(p.H, false, p.social_force != 0).per_env + 624 * sizeof(uint32_t) + 64);
+  env->heavy_smem = align16(env_layout(p.H, false, p.social_force != 0).per_env + 624 * sizeof(uint32_t) + 64 + 5 * CN_FTAB * sizeof(float));
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);

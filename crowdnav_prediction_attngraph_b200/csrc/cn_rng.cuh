@@ -28,7 +28,9 @@ struct CnRng {
 struct CnCoop {
   int lane, nlanes;
   int* scratch;
+  float* ftab;       // CTA scope: 5 x CN_FTAB floats of shared memory (fp32 agent table of the rejection sampler)
 };
+#define CN_FTAB 132
 CN_HD bool cn_any(const CnCoop& c, bool pred) {
 #if defined(__CUDA_ARCH__)
   if (c.nlanes > 32) return __syncthreads_or(pred ? 1 : 0) != 0;

@@ -50,7 +50,7 @@ static void run(Harness* hn, const float* action, const cn_obs_ptrs* o, const cn
     s.vx = f.data(); s.vy = s.vx + H; s.fx = s.vy + H; s.fy = s.fx + H; s.nvx = s.fy + H; s.nvy = s.nvx + H;
     s.visr = u.data();
     s.lean = 0;
-    const CnCoop co = {0, 1, nullptr};
+    const CnCoop co = {0, 1, nullptr, nullptr};
     uint32_t* prep_key = g.prep_mt + (size_t)e * 624;
     if (mode == 1) {
       // full reset = prepare (event kernel, forced) -> install + first observation (step kernel, mode 1)
@@ -202,7 +202,7 @@ int harness_state_copy(void* h, const char* name, void* buf, size_t bytes, int d
 void harness_rng_doubles(uint32_t seed, int n, double* out) {
   uint32_t key[624];
   CnRng r; r.key = key; r.pos = 624;
-  const CnCoop co = {0, 1, nullptr};
+  const CnCoop co = {0, 1, nullptr, nullptr};
   cn_rng_seed(r, seed, co);
   for (int i = 0; i < n; ++i) out[i] = cn_rng_double(r, co);
 }
