@@ -68,7 +68,7 @@ __device__ inline CnEnvSh* env_view(unsigned char* base, const EnvSmemLayout& L,
 // (g.prep_*, computed off the critical path by cn_env_event_kernel) and emit its first observation in
 // the same launch.  mode 1 = reset of the whole vector env: no step, every environment installs.
 template <int MAXH, int MAXW>
-__global__ void __launch_bounds__(288) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
+__global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState g, const float* __restrict__ action,
                                                           CnObs ob, CnStepOut out, int epb, int line_cap, int mode) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = p.H;
