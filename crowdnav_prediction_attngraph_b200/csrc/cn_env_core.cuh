@@ -574,7 +574,10 @@ CN_HD CnCand cn_rejection_sample(const CnParams& p, const CnEnvSh& s, CnRng& rng
       if (free_mask || last) {
         const int lane_j = free_mask ? cn_ffs(free_mask) : (nbt - 1) * sub;
         const int tj = lane_j / sub;
-        c.x = cn_bcast_d(co, c.x, lane_j); c.y = cn_bcast_d(co, c.y, lane_j);
+        // every lane recomputes the accepted candidate (a candidate accepted at the try limit may have been rejected
+        // by the fp32 screen, in which case no lane holds its fp64 coordinates)
+        c = cn_cand_point(p, cn_rng_peek_double(rng, 6 * tj), cn_rng_peek_double(rng, 6 * tj + 2),
+                          cn_rng_peek_double(rng, 6 * tj + 4), goal_kind, vp);
         rng.pos += 6 * (tj + 1);
         if (!free_mask && co.lane == 0) *overflow = 1;
         return c;
