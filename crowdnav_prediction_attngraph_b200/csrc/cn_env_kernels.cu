@@ -90,18 +90,25 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
   // cooperative linearProgram3 in a per-warp shared scratch.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4* lines_smem = reinterpret_cast<float4*>(smem + align16((size_t)epb * L.per_env));
+  // line slots only for the epb * H threads that own a human (the <= 31 padding threads of the last warp own none)
+  const int lstride = epb * H;
   CnWarpLines W;
   W.smem0 = lines_smem + warp * 32;
-  W.stride = blockDim.x;
+  W.stride = lstride;
   W.cap = line_cap;
   W.ovf_stride = g.ovf_stride;
   W.ovf0 = reinterpret_cast<float4*>(g.line_ovf) + ((size_t)blockIdx.x * blockDim.x + warp * 32) * g.ovf_stride;
+  // The two HALVES of a warp run the cooperative linear programs of different humans at the same time (a scan over the
+  // <= H - 1 previous lines rarely has work for more than 16 lanes): half-warp contexts and one projection scratch
+  // (<= H - 2 projected lines of linearProgram3) per half.
+  const int half = lane >> 4;
+  const CnCoop hco = {lane & 15, 16, nullptr, nullptr, half ? 0xffff0000u : 0x0000ffffu, half << 4};
   CnLineStore proj;
-  proj.base = lines_smem + (size_t)line_cap * blockDim.x + (size_t)warp * MAXH;
-  proj.stride = 1; proj.cap = MAXH; proj.ovf = nullptr;
+  proj.base = lines_smem + (size_t)line_cap * lstride + (size_t)(2 * warp + half) * H;
+  proj.stride = 1; proj.cap = H; proj.ovf = nullptr;
   // CTA-wide linearProgram3 task queue: {count, head, tasks[blockDim]} after the projection scratch
-  unsigned char* lp3_q = reinterpret_cast<unsigned char*>(lines_smem + (size_t)line_cap * blockDim.x +
-                                                          (size_t)(blockDim.x >> 5) * MAXH);
+  unsigned char* lp3_q = reinterpret_cast<unsigned char*>(lines_smem + (size_t)line_cap * lstride +
+                                                          (size_t)(blockDim.x >> 4) * H);
   if (threadIdx.x == 0) { reinterpret_cast<int*>(lp3_q)[0] = 0; reinterpret_cast<int*>(lp3_q)[1] = 0; }
   const CnCoop co = {lane, 32, nullptr, nullptr};
 
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
     result = f2(0.0f, 0.0f);
     if (live) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref, use_fov);
     __syncwarp();
-    cn_orca_lp2_warp(co, W, nl, vmax, pref, result, fail);            // all 32 lanes, idle ones with nl = 0
+    cn_orca_lp2_warp(hco, W, nl, vmax, pref, result, fail);           // per half-warp; idle lanes with nl = 0
     if (fail >= 0) {
       s->nvx[h] = result.x; s->nvy[h] = result.y;                     // LP2 result at the failure point
       reinterpret_cast<int*>(&s->t0[h])[0] = nl | (fail << 8);        // t0 is free until the solve is published
@@ -136,10 +143,10 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
     }
     __syncthreads();
     const int ntask = *lp3_count;
-    for (;;) {
+    for (;;) {                                                        // every HALF-warp pops its own tasks
       int t = 0;
-      if (lane == 0) t = atomicAdd(lp3_head, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
+      if (hco.lane == 0) t = atomicAdd(lp3_head, 1);
+      t = __shfl_sync(hco.mask, t, hco.base);
       if (t >= ntask) break;
       const int owner = lp3_tasks[t];
       const int ole = owner / H, oh = owner - ole * H;
@@ -148,10 +155,10 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
       const float ovmax = reinterpret_cast<const float*>(&os->t0[oh])[1];
       CnF2 ores = f2(os->nvx[oh], os->nvy[oh]);
       CnLineStore ol;
-      ol.base = lines_smem + owner; ol.stride = blockDim.x; ol.cap = line_cap;
+      ol.base = lines_smem + owner; ol.stride = lstride; ol.cap = line_cap;
       ol.ovf = reinterpret_cast<float4*>(g.line_ovf) + ((size_t)blockIdx.x * blockDim.x + owner) * g.ovf_stride;
-      cn_lp3_coop(co, ol, packed & 0xff, packed >> 8, ovmax, ores, proj);
-      if (lane == 0) { os->nvx[oh] = ores.x; os->nvy[oh] = ores.y; }
+      cn_lp3_coop(hco, ol, packed & 0xff, packed >> 8, ovmax, ores, proj);
+      if (hco.lane == 0) { os->nvx[oh] = ores.x; os->nvy[oh] = ores.y; }
     }
     __syncthreads();
     if (fail >= 0) result = f2(s->nvx[h], s->nvy[h]);
@@ -672,8 +679,8 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
     if (threads > 288) continue;
     const int grid_try = (p.N + epb - 1) / epb;
     for (int cap = cap_max; cap >= 1; --cap) {
-      const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * threads * sizeof(float4) +
-                          (size_t)(threads / 32) * env->maxh * sizeof(float4) +   // + per-warp LP3 scratch
+      const size_t need = align16((size_t)epb * L.per_env) + (size_t)cap * epb * p.H * sizeof(float4) +
+                          (size_t)(threads / 16) * p.H * sizeof(float4) +         // + per-half-warp LP3 scratch
                           align16(8 + 2 * (size_t)threads);                       // + CTA LP3 task queue
       if (need > 227 * 1024) continue;
       int per_sm = 0;

@@ -347,7 +347,7 @@ struct CnWarpLines {
 // failure index (-1 = LP2 succeeded; otherwise linearProgram3 must follow from that line).
 CN_HD void cn_orca_lp2_warp(const CnCoop& co, const CnWarpLines& W, int nl, float vmax, CnF2 pref, CnF2& result,
                             int& fail) {
-  const CnLineStore mine = W.of(co.lane);
+  const CnLineStore mine = W.of(co.base + co.lane);
   // linearProgram2 initialisation (closest point, not direction)
   if (f2abssq(pref) > vmax * vmax) result = f2scale(vmax, f2normalize(pref));
   else result = pref;
@@ -373,7 +373,7 @@ CN_HD void cn_orca_lp2_warp(const CnCoop& co, const CnWarpLines& W, int nl, floa
       const float rL = cn_bcast_f(co, vmax, L);
       const CnF2 oL = f2(cn_bcast_f(co, pref.x, L), cn_bcast_f(co, pref.y, L));
       CnF2 r2 = f2(0.0f, 0.0f);
-      const bool ok = cn_lp1_coop(co, W.of(L), iL, rL, oL, false, r2);
+      const bool ok = cn_lp1_coop(co, W.of(co.base + L), iL, rL, oL, false, r2);
       if (co.lane == L) {
         if (ok) { result = r2; ++i; }
         else { fail = i; running = 0; }
@@ -393,7 +393,7 @@ CN_HD void cn_orca_lp3_warp(const CnCoop& co, const CnWarpLines& W, int nl, floa
     const int nlL = cn_bcast_i(co, nl, L), fL = cn_bcast_i(co, fail, L);
     const float rL = cn_bcast_f(co, vmax, L);
     CnF2 resL = f2(cn_bcast_f(co, result.x, L), cn_bcast_f(co, result.y, L));
-    cn_lp3_coop(co, W.of(L), nlL, fL, rL, resL, proj);
+    cn_lp3_coop(co, W.of(co.base + L), nlL, fL, rL, resL, proj);
     if (co.lane == L) result = resL;
   }
 }

@@ -29,38 +29,43 @@ struct CnCoop {
   int lane, nlanes;
   int* scratch;
   float* ftab;       // CTA scope: 5 x CN_FTAB floats of shared memory (fp32 agent table of the rejection sampler)
+  // sub-warp groups (nlanes = 16: the two halves of a warp work on different humans at the same time): member mask of
+  // the group and the warp lane of its lane 0.  mask == 0 means the whole warp (base 0).
+  uint32_t mask;
+  int base;
 };
+CN_HD uint32_t cn_gmask(const CnCoop& c) { return c.mask ? c.mask : 0xffffffffu; }
 #define CN_FTAB 132
 CN_HD bool cn_any(const CnCoop& c, bool pred) {
 #if defined(__CUDA_ARCH__)
   if (c.nlanes > 32) return __syncthreads_or(pred ? 1 : 0) != 0;
-  if (c.nlanes > 1) return __any_sync(0xffffffffu, pred) != 0;
+  if (c.nlanes > 1) return __any_sync(cn_gmask(c), pred) != 0;
 #endif
   return pred;
 }
 CN_HD void cn_coop_sync(const CnCoop& c) {
 #if defined(__CUDA_ARCH__)
   if (c.nlanes > 32) __syncthreads();
-  else if (c.nlanes > 1) __syncwarp();
+  else if (c.nlanes > 1) __syncwarp(cn_gmask(c));
 #endif
   (void)c;
 }
 CN_HD uint32_t cn_ballot(const CnCoop& c, bool pred) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) return __ballot_sync(0xffffffffu, pred);
+  if (c.nlanes > 1) return (__ballot_sync(cn_gmask(c), pred) & cn_gmask(c)) >> c.base;      // group-relative bits
 #endif
   return pred ? 1u : 0u;
 }
 CN_HD float cn_bcast_f(const CnCoop& c, float v, int src) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) return __shfl_sync(0xffffffffu, v, src);
+  if (c.nlanes > 1) return __shfl_sync(cn_gmask(c), v, c.base + src);
 #endif
   (void)src;
   return v;
 }
 CN_HD int cn_bcast_i(const CnCoop& c, int v, int src) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) return __shfl_sync(0xffffffffu, v, src);
+  if (c.nlanes > 1) return __shfl_sync(cn_gmask(c), v, c.base + src);
 #endif
   (void)src;
   return v;
@@ -73,14 +78,14 @@ __device__ __forceinline__ float cn_ord2f(int o) { return __int_as_float(o ^ ((o
 #endif
 CN_HD float cn_warp_min(const CnCoop& c, float v) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) return cn_ord2f(__reduce_min_sync(0xffffffffu, cn_f2ord(v)));
+  if (c.nlanes > 1) return cn_ord2f(__reduce_min_sync(cn_gmask(c), cn_f2ord(v)));
 #endif
   (void)c;
   return v;
 }
 CN_HD float cn_warp_max(const CnCoop& c, float v) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) return cn_ord2f(__reduce_max_sync(0xffffffffu, cn_f2ord(v)));
+  if (c.nlanes > 1) return cn_ord2f(__reduce_max_sync(cn_gmask(c), cn_f2ord(v)));
 #endif
   (void)c;
   return v;
@@ -172,7 +177,7 @@ CN_HD double cn_rng_peek_double(const CnRng& r, int off) {
 }
 CN_HD double cn_bcast_d(const CnCoop& c, double v, int src) {
 #if defined(__CUDA_ARCH__)
-  if (c.nlanes > 1) return __shfl_sync(0xffffffffu, v, src);
+  if (c.nlanes > 1) return __shfl_sync(cn_gmask(c), v, c.base + src);
 #endif
   (void)src;
   return v;

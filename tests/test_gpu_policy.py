@@ -118,3 +118,39 @@ def test_cuda_policy_varnum_input_size_2_both_gemm_modes():
         value, action, logp, h1, mean = pol.act({k: v.cuda() for k, v in obs.items()}, h.cuda(), masks.cuda(),
                                                 deterministic=True, return_mean=True)
         assert (value.cpu() - rv).abs().max() < TOL and (mean.cpu() - rm).abs().max() < TOL and (h1.cpu() - rh).abs().max() < TOL
+
+
+@pytest.mark.parametrize("H,seed", [(20, 11), (50, 12)])
+def test_benchmarked_tensor_core_path_at_full_size_matches_oracle(H, seed):
+    """The configuration bench.py times: gemm_mode = 1 (tcgen05 3xFP16), N = 4096 environments, device-side row
+    compaction with random detected_human_num (ragged rows, many 128-row tiles per CTA: persistent tile loop, both TMEM
+    accumulators in flight), 3 consecutive calls (the double-buffered outputs and the hidden-state feedback) -- against
+    the plain PyTorch fp32 oracle (oracle/policy_ref.py), action mean / hidden state 1e-4, value 1e-4 of its scale."""
+    from oracle.policy_ref import PolicyRef
+    from crowdnav_prediction_attngraph_b200.policy import make_reference_like_state_dict
+    N = 4096
+    sd = make_reference_like_state_dict(12, seed=seed)
+    ref = PolicyRef(12)
+    ref.load_state_dict(sd)
+    pol = _cuda_policy(N, H, sd, gemm_mode=1)
+    gen = torch.Generator().manual_seed(seed)
+    h = torch.randn(N, 1, 128, generator=gen) * 0.5
+    for it in range(3):
+        n = torch.randint(1, H + 1, (N, 1), generator=gen).float()
+        if it == 1:
+            n[: N // 2] = 1.0                 # half of the batch sees a single human: many tiny segments
+        sp = torch.randn(N, H, 12, generator=gen) * 3
+        sp[torch.arange(H)[None, :] >= n] = 15.0
+        obs = dict(robot_node=torch.randn(N, 1, 7, generator=gen) * 3, temporal_edges=torch.randn(N, 1, 2, generator=gen),
+                   spatial_edges=sp, detected_human_num=n)
+        masks = (torch.rand(N, 1, generator=gen) > 0.1).float()
+        with torch.no_grad():
+            rv, rm, rh = ref(obs, h, masks)
+        dobs = {k: v.cuda() for k, v in obs.items()}
+        value, action, logp, h1, mean = pol.act(dobs, h.cuda(), masks.cuda(), deterministic=True, return_mean=True)
+        assert int(pol.lib.cn_policy_last_rows(pol._h)) == int(n.sum())
+        scale = max(1.0, float(rv.abs().max()))
+        assert float((value.cpu() - rv).abs().max()) < TOL * scale, it
+        assert float((mean.cpu() - rm).abs().max()) < TOL, it
+        assert float((h1.cpu() - rh).abs().max()) < TOL, it
+        h = rh                                 # oracle's state feeds both (no error accumulation across calls)
