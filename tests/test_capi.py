@@ -29,12 +29,26 @@ def test_header_symbols_exported(lib):
     assert lib.cn_abi_version() == 3
 
 
-def test_struct_layout_matches_header():
-    # 16 int32 + 20 double, no padding surprises
-    assert C.sizeof(_capi.CnConfig) == 16 * 4 + 20 * 8
-    assert C.sizeof(_capi.CnCopySeg) == 3 * 8
-    assert C.sizeof(_capi.CnObsPtrs) == 5 * 8 and C.sizeof(_capi.CnStepPtrs) == 7 * 8
-    assert C.sizeof(_capi.CnActPtrs) == 12 * 8 and C.sizeof(_capi.CnPolicyConfig) == 5 * 4
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors == the C structs of include/crowdnav_b200.h: a C program compiled against the header prints
+    sizeof / offsetof of every cn_config field, compared with the ctypes layout field by field."""
+    import subprocess
+    fields = [n for n, _ in _capi.CnConfig._fields_]
+    src = tmp_path / "layout.c"
+    body = "".join('  printf("%s %%zu\\n", offsetof(cn_config, %s));\n' % (f, f) for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "crowdnav_b200.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu %zu %zu %zu %zu %zu\\n", sizeof(cn_config), sizeof(cn_copy_seg), sizeof(cn_obs_ptrs),\n'
+                   '         sizeof(cn_step_ptrs), sizeof(cn_act_ptrs), sizeof(cn_policy_config));\n' + body + '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    sizes = [int(x) for x in out[0].split()[1:]]
+    assert sizes == [C.sizeof(_capi.CnConfig), C.sizeof(_capi.CnCopySeg), C.sizeof(_capi.CnObsPtrs), C.sizeof(_capi.CnStepPtrs),
+                     C.sizeof(_capi.CnActPtrs), C.sizeof(_capi.CnPolicyConfig)], sizes
+    for line in out[1:]:
+        name, off = line.split()
+        assert getattr(_capi.CnConfig, name).offset == int(off), name
+    assert C.sizeof(_capi.CnConfig) == 18 * 4 + 23 * 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

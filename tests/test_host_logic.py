@@ -23,7 +23,8 @@ def _ref_config(**over):
            env=ns(randomize_attributes=False, time_step=0.25, time_limit=50, val_size=100, test_size=500),
            data=ns(pred_timestep=0.25),
            reward=ns(discomfort_dist=0.25, discomfort_penalty_factor=10, success_reward=10, collision_penalty=-20),
-           orca=ns(neighbor_dist=10, safety_space=0.15, time_horizon=5), args=ns(sort_humans=True))
+           orca=ns(neighbor_dist=10, safety_space=0.15, time_horizon=5), sf=ns(A=2.0, B=1.0, KI=1.0),
+           args=ns(sort_humans=True))
     for k, v in over.items():
         setattr(c.sim, k, v)
     return c
@@ -39,8 +40,20 @@ def test_config_snapshot_follows_the_reference_phase_rule_and_scope():
     assert config_dict_from_reference(c, 8, 425, "CrowdSimPred-v0", phase="test")["phase"] == 2
     with pytest.raises(NotImplementedError):
         config_dict_from_reference(c, 8, 425, "CrowdSimPred-v0", phase="val")
+    # sim.human_num_range > 0 and social-force humans are engine features since round 2
+    d2 = config_dict_from_reference(_ref_config(human_num_range=2), 8, 425, "CrowdSimPred-v0")
+    assert d2["human_num_range"] == 2 and d2["human_num"] == 20
+    csf = _ref_config()
+    csf.humans.policy = "social_force"
+    assert config_dict_from_reference(csf, 8, 425, "CrowdSimPred-v0")["human_policy"] == 1
+    cuni = _ref_config()
+    cuni.action_space.kinematics = "unicycle"
     with pytest.raises(NotImplementedError):
-        config_dict_from_reference(_ref_config(human_num_range=2), 8, 425, "CrowdSimPred-v0")
+        config_dict_from_reference(cuni, 8, 425, "CrowdSimPred-v0")
+    cus = _ref_config()
+    cus.args.sort_humans = False
+    with pytest.raises(NotImplementedError):
+        config_dict_from_reference(cus, 8, 425, "CrowdSimPred-v0")
     with pytest.raises(NotImplementedError):
         config_dict_from_reference(c, 8, 425, "rosTurtlebot2iEnv-v0")
     # the flat dict maps 1:1 onto the C struct
@@ -53,7 +66,7 @@ def test_lazy_infos_materialise_like_the_reference_dicts():
                       np.array([0.0, 0.0, -3.25]), np.array([0, 0, 17]))
     assert len(infos) == 3 and 'episode' not in infos[0]
     assert isinstance(infos[1]['info'], Danger) and abs(infos[1]['info'].min_dist - 0.41) < 1e-6
-    assert isinstance(infos[2]['info'], Collision) and infos[2]['episode'] == {'r': -3.25, 'l': 17}
+    assert isinstance(infos[2]['info'], Collision) and infos[2]['episode'] == {'r': -3.25, 'l': 17, 't': 0.0}
 
 
 def test_evaluation_summary_matches_rl_evaluation_bookkeeping():
