@@ -152,3 +152,32 @@ def test_two_rank_update_equals_single_rank_update_on_the_whole_batch(tmp_path):
     # one Adam step of lr 1e-4: entries move by ~1e-4; agreement to a few percent of a step (fp32 reduction order,
     # and the sign-like Adam normalisation amplifies gradient noise near zero)
     assert worst <= 2e-5, worst
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_unmodified_train_py_under_torchrun_two_ranks(tmp_path):
+    """`torchrun --nproc-per-node 2 <reference>/train.py` with the compat aliases: make_vec_envs shards the environments
+    over the ranks (32 each), PPO broadcasts the initial weights and all-reduces the gradients over NCCL; train.py itself
+    is the reference's file, byte for byte (sha256 manifest).  Both ranks finish 2 updates and rank files agree."""
+    import subprocess
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_dropin_reference_scripts as td
+    root = td._ref_root()
+    td._check_unmodified(root, ["train.py", "arguments.py"])
+    w = td._workdir(tmp_path, root, td.C2_EDITS)
+    out = os.path.join(w, "out")
+    env = dict(os.environ)
+    env["PYTHONSAFEPATH"] = "1"
+    env["PYTHONPATH"] = os.pathsep.join([w, td.COMPAT, td.REPO, root])
+    env["CROWDNAV_B200_TRACE"] = "1"
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(_free_port()), os.path.join(root, "train.py"), "--num-processes", "32",
+                        "--env-name", "CrowdSimPred-v0", "--num-env-steps", str(32 * 30 * 2), "--output_dir", out,
+                        "--log-interval", "1", "--save-interval", "1"], cwd=w, env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    # both ranks built a 32-environment shard of a 64-environment job
+    assert p.stderr.count("N=32 (of 64, offset 0)") == 1 and p.stderr.count("N=32 (of 64, offset 32)") == 1, p.stderr[-2000:]
+    sd = torch.load(os.path.join(out, "checkpoints", "00001.pt"), map_location="cpu", weights_only=True)
+    assert all(bool(np.isfinite(v.numpy()).all()) for v in sd.values())
