@@ -353,9 +353,12 @@ void cn_gst_tc_destroy(void* handle);
 int64_t cn_gst_tc_launches(void* handle);
 int cn_gst_tc_step(void* handle, float* ring_pos, uint8_t* ring_mask, int newest, const float* robot, const float* sp2,
                    const uint8_t* vis, float* reward, float* penalty, float* out_sp, cudaStream_t st);
+int cn_gst_tcc_step(void* handle, float* ring_pos, uint8_t* ring_mask, int newest, const float* robot, const float* sp2,
+                    const uint8_t* vis, float* reward, float* penalty, float* out_sp, cudaStream_t st);
 
 struct cn_gst {
-  void* tc;           // non-null: dense layers on the tcgen05 GEMM (CN_GST_MODE=tc)
+  void* tc;           // non-null: dense layers on the tcgen05 GEMM (CN_GST_MODE=tcc (default) or tc)
+  bool compact;       // tcc: only the rows whose mask is 1 are computed (cn_gst_tcc_step)
   int N, H, P, device;
   float thr, collision_penalty;
   std::map<std::string, std::vector<float>> host;
@@ -392,7 +395,7 @@ int cn_gst_create(int num_envs, int human_num, int predict_steps, double robot_r
   cn_gst* g = new cn_gst();
   g->N = num_envs; g->H = human_num; g->P = predict_steps; g->device = device;
   g->thr = (float)(robot_radius + human_radius); g->collision_penalty = (float)collision_penalty;
-  g->newest = GST_T - 1; g->finalized = false; g->launches = 0; g->smem = smem; g->tc = nullptr;
+  g->newest = GST_T - 1; g->finalized = false; g->launches = 0; g->smem = smem; g->tc = nullptr; g->compact = true;
   g->ring_pos = nullptr; g->ring_mask = nullptr;
   void* q = nullptr;
   err = cudaMalloc(&q, (size_t)GST_T * num_envs * human_num * 2 * sizeof(float));
@@ -456,6 +459,7 @@ int cn_gst_finalize(cn_gst* g) {
   // default: dense layers as batched tcgen05 GEMMs over all environments (cn_gst_tc.cuh, 2.5x faster at N = 4096);
   // CN_GST_MODE=fused selects the single fused CUDA-core kernel of this file (no workspace, one launch)
   const char* mode = getenv("CN_GST_MODE");
+  g->compact = !(mode && strcmp(mode, "tc") == 0);          // default "tcc": compact rows; "tc": every row
   if (!(mode && strcmp(mode, "fused") == 0)) {
     if (g->tc) { cn_gst_tc_destroy(g->tc); g->tc = nullptr; }
     const float* hp[kNumParams];
@@ -493,6 +497,9 @@ int cn_gst_step(cn_gst* g, const float* d_robot_node, const float* d_spatial2, c
   g->newest = (g->newest + 1) % GST_T;
   if (g->tc) {
     g->launches += 1;
+    if (g->compact)
+      return cn_gst_tcc_step(g->tc, g->ring_pos, g->ring_mask, g->newest, d_robot_node, d_spatial2, d_visible, d_reward, d_penalty,
+                             d_spatial_out, (cudaStream_t)stream);
     return cn_gst_tc_step(g->tc, g->ring_pos, g->ring_mask, g->newest, d_robot_node, d_spatial2, d_visible, d_reward, d_penalty,
                           d_spatial_out, (cudaStream_t)stream);
   }

@@ -289,6 +289,273 @@ __global__ void __launch_bounds__(32) gt_final_kernel(int N, int H, int P, float
   }
 }
 
+// ==========================================================================================================
+// COMPACT path (default).  Every row-wise quantity of the predictor is multiplied by a 0/1 mask: the node embedding by
+// the row's input mask, attention weights by the query's and the key's mask (a masked query's output is exactly 0, a
+// masked key has weight exactly 0), the encoder output by the row mask again before W_ih, the LSTM state by the
+// "visible in the newest frame" flag fp after the observation period and in every decoding step, the prediction by fp.
+// So a masked row carries constants (its Q|K|V row is the bias, its W_ih input is 0 -> its gate pre-activation is
+// b_ih) and a human with fp = 0 carries nothing at all.  With the robot seeing ~4.4 of 20 humans, 78 % of the
+// N*5*H observation rows and of the N*H decoding rows are such constants.  Here only the valid rows exist:
+//   observation period: rows with mask 1, compacted in (env, frame) group order  (count counts[0], group g = e*5+t owns
+//                       compact rows [gstart[g], gstart[g+1]))
+//   LSTM + decoding:    humans with fp = 1, compacted in env order             (count counts[1], env e owns [estart[e], ..))
+// The only place masked rows enter a valid row's arithmetic is the soft-max denominator (soft-max over ALL H neighbours,
+// then mask and renormalise, mha.py:236-242): all masked keys share the key vector b_k, so their H - n terms are
+// (H - n) * exp(q . b_k - max).  Results equal the dense path up to the order of that sum (~1e-9 relative).
+#define GTC_WARPS 8
+
+// one warp per (env, frame) group, lane = human: masks, masked input displacement, group counts, newest-frame bookkeeping
+__global__ void __launch_bounds__(GTC_WARPS * 32) gtc_prep_kernel(int N, int H, float* __restrict__ ring_pos, uint8_t* __restrict__ ring_mask,
+                                                                   int newest, const float* __restrict__ robot, const float* __restrict__ sp2,
+                                                                   const uint8_t* __restrict__ vis, float* __restrict__ rowm,
+                                                                   float* __restrict__ inp, int* __restrict__ gcount,
+                                                                   int* __restrict__ ecount, float* __restrict__ fp,
+                                                                   float* __restrict__ pos_last) {
+  cn_pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * GTC_WARPS + (threadIdx.x >> 5);
+  if (g >= N * GT_T) return;
+  const int e = g / GT_T, t = g - e * GT_T, n = lane;
+  bool valid = false, vnow = false;
+  if (n < H) {
+    auto frame_pos = [&](int tt, float& x, float& y, float& m) {
+      if (tt == GT_T - 1) {
+        x = robot[e * 7] + sp2[((size_t)e * H + n) * 2];
+        y = robot[e * 7 + 1] + sp2[((size_t)e * H + n) * 2 + 1];
+        m = vis[(size_t)e * H + n] ? 1.0f : 0.0f;
+      } else {
+        const int slot = (newest + 1 + tt) % GT_T;
+        const size_t o = ((size_t)slot * N + e) * H + n;
+        x = ring_pos[2 * o]; y = ring_pos[2 * o + 1]; m = (float)ring_mask[o];
+      }
+    };
+    float x, y, m, xp = 0, yp = 0, mp = 0, xl_, yl_, ml_;
+    frame_pos(t, x, y, m);
+    frame_pos(GT_T - 1, xl_, yl_, ml_);
+    if (t > 0) frame_pos(t - 1, xp, yp, mp);
+    const float mrel = t == 0 ? m : mp * ml_;                  // interface.forward:77-78 (sic)
+    const float dx = t == 0 ? 0.0f : x - xp, dy = t == 0 ? 0.0f : y - yp;
+    const size_t r = (size_t)g * H + n;
+    rowm[r] = mrel;
+    inp[2 * r] = GT_INVALID * (1.0f - mrel) + dx * mrel;
+    inp[2 * r + 1] = GT_INVALID * (1.0f - mrel) + dy * mrel;
+    valid = mrel != 0.0f;
+    if (t == GT_T - 1) {
+      const size_t rd = (size_t)e * H + n;
+      fp[rd] = mrel; pos_last[2 * rd] = x; pos_last[2 * rd + 1] = y;
+      vnow = valid;
+    }
+  }
+  const uint32_t b = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) gcount[g] = __popc(b);
+  if (t == GT_T - 1) {
+    const uint32_t bn = __ballot_sync(0xffffffffu, vnow);
+    if (lane == 0) ecount[e] = __popc(bn);
+    // traj_buffer.append / mask_buffer.append.  Other groups of this launch read the newest frame from the observation,
+    // never from this slot (frame_pos), so the write cannot race with them.
+    if (n < H) {
+      const size_t o = ((size_t)newest * N + e) * H + n;
+      ring_pos[2 * o] = robot[e * 7] + sp2[((size_t)e * H + n) * 2];
+      ring_pos[2 * o + 1] = robot[e * 7 + 1] + sp2[((size_t)e * H + n) * 2 + 1];
+      ring_mask[o] = vis[(size_t)e * H + n] ? 1 : 0;
+    }
+  }
+}
+
+// exclusive prefix sums of the group counts (G) and of the per-env visible counts (N); totals -> counts[0], counts[1]
+__global__ void __launch_bounds__(1024) gtc_scan_kernel(const int* __restrict__ gcount, int G, int* __restrict__ gstart,
+                                                        const int* __restrict__ ecount, int N, int* __restrict__ estart,
+                                                        int* __restrict__ counts) {
+  cn_pdl_prologue();
+  __shared__ int part[1024];
+  for (int pass = 0; pass < 2; ++pass) {
+    const int* in = pass ? ecount : gcount;
+    int* out = pass ? estart : gstart;
+    const int L = pass ? N : G;
+    const int per = (L + 1023) / 1024, b0 = threadIdx.x * per;
+    int s = 0;
+    for (int i = b0; i < b0 + per && i < L; ++i) s += in[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                      // Hillis-Steele inclusive scan of the 1024 partials
+      const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+      __syncthreads();
+      part[threadIdx.x] += v;
+      __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;                          // exclusive
+    for (int i = b0; i < b0 + per && i < L; ++i) { out[i] = run; run += in[i]; }
+    if (threadIdx.x == 1023) { out[L] = part[1023]; counts[pass] = part[1023]; }
+    __syncthreads();
+  }
+}
+
+// compaction maps: cidx[r] (compact row or -1), crow[c] (source row), drow[d] (env * H + human of decode row d)
+__global__ void __launch_bounds__(GTC_WARPS * 32) gtc_index_kernel(int N, int H, const float* __restrict__ rowm, const float* __restrict__ fp,
+                                                                    const int* __restrict__ gstart, const int* __restrict__ estart,
+                                                                    int* __restrict__ cidx, int* __restrict__ crow, int* __restrict__ drow) {
+  cn_pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * GTC_WARPS + (threadIdx.x >> 5);
+  if (g >= N * GT_T) return;
+  const int e = g / GT_T, t = g - e * GT_T;
+  const size_t r = (size_t)g * H + lane;
+  const bool valid = lane < H && rowm[r] != 0.0f;
+  const uint32_t b = __ballot_sync(0xffffffffu, valid);
+  const int c = gstart[g] + __popc(b & ((1u << lane) - 1u));
+  if (lane < H) cidx[r] = valid ? c : -1;
+  if (valid) crow[c] = (int)r;
+  if (t == GT_T - 1) {
+    const size_t rd = (size_t)e * H + lane;
+    const bool vnow = lane < H && fp[rd] != 0.0f;
+    const uint32_t bn = __ballot_sync(0xffffffffu, vnow);
+    if (vnow) drow[estart[e] + __popc(bn & ((1u << lane) - 1u))] = (int)rd;
+  }
+}
+
+// node embedding + norm_node of the compact rows (mask == 1).  src: crow (observation period, input from inp[row]) or
+// null (decoding: input = xin[c]).  One warp per row, grid-stride.
+__global__ void __launch_bounds__(256) gtc_embed_kernel(GstTcW w, const int* __restrict__ count, const int* __restrict__ src,
+                                                        const float* __restrict__ in2, float* __restrict__ X0, __half* __restrict__ xh,
+                                                        __half* __restrict__ xl) {
+  cn_pdl_prologue();
+  const int lane = threadIdx.x & 31, C = cn_ld_after_wait(count);
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < C; c += (gridDim.x * blockDim.x) >> 5) {
+    const int r = src ? src[c] : c;
+    const float ix = in2[2 * (size_t)r], iy = in2[2 * (size_t)r + 1];
+    const float e0 = fmaf(iy, w.We_t[64 + lane], fmaf(ix, w.We_t[lane], w.be[lane]));
+    const float e1 = fmaf(iy, w.We_t[96 + lane], fmaf(ix, w.We_t[32 + lane], w.be[32 + lane]));
+    float o0, o1;
+    gt_ln(e0, e1, w.ln0_g, w.ln0_b, lane, o0, o1);
+    const size_t b = (size_t)c * 64;
+    X0[b + lane] = o0; X0[b + lane + 32] = o1;
+    gt_split_store(xh, xl, b + lane, o0); gt_split_store(xh, xl, b + lane + 32, o1);
+  }
+}
+
+// attention within a group's compact rows [start[g], start[g+1]); the H - n masked neighbours enter the soft-max
+// denominator through their common key b_k (see the header of this section).  One CTA per group.
+__global__ void __launch_bounds__(8 * GT_MAXH) gtc_attn_kernel(int H, const int* __restrict__ start, const float* __restrict__ qkv,
+                                                               const float* __restrict__ bk /* b_in + 64 */, __half* __restrict__ ah,
+                                                               __half* __restrict__ al) {
+  cn_pdl_prologue();
+  __shared__ __align__(16) float sq[GT_MAXH * 192];
+  const int c0 = cn_ld_after_wait(start + blockIdx.x), ng = cn_ld_after_wait(start + blockIdx.x + 1) - c0;
+  if (ng <= 0) return;
+  for (int i = threadIdx.x; i < ng * 48; i += blockDim.x)
+    reinterpret_cast<float4*>(sq)[i] = __ldg(reinterpret_cast<const float4*>(qkv + (size_t)c0 * 192) + i);
+  __syncthreads();
+  const int lr = threadIdx.x >> 3, hd = threadIdx.x & 7;
+  if (lr >= ng) return;
+  const float scaling = 0.35355339059327373f;
+  float q[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) q[d] = sq[lr * 192 + hd * 8 + d] * scaling;
+  const int nmask = H - ng;
+  float sm = 0.0f;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) sm = fmaf(q[d], __ldg(bk + hd * 8 + d), sm);
+  float mx = nmask > 0 ? sm : -INFINITY;
+  for (int j = 0; j < ng; ++j) {
+    const float* kj = sq + j * 192 + 64 + hd * 8;
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) s = fmaf(q[d], kj[d], s);
+    mx = fmaxf(mx, s);
+  }
+  float den = 0.0f, dm = 0.0f, o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < ng; ++j) {
+    const float* kj = sq + j * 192 + 64 + hd * 8;
+    const float* vj = sq + j * 192 + 128 + hd * 8;
+    float s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) s = fmaf(q[d], kj[d], s);
+    const float ex = expf(s - mx);
+    den += ex;
+    dm += ex;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] = fmaf(ex, vj[d], o[d]);
+  }
+  if (nmask > 0) den += (float)nmask * expf(sm - mx);
+  const float scale = (1.0f / den) / (dm / den + 1e-10f);
+  const size_t ob = (size_t)(c0 + lr) * 64 + hd * 8;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) gt_split_store(ah, al, ob + d, o[d] * scale);
+}
+
+// X1 = X0 + O, Y = norm1(X1) (compact rows, grid-stride)
+__global__ void __launch_bounds__(256) gtc_res_ln_kernel(GstTcW w, const int* __restrict__ count, const float* __restrict__ X0,
+                                                         const float* __restrict__ O, float* __restrict__ X1, __half* __restrict__ yh,
+                                                         __half* __restrict__ yl) {
+  cn_pdl_prologue();
+  const int lane = threadIdx.x & 31, C = cn_ld_after_wait(count);
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < C; c += (gridDim.x * blockDim.x) >> 5) {
+    const size_t b = (size_t)c * 64;
+    const float a0 = X0[b + lane] + O[b + lane], a1 = X0[b + lane + 32] + O[b + lane + 32];
+    X1[b + lane] = a0; X1[b + lane + 32] = a1;
+    float o0, o1;
+    gt_ln(a0, a1, w.ln1_g, w.ln1_b, lane, o0, o1);
+    gt_split_store(yh, yl, b + lane, o0); gt_split_store(yh, yl, b + lane + 32, o1);
+  }
+}
+
+// XS = X1 + O2 (row mask == 1) as fp16 hi / lo
+__global__ void __launch_bounds__(256) gtc_res_kernel(const int* __restrict__ count, const float* __restrict__ X1,
+                                                      const float* __restrict__ O2, __half* __restrict__ sh, __half* __restrict__ sl) {
+  cn_pdl_prologue();
+  const size_t total = (size_t)cn_ld_after_wait(count) * 64;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    gt_split_store(sh, sl, i, X1[i] + O2[i]);
+}
+
+// LSTM cell over the compact decode rows.  t >= 0: observation frame t, the row's gate input is GX[cidx] or, when that
+// frame of the human is masked, the constant b_ih;  t < 0: decoding, gate input GX[d].  Also initialises (t == 0).
+__global__ void __launch_bounds__(256) gtc_cell_kernel(int H, int t, const int* __restrict__ count, const int* __restrict__ drow,
+                                                       const int* __restrict__ cidx, const float* __restrict__ GX,
+                                                       const float* __restrict__ bih, const float* __restrict__ bhh,
+                                                       const float* __restrict__ GH, float* __restrict__ h32,
+                                                       float* __restrict__ c32, __half* __restrict__ hh, __half* __restrict__ hl) {
+  cn_pdl_prologue();
+  const size_t total = (size_t)cn_ld_after_wait(count) * 64;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 63);
+    const size_t d = i >> 6;
+    const float* gx;
+    if (t >= 0) {
+      const int rd = drow[d], e = rd / H, n = rd - e * H;
+      const int c = cidx[((size_t)e * GT_T + t) * H + n];
+      gx = c >= 0 ? GX + (size_t)c * 256 : bih;
+    } else {
+      gx = GX + d * 256;
+    }
+    const float* gh = t == 0 ? bhh : GH + d * 256;            // h0 = 0: W_hh h + b_hh = b_hh
+    const float cprev = t == 0 ? 0.0f : c32[i];
+    const float ig = gt_sigmoid(gx[j] + gh[j]), fg = gt_sigmoid(gx[64 + j] + gh[64 + j]);
+    const float gg = tanhf(gx[128 + j] + gh[128 + j]), og = gt_sigmoid(gx[192 + j] + gh[192 + j]);
+    const float c2 = fg * cprev + ig * gg, h2 = og * tanhf(c2);
+    c32[i] = c2; h32[i] = h2;
+    gt_split_store(hh, hl, i, h2);
+  }
+}
+
+// hidden2pos (mean only) of the compact decode rows -> next input, cumulative mean, predicted world position
+__global__ void __launch_bounds__(256) gtc_h2p_kernel(GstTcW w, int tt, const int* __restrict__ count, const int* __restrict__ drow,
+                                                      const float* __restrict__ h32, const float* __restrict__ pos_last,
+                                                      float* __restrict__ xin, float* __restrict__ mu_cum, float* __restrict__ pred) {
+  cn_pdl_prologue();
+  const int total = cn_ld_after_wait(count) * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int d = i >> 1, dim = i & 1, rd = drow[d];
+    float a = w.bp[dim];
+    for (int k = 0; k < 64; ++k) a = fmaf(h32[(size_t)d * 64 + k], w.Wp[dim * 64 + k], a);
+    xin[i] = a;
+    const float cum = (tt == 0 ? 0.0f : mu_cum[i]) + a;
+    mu_cum[i] = cum;
+    pred[((size_t)rd * GT_T + tt) * 2 + dim] = cum + pos_last[2 * (size_t)rd + dim];
+  }
+}
+
 struct GstTc {
   cn_policy* ctx;
   int N, H, P;
@@ -297,6 +564,9 @@ struct GstTc {
   TcMat tWin, tWout, tW1, tW2, tWih, tWhh;                   // weights (x 2^6, fp16 hi/lo)
   TcMat tX, tA, tY, tF, tXS, tHd;                            // activations (fp16 hi/lo A operands)
   float *X0, *QKV, *O, *X1, *GX, *GH, *rowm, *fp, *pos_last, *h32, *c32, *mu_cum, *xin, *pred;
+  // compact path (cn_gst_tcc_step): only rows whose mask is 1 are computed
+  float* inp;                                                // [R, 2] masked input displacement of every (env, frame, human) row
+  int *cidx, *crow, *gcount, *gstart, *ecount, *estart, *drow, *counts;   // compaction maps (see gtc_* kernels)
 };
 
 int gt_upload(cn_policy* ctx, const float** dst, const float* src, size_t count) {
@@ -350,7 +620,12 @@ void* cn_gst_tc_create(int N, int H, int P, float thr, float pen, int device, co
 #define GA(name, count) if (!rc) rc = palloc(ctx, &g->name, (count))
   GA(X0, R * 64); GA(QKV, R * 192); GA(O, R * 64); GA(X1, R * 64); GA(GX, R * 256); GA(GH, Rd * 256); GA(rowm, R); GA(fp, Rd);
   GA(pos_last, Rd * 2); GA(h32, Rd * 64); GA(c32, Rd * 64); GA(mu_cum, Rd * 2); GA(xin, Rd * 2); GA(pred, Rd * GT_T * 2);
+  GA(inp, R * 2);
 #undef GA
+#define GI(name, count) if (!rc) { float* q_ = nullptr; rc = palloc(ctx, &q_, (count)); g->name = reinterpret_cast<int*>(q_); }
+  GI(cidx, R); GI(crow, R); GI(gcount, (size_t)N * GT_T); GI(gstart, (size_t)N * GT_T + 1); GI(ecount, N); GI(estart, N + 1);
+  GI(drow, Rd); GI(counts, 4);
+#undef GI
   if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = cn_set_error("gst tc: setup failed");
   if (rc) { return nullptr; }
   return g;
@@ -410,6 +685,59 @@ int cn_gst_tc_step(void* handle, float* ring_pos, uint8_t* ring_mask, int newest
            out_sp);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("gst tc step: %s", cudaGetErrorString(err));
+  if (p->launch_error) { p->launch_error = false; return 1; }
+  return 0;
+}
+
+// Compact variant of cn_gst_tc_step (default): same outputs, only the valid rows are computed.
+int cn_gst_tcc_step(void* handle, float* ring_pos, uint8_t* ring_mask, int newest, const float* robot, const float* sp2,
+                    const uint8_t* vis, float* reward, float* penalty, float* out_sp, cudaStream_t st) {
+  GstTc* g = static_cast<GstTc*>(handle);
+  cn_policy* p = g->ctx;
+  const int N = g->N, H = g->H;
+  const int R = N * GT_T * H, Rd = N * H, G = N * GT_T;
+  p->dbg_launch_idx = 0;
+  const int* cntR = g->counts;          // valid observation rows
+  const int* cntD = g->counts + 1;      // humans visible in the newest frame
+  const dim3 rows_grid((unsigned)(p->num_sms * 4)), grp_grid((unsigned)((G + GTC_WARPS - 1) / GTC_WARPS));
+  auto encoder = [&](int maxrows, const int* cnt, int groups, const int* start) {
+    gemm_tc(p, st, g->tX, g->tWin, maxrows, 192, 64, 64, g->w.bin, CN_ACT_NONE, out32(g->QKV, 192), cnt);
+    launch_k(p, gtc_attn_kernel, dim3((unsigned)groups), dim3((unsigned)(8 * H)), 0, st, H, start, g->QKV, g->w.bin + 64, g->tA.hi, g->tA.lo);
+    gemm_tc(p, st, g->tA, g->tWout, maxrows, 64, 64, 64, g->w.bout, CN_ACT_NONE, out32(g->O, 64), cnt);
+    launch_k(p, gtc_res_ln_kernel, rows_grid, dim3(256), 0, st, g->w, cnt, g->X0, g->O, g->X1, g->tY.hi, g->tY.lo);
+    gemm_tc(p, st, g->tY, g->tW1, maxrows, 128, 64, 64, g->w.b1, CN_ACT_RELU, out16(g->tF), cnt);
+    gemm_tc(p, st, g->tF, g->tW2, maxrows, 64, 128, 64, g->w.b2, CN_ACT_NONE, out32(g->O, 64), cnt);
+    launch_k(p, gtc_res_kernel, rows_grid, dim3(256), 0, st, cnt, g->X1, g->O, g->tXS.hi, g->tXS.lo);
+    gemm_tc(p, st, g->tXS, g->tWih, maxrows, 256, 64, 256, g->w.bih, CN_ACT_NONE, out32(g->GX, 256), cnt);
+  };
+  launch_k(p, gtc_prep_kernel, grp_grid, dim3(GTC_WARPS * 32), 0, st, N, H, ring_pos, ring_mask, newest, robot, sp2, vis, g->rowm, g->inp,
+           g->gcount, g->ecount, g->fp, g->pos_last);
+  launch_k(p, gtc_scan_kernel, dim3(1), dim3(1024), 0, st, g->gcount, G, g->gstart, g->ecount, N, g->estart, g->counts);
+  launch_k(p, gtc_index_kernel, grp_grid, dim3(GTC_WARPS * 32), 0, st, N, H, g->rowm, g->fp, g->gstart, g->estart, g->cidx, g->crow,
+           g->drow);
+  launch_k(p, gtc_embed_kernel, rows_grid, dim3(256), 0, st, g->w, cntR, g->crow, g->inp, g->X0, g->tX.hi, g->tX.lo);
+  encoder(R, cntR, G, g->gstart);
+  // LSTM over the 5 observed frames, humans visible now only (h0 = c0 = 0: frame 0 has no recurrent GEMM, its
+  // hidden-state gate term is b_hh)
+  for (int t = 0; t < GT_T; ++t) {
+    if (t > 0) gemm_tc(p, st, g->tHd, g->tWhh, Rd, 256, 64, 256, g->w.bhh, CN_ACT_NONE, out32(g->GH, 256), cntD);
+    launch_k(p, gtc_cell_kernel, rows_grid, dim3(256), 0, st, H, t, cntD, g->drow, g->cidx, g->GX, g->w.bih, g->w.bhh, g->GH, g->h32,
+             g->c32, g->tHd.hi, g->tHd.lo);
+  }
+  for (int tt = 0; tt < GT_T; ++tt) {
+    if (tt > 0) {
+      launch_k(p, gtc_embed_kernel, rows_grid, dim3(256), 0, st, g->w, cntD, (const int*)nullptr, g->xin, g->X0, g->tX.hi, g->tX.lo);
+      encoder(Rd, cntD, N, g->estart);
+      gemm_tc(p, st, g->tHd, g->tWhh, Rd, 256, 64, 256, g->w.bhh, CN_ACT_NONE, out32(g->GH, 256), cntD);
+      launch_k(p, gtc_cell_kernel, rows_grid, dim3(256), 0, st, H, -1, cntD, g->drow, g->cidx, g->GX, g->w.bih, g->w.bhh, g->GH, g->h32,
+               g->c32, g->tHd.hi, g->tHd.lo);
+    }
+    launch_k(p, gtc_h2p_kernel, rows_grid, dim3(256), 0, st, g->w, tt, cntD, g->drow, g->h32, g->pos_last, g->xin, g->mu_cum, g->pred);
+  }
+  launch_k(p, gt_final_kernel, dim3((unsigned)N), dim3(32), 0, st, N, H, g->P, g->thr, g->pen, robot, sp2, g->fp, g->pred, reward, penalty,
+           out_sp);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return cn_set_error("gst tcc step: %s", cudaGetErrorString(err));
   if (p->launch_error) { p->launch_error = false; return 1; }
   return 0;
 }

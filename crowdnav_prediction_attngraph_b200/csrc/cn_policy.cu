@@ -36,6 +36,7 @@ struct cn_policy {
   int64_t launches;
   int num_sms;
   bool pdl;           // programmatic dependent launch along the kernel chain (CN_PDL=0 disables)
+  long dbg_launch_idx = 0;   // launch index within the current step (CN_PDL_WINDOW debugging)
   bool launch_error;  // a launch or a GEMM output map failed (cn_last_error has the stage and the reason)
   const char* cur_stage = nullptr;   // stage name of the launches being enqueued (error reports)
   int qkv_chunks;     // 1 (default): single pass; 2 (CN_QKV_CHUNKS=2): QKV + attention in two row chunks with overlap
@@ -190,7 +191,15 @@ void launch_k(cn_policy* p, void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = p->pdl ? 1 : 0;
+  // debug aid: CN_PDL_WINDOW=lo:hi keeps the attribute only for launches lo <= index < hi of the context
+  static int win_lo = -1, win_hi = -1;
+  if (win_lo < 0) {
+    const char* w = getenv("CN_PDL_WINDOW");
+    win_lo = 0; win_hi = 1 << 30;
+    if (w) sscanf(w, "%d:%d", &win_lo, &win_hi);
+  }
+  const long idx = p->dbg_launch_idx++;
+  cfg.attrs = at; cfg.numAttrs = (p->pdl && idx >= win_lo && idx < win_hi) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
   if (e != cudaSuccess && !p->launch_error) {     // keep the FIRST failure and the stage it happened in
     p->launch_error = true;

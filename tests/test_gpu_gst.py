@@ -52,9 +52,9 @@ def _unsort(sp2, rows):
     return out
 
 
-@pytest.fixture(params=["tc", "fused"], autouse=True)
+@pytest.fixture(params=["tcc", "tc", "fused"], autouse=True)
 def gst_mode(request, monkeypatch):
-    """both implementations: batched tcgen05 GEMMs (default) and the single fused CUDA-core kernel"""
+    """all three implementations: compact-row tcgen05 GEMMs (default), dense-row tcgen05 GEMMs, single fused CUDA-core kernel"""
     monkeypatch.setenv("CN_GST_MODE", request.param)
     return request.param
 
