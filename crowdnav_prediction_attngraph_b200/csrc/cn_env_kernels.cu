@@ -754,7 +754,7 @@ int cn_env_destroy(cn_env* env) {
 
 int cn_env_reset(cn_env* env, const cn_obs_ptrs* d_obs, void* stream) {
   if (!env || !d_obs) return cn_set_error("cn_env_reset: null argument");
-  cudaSetDevice(env->device);
+  CnDeviceGuard guard(env->device);
   // a reset of the whole vec env restarts Monitor bookkeeping but NOT case_counter (it keeps advancing)
   return launch_step(env, nullptr, d_obs, nullptr, 1, (cudaStream_t)stream);
 }
@@ -764,7 +764,7 @@ int cn_env_step(cn_env* env, const float* d_action, const cn_obs_ptrs* d_obs, co
   if (!env || !d_action || !d_obs || !d_out) return cn_set_error("cn_env_step: null argument");
   if (!d_out->reward || !d_out->done || !d_out->info || !d_out->info_aux || !d_out->ep_ret || !d_out->ep_len)
     return cn_set_error("cn_env_step: every cn_step_ptrs field must be set");
-  cudaSetDevice(env->device);
+  CnDeviceGuard guard(env->device);
   return launch_step(env, d_action, d_obs, d_out, 0, (cudaStream_t)stream);
 }
 
@@ -828,13 +828,22 @@ int cn_copy_segments(const cn_copy_seg* segs, int n, int device, void* stream) {
     p.s[i] = segs[i];
     if (segs[i].bytes > maxb) maxb = segs[i].bytes;
   }
-  cudaSetDevice(device);
+  CnDeviceGuard guard(device);
   size_t blocks = (maxb / 16 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 1184) blocks = 1184;
   cn_copy_segments_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_copy_segments launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+int cn_fetch_sync(void* h_dst, const void* d_src, size_t bytes, int device, void* stream) {
+  if (!h_dst || !d_src) return cn_set_error("cn_fetch_sync: null argument");
+  CnDeviceGuard guard(device);
+  cudaError_t err = cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize((cudaStream_t)stream);
+  if (err != cudaSuccess) return cn_set_error("cn_fetch_sync: %s", cudaGetErrorString(err));
   return 0;
 }
 

@@ -493,7 +493,7 @@ int cn_gst_step(cn_gst* g, const float* d_robot_node, const float* d_spatial2, c
                 float* d_penalty, float* d_spatial_out, void* stream) {
   if (!g || !d_robot_node || !d_spatial2 || !d_visible || !d_spatial_out) return cn_set_error("cn_gst_step: null argument");
   if (!g->finalized) return cn_set_error("cn_gst_step: call cn_gst_finalize after setting the parameters");
-  cudaSetDevice(g->device);
+  CnDeviceGuard guard(g->device);
   g->newest = (g->newest + 1) % GST_T;
   if (g->tc) {
     g->launches += 1;

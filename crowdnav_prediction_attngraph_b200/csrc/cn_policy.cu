@@ -22,6 +22,7 @@
 #include "cn_host_util.h"
 #include "cn_policy_kernels.cuh"
 #include "cn_gemm_tc.cuh"
+#include "cn_qkv_attn.cuh"
 
 // A split-fp16 matrix [rows, K] (row pitch `pitch` elements) and its TMA descriptors.
 struct TcMat {
@@ -39,6 +40,12 @@ struct cn_policy {
   long dbg_launch_idx = 0;   // launch index within the current step (CN_PDL_WINDOW debugging)
   bool launch_error;  // a launch or a GEMM output map failed (cn_last_error has the stage and the reason)
   const char* cur_stage = nullptr;   // stage name of the launches being enqueued (error reports)
+  bool fuse_qkv;      // QKV projection + human-human attention in ONE kernel (cn_qkv_attn.cuh; CN_FUSE_QKV=0 disables)
+  TcMat tWqkvH;       // folded QKV weight, rows head-major: [8][Q 64 | K 64 | V 64][512]
+  CUtensorMap qa_ah, qa_al, qa_bh, qa_bl;   // 32-wide (SWIZZLE_64B) boxes of tE2 and tWqkvH for the fused kernel
+  float* bqkvH = nullptr;
+  int* tile_tab = nullptr;   // row tiles of the fused kernel (cn_qkv_tiles_kernel)
+  cudaEvent_t ev_tiles;
   int qkv_chunks;     // 1 (default): single pass; 2 (CN_QKV_CHUNKS=2): QKV + attention in two row chunks with overlap
   bool finalized;
   std::map<std::string, std::vector<float>> host;
@@ -116,16 +123,17 @@ EncodeFn get_encode() {
 }
 
 // 2-D fp16 row-major [rows, K] tensor with row pitch `pitch`, box = 64 (K) x box_rows, 128-byte swizzle
-int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch) {
+// (box_k = 32: 64-byte rows with SWIZZLE_64B, the half-width K blocks of cn_qkv_attn.cuh)
+int make_map(CUtensorMap* map, const __half* ptr, int rows, int K, int box_rows, int pitch, int box_k = TC_BK) {
   EncodeFn enc = get_encode();
   if (!enc) return cn_set_error("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cn_set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K);
   return 0;
 }
@@ -254,6 +262,8 @@ int tc_set_attrs() {
                                        TcCfg<256>::kSmemBytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(cn_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::kSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(cn_qkv_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM_BYTES);
   if (e != cudaSuccess) return cn_set_error("cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e));
   return 0;
 }
@@ -324,7 +334,10 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
     p->pdl = !(pd && pd[0] == '0');
     const char* qc = getenv("CN_QKV_CHUNKS");
     p->qkv_chunks = (qc && qc[0] == '2') ? 2 : 1;
+    const char* fq = getenv("CN_FUSE_QKV");
+    p->fuse_qkv = cfg->gemm_mode == 1 && p->qkv_chunks == 1 && !(fq && fq[0] == '0') && p->N <= QA_MAX_ENVS && p->H <= 128;
   }
+  cudaEventCreateWithFlags(&p->ev_tiles, cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&p->st3, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&p->ev_fork3, cudaEventDisableTiming);
@@ -345,6 +358,8 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
     p->mc = reinterpret_cast<int*>(q);
     if (!rc) rc = palloc(p, &q, M + 1);
     p->row_env = reinterpret_cast<int*>(q);
+    if (!rc) rc = palloc(p, &q, 2 * N + 4);
+    p->tile_tab = reinterpret_cast<int*>(q);
   }
   WS(x16, M * 16); WS(e1, M * 128); WS(e2, M * 512); WS(qkv, M * 1536); WS(ao, M * 512); WS(sout, M * 256);
   WS(xr, N * 16); WS(rs, N * 256); WS(t1, N * 128); WS(u, N * 256); WS(wv, N * 256); WS(h0, N * 128);
@@ -381,7 +396,7 @@ int cn_policy_destroy(cn_policy* p) {
   for (auto& e : p->ev) cudaEventDestroy(e);
   if (p->st2) {
     cudaStreamDestroy(p->st2);
-    cudaStreamDestroy(p->st3); cudaEventDestroy(p->ev_fork3); cudaEventDestroy(p->ev_join3);
+    cudaStreamDestroy(p->st3); cudaEventDestroy(p->ev_fork3); cudaEventDestroy(p->ev_join3); cudaEventDestroy(p->ev_tiles);
     cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); cudaEventDestroy(p->ev_fork2); cudaEventDestroy(p->ev_join2);
   }
   delete p;
@@ -521,6 +536,20 @@ int cn_policy_finalize(cn_policy* p, void* stream) {
       if (rc) return rc;
       split16(p, st, t.src, 64.0f, t.t->hi, t.t->lo, (size_t)t.rows * t.k);
     }
+    if (p->fuse_qkv) {
+      // head-major copy of the folded QKV projection for the fused kernel: row h * 192 + s * 64 + d <- row s * 512 + h * 64 + d
+      float* wh = nullptr;
+      rc = palloc(p, &wh, (size_t)1536 * 512);
+      if (!rc) rc = palloc(p, &p->bqkvH, 1536);
+      if (!rc) rc = tc_alloc(p, p->tWqkvH, 1536, 512, QA_BN);
+      if (!rc) rc = make_map(&p->qa_bh, p->tWqkvH.hi, 1536, 512, QA_BN, 512, QA_BK);
+      if (!rc) rc = make_map(&p->qa_bl, p->tWqkvH.lo, 1536, 512, QA_BN, 512, QA_BK);
+      if (!rc) rc = make_map(&p->qa_ah, p->tE2.hi, p->M, 512, TC_BM, 512, QA_BK);
+      if (!rc) rc = make_map(&p->qa_al, p->tE2.lo, p->M, 512, TC_BM, 512, QA_BK);
+      if (rc) return rc;
+      cn_head_major_kernel<<<1536, 128, 0, st>>>(p->Wqkv, p->bqkv, wh, p->bqkvH);
+      split16(p, st, wh, 64.0f, p->tWqkvH.hi, p->tWqkvH.lo, (size_t)1536 * 512);
+    }
   }
   cudaError_t err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) return cn_set_error("cn_policy_finalize: %s", cudaGetErrorString(err));
@@ -534,7 +563,7 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   if (!d->robot_node || !d->temporal_edges || !d->spatial_edges || !d->detected_human_num || !d->h_in || !d->masks ||
       !d->value || !d->action || !d->log_prob || !d->h_out)
     return cn_set_error("cn_policy_act: missing input/output pointer");
-  cudaSetDevice(p->cfg.device);
+  CnDeviceGuard guard(p->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   const int N = p->N, H = p->H, M = p->M;
   const bool tcm = p->cfg.gemm_mode == 1;
@@ -554,6 +583,11 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
   cudaStream_t s2 = p->st2;
   cudaEventRecord(p->ev_fork, st);
   cudaStreamWaitEvent(s2, p->ev_fork, 0);
+  if (p->fuse_qkv) {
+    cn_qkv_tiles_kernel<<<1, 1024, 0, s2>>>(p->row_start, N, p->tile_tab);
+    p->launches += 1;
+    cudaEventRecord(p->ev_tiles, s2);
+  }
   if (tcm) {
     gemm(p, s2, p->xr, 16, p->Wr, 16, p->br, nullptr, 256, N, 256, 16, CN_ACT_RELU, 0, ALL, nullptr, p->tRs.hi, p->tRs.lo);
     gemm_tc(p, s2, p->tRs, p->tWet, N, 128, 256, 64, p->bet, CN_ACT_RELU, out_both(p->t1, 128, p->tT1), nullptr, 0, 64);
@@ -583,7 +617,14 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
     const int* mid = p->row_start + N / 2;
     __half* ah = p->tAo.hi;
     __half* al = p->tAo.lo;
-    if (p->qkv_chunks == 1) {
+    if (p->fuse_qkv) {
+      // one kernel: projection tile (128 rows of whole environments x one head's Q | K | V) -> attention -> tAo
+      cudaStreamWaitEvent(st, p->ev_tiles, 0);                 // tile table from the side stream
+      launch_k(p, cn_qkv_attn_kernel, dim3(p->num_sms), dim3(QA_THREADS), QA_SMEM_BYTES, st, p->qa_ah, p->qa_al, p->qa_bh,
+               p->qa_bl, p->bqkvH, 1.0f / 64.0f, p->tile_tab, p->row_start, p->row_env, ah, al,
+               getenv("CN_QA_DBG") ? atoi(getenv("CN_QA_DBG")) : 0);
+      mark(p, st, 4);
+    } else if (p->qkv_chunks == 1) {
       gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc);
       mark(p, st, 4);
       launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, nullptr,

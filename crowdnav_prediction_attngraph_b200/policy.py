@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from . import _capi
 
 HIDDEN = 128
+NOISE_BLOCK = 32          # rollout steps of action noise drawn per generator call (CudaPolicy.act)
 
 
 class _AddBias(nn.Module):
@@ -108,7 +109,7 @@ class CudaPolicy(object):
         self._gen = None
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return _capi.raw_stream(self.device.index or 0)
 
     def load_state_dict(self, sd):
         for k, v in sd.items():
@@ -141,20 +142,32 @@ class CudaPolicy(object):
                     and torch.distributed.get_world_size() > 1:
                 self._gen = torch.Generator(device=self.device)
                 self._gen.manual_seed(torch.initial_seed() + 7919 * torch.distributed.get_rank())
-            noise = torch.randn(N, 2, device=self.device, generator=self._gen)
+            # one generator call serves NOISE_BLOCK steps (a torch.randn launch costs ~10 us of host time per step)
+            # The block is dropped when the generator was re-seeded or used by anyone else in between, so
+            # torch.manual_seed(s) followed by act() still restarts the noise sequence.
+            g = self._gen if self._gen is not None else torch.cuda.default_generators[self.device.index or 0]
+            nb = self.__dict__.get("_noise_block")
+            if nb is None or self._noise_i >= nb.shape[0] or self._noise_state != (g.initial_seed(), g.get_offset()):
+                nb = self._noise_block = torch.randn(NOISE_BLOCK, N, 2, device=self.device, generator=self._gen)
+                self._noise_i = 0
+                self._noise_state = (g.initial_seed(), g.get_offset())
+            noise = nb[self._noise_i]
+            self._noise_i += 1
         sp = obs["spatial_edges"]
         args = dict(robot_node=obs["robot_node"], temporal_edges=obs["temporal_edges"], spatial_edges=sp,
                     detected_human_num=obs["detected_human_num"], h_in=h, masks=masks)
+        f32, dev = torch.float32, self.device
         for k, t in args.items():
-            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
-                args[k] = t.to(self.device, torch.float32).contiguous()
+            if t.dtype is not f32 or not t.is_contiguous() or t.device != dev:
+                args[k] = t.to(dev, f32).contiguous()
         ptrs = _capi.CnActPtrs(
             args["robot_node"].data_ptr(), args["temporal_edges"].data_ptr(), args["spatial_edges"].data_ptr(),
             args["detected_human_num"].data_ptr(), args["h_in"].data_ptr(), args["masks"].data_ptr(),
             None if deterministic else noise.data_ptr(), b["value"].data_ptr(), b["action"].data_ptr(),
             b["log_prob"].data_ptr(), b["h_out"].data_ptr(), b["mean"].data_ptr())
-        with torch.cuda.device(self.device):
-            _capi.check(self.lib, self.lib.cn_policy_act(self._h, C.byref(ptrs), self._stream()), "cn_policy_act")
+        rc = self.lib.cn_policy_act(self._h, C.byref(ptrs), self._stream())     # restores the caller's device itself
+        if rc:
+            _capi.check(self.lib, rc, "cn_policy_act")
         self._keep = (args, noise)      # keep inputs alive until the kernels are enqueued behind the next call
         if return_mean:
             return b["value"], b["action"], b["log_prob"], b["h_out"], b["mean"]
@@ -230,11 +243,11 @@ class Policy(nn.Module):
         plist = self.__dict__.get("_plist")
         if plist is None:
             plist = self.__dict__["_plist"] = list(self.parameters())
-        v, a = 0, 0
+        v = 0
         for p in plist:
             v += p._version
-            a ^= p.data_ptr()             # .to() / .data swaps replace storage without bumping the version
-        ver = (v, a)
+        # .to() / .data swaps replace storage without bumping the version: they move every parameter, watch the two ends
+        ver = (v, plist[0].data_ptr(), plist[-1].data_ptr())
         if ver != self._cuda_version:                       # parameters changed (optimizer step / load_state_dict)
             self._cuda.load_state_dict(self.state_dict())
             self._cuda_version = ver

@@ -52,42 +52,61 @@ class RolloutStorage(object):
             setattr(self, name, getattr(self, name).to(dev))
         self.device = dev
 
+    def _slot_table(self):
+        """Per step index: the destination tensors of insert() with their device pointers and byte sizes, built once per
+        device (the storage tensors are never reallocated except by .to(), which drops the table)."""
+        tab = []
+        for s in range(self.num_steps):
+            dst = [self.obs[key][s + 1] for key in self.obs]
+            dst += [self.recurrent_hidden_states['human_node_rnn'][s + 1], self.actions[s], self.action_log_probs[s],
+                    self.value_preds[s], self.rewards[s], self.masks[s + 1], self.bad_masks[s + 1]]
+            tab.append([(d, d.data_ptr(), d.numel() * d.element_size()) for d in dst])
+        return tab
+
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs, value_preds, rewards, masks, bad_masks=None):
-        """rl/networks/storage.py:70-86.  Device-resident sources (observations, hidden state, action, log-prob,
-        value) are copied by ONE cn_copy_segments launch instead of nine torch copy_ calls; host tensors
-        (reward / masks built by the caller from `done`) take the usual async H2D copies."""
+        """rl/networks/storage.py:70-86.  Every source that the GPU can read directly -- device tensors (observations,
+        hidden state, action, log-prob, value) and PINNED host tensors (reward / masks built by the caller from `done`)
+        -- is copied by ONE cn_copy_segments launch instead of twelve torch copy_ calls; pageable host tensors (what the
+        reference's train.py builds) take the usual H2D copy_."""
         s = self.step
-        pairs = [(self.obs[key][s + 1], obs[key]) for key in self.obs]
-        pairs.append((self.recurrent_hidden_states['human_node_rnn'][s + 1], recurrent_hidden_states['human_node_rnn']))
-        pairs.append((self.actions[s], actions))
-        pairs.append((self.action_log_probs[s], action_log_probs))
-        pairs.append((self.value_preds[s], value_preds))
-        pairs.append((self.rewards[s], rewards.reshape(-1, 1)))
-        pairs.append((self.masks[s + 1], masks))
-        if bad_masks is not None:
-            pairs.append((self.bad_masks[s + 1], bad_masks))
-        segs = None
-        if self.device.type == "cuda":
-            segs = self.__dict__.get("_segs")
-            if segs is None:
-                from . import _capi
-                self._lib = _capi.load_library()
-                segs = self._segs = (_capi.CnCopySeg * 16)()
-        n = 0
-        for dst, src in pairs:
-            if (segs is not None and n < 16 and src.is_cuda and src.device == dst.device and src.dtype == dst.dtype
-                    and src.is_contiguous() and src.numel() == dst.numel()):
-                if src.data_ptr() != dst.data_ptr():
+        srcs = [obs[key] for key in self.obs]
+        srcs += [recurrent_hidden_states['human_node_rnn'], actions, action_log_probs, value_preds, rewards, masks, bad_masks]
+        if self.device.type != "cuda":
+            dsts = [self.obs[key][s + 1] for key in self.obs]
+            dsts += [self.recurrent_hidden_states['human_node_rnn'][s + 1], self.actions[s], self.action_log_probs[s],
+                     self.value_preds[s], self.rewards[s], self.masks[s + 1], self.bad_masks[s + 1]]
+            for dst, src in zip(dsts, srcs):
+                if src is not None:
+                    dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src)
+            self.step = (s + 1) % self.num_steps
+            return
+        d = self.__dict__
+        segs = d.get("_segs")
+        if segs is None:
+            from . import _capi
+            self._capi, self._lib = _capi, _capi.load_library()
+            segs = self._segs = (_capi.CnCopySeg * 16)()
+        tab = d.get("_slots")
+        if tab is None or d.get("_slots_key") != self.rewards.data_ptr():
+            tab = self._slots = self._slot_table()
+            self._slots_key = self.rewards.data_ptr()
+        dev, n = self.device, 0
+        for (dst, dptr, nbytes), src in zip(tab[s], srcs):
+            if src is None:
+                continue
+            if (n < 16 and src.dtype is dst.dtype and src.numel() * src.element_size() == nbytes and src.is_contiguous()
+                    and (src.device == dev if src.is_cuda else src.is_pinned())):
+                sptr = src.data_ptr()
+                if sptr != dptr:
                     g = segs[n]
-                    g.dst, g.src, g.bytes = dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size()
+                    g.dst, g.src, g.bytes = dptr, sptr, nbytes
                     n += 1
             else:
                 dst.copy_(src.reshape(dst.shape) if src.numel() == dst.numel() else src, non_blocking=True)
         if n:
-            from . import _capi
-            with torch.cuda.device(self.device):      # cn_copy_segments calls cudaSetDevice: keep the caller's device
-                _capi.check(self._lib, self._lib.cn_copy_segments(segs, n, self.device.index or 0, C.c_void_p(
-                    torch.cuda.current_stream(self.device).cuda_stream)), "cn_copy_segments")
+            rc = self._lib.cn_copy_segments(segs, n, dev.index or 0, self._capi.raw_stream(dev.index or 0))
+            if rc:
+                self._capi.check(self._lib, rc, "cn_copy_segments")
         self.step = (s + 1) % self.num_steps
 
     def rollout_step_zero_copy(self, engine, env, deterministic=False):

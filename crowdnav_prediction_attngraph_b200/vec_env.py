@@ -242,6 +242,12 @@ class CudaCrowdVecEnv(object):
             off += nb
         self._outp = _capi.CnStepPtrs(*[self._out[k].data_ptr() if k in self._out else None
                                         for k, _ in _capi.CnStepPtrs._fields_])
+        self._host_np = self._host_packed.numpy()
+        self._np_layout, off = {}, 0            # field -> (byte offset, byte length, numpy dtype) inside the packed buffer
+        for k, dt in layout:
+            nb = N * torch.empty(0, dtype=dt).element_size()
+            self._np_layout[k] = (off, off + nb, self._host[k].numpy().dtype)
+            off += nb
         self._t_start = time.time()
         self.closed = False
         _trace("engine CudaCrowdVecEnv N=%d (of %d, offset %d) H=%d const_vel=%d phase=%d device=%s gst=0" % (
@@ -257,14 +263,13 @@ class CudaCrowdVecEnv(object):
         return t, ptrs
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return _capi.raw_stream(self.device.index or 0)
 
     # ------------------------------------------------------------------ VecEnv surface
     def reset(self):
         self._flip ^= 1
         obs, ptrs = self._obs_bufs[self._flip]
-        with torch.cuda.device(self.device):
-            _capi.check(self.lib, self.lib.cn_env_reset(self._h, C.byref(ptrs), self._stream()), "cn_env_reset")
+        _capi.check(self.lib, self.lib.cn_env_reset(self._h, C.byref(ptrs), self._stream()), "cn_env_reset")
         return dict(obs)
 
     def step_device(self, actions, obs_out=None, reward_out=None, not_done_out=None):
@@ -298,24 +303,36 @@ class CudaCrowdVecEnv(object):
                     and not_done_out.dtype == torch.float32      # the kernel stores float 0.0 / 1.0
                 vals["not_done"] = not_done_out.data_ptr()
             outp = _capi.CnStepPtrs(*[vals.get(k) for k, _ in _capi.CnStepPtrs._fields_])
-        with torch.cuda.device(self.device):
-            _capi.check(self.lib, self.lib.cn_env_step(self._h, C.c_void_p(actions.data_ptr()), C.byref(ptrs),
-                                                       C.byref(outp), self._stream()), "cn_env_step")
+        # the C entry points restore the caller's current device themselves (CnDeviceGuard): no context manager here
+        rc = self.lib.cn_env_step(self._h, C.c_void_p(actions.data_ptr()), C.byref(ptrs), C.byref(outp), self._stream())
+        if rc:
+            _capi.check(self.lib, rc, "cn_env_step")
         return dict(obs), reward, self._out["done"], self._out["info"]
 
     def step_async(self, actions):
         self._pending = self.step_device(actions)
 
+    def _fetch(self):
+        """Packed step outputs (reward, done, info, episode stats: 25 B/env) -> pinned host buffer, then wait."""
+        hp, dp = self._host_packed, self._out_packed
+        rc = self.lib.cn_fetch_sync(C.c_void_p(hp.data_ptr()), C.c_void_p(dp.data_ptr()), dp.numel() * dp.element_size(),
+                                    self.device.index or 0, self._stream())
+        if rc:
+            _capi.check(self.lib, rc, "cn_fetch_sync")
+
     def step_wait(self):
         obs, _, _, _ = self._pending
-        self._host_packed.copy_(self._out_packed, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        h = self._host
-        reward = h["reward"].clone().unsqueeze(1)
-        done = h["done"].numpy().astype(np.bool_)
-        infos = LazyInfos(h["info"].numpy().copy(), h["info_aux"].numpy().copy(), done, h["ep_ret"].numpy().copy(),
-                          h["ep_len"].numpy().copy(), self._t_start)
-        return obs, reward, done, infos
+        return (obs,) + self._host_results()
+
+    def _host_results(self):
+        """(reward CPU [N,1], done np.bool_[N], lazy infos) from ONE snapshot of the pinned mirror (the mirror is
+        overwritten by the next step; the snapshot belongs to the caller)."""
+        self._fetch()
+        snap = self._host_np.copy()
+        f = {k: snap[a:b].view(dt) for k, (a, b, dt) in self._np_layout.items()}
+        done = f["done"].view(np.bool_)
+        infos = LazyInfos(f["info"], f["info_aux"], done, f["ep_ret"], f["ep_len"], self._t_start)
+        return torch.from_numpy(f["reward"]).unsqueeze(1), done, infos
 
     def step(self, actions):
         self.step_async(actions)
@@ -449,17 +466,16 @@ class CudaPretextVecEnv(object):
         self.closed = False
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return _capi.raw_stream(self.device.index or 0)
 
     def _process(self, obs, reward):
         self._flip ^= 1
         sp = self._sp[self._flip]
         vm = obs['visible_masks']
-        with torch.cuda.device(self.device):
-            _capi.check(self.lib, self.lib.cn_gst_step(
-                self._h, C.c_void_p(obs['robot_node'].data_ptr()), C.c_void_p(obs['spatial_edges'].data_ptr()),
-                C.c_void_p(vm.data_ptr()), C.c_void_p(reward.data_ptr()) if reward is not None else None,
-                C.c_void_p(self._pen.data_ptr()), C.c_void_p(sp.data_ptr()), self._stream()), "cn_gst_step")
+        _capi.check(self.lib, self.lib.cn_gst_step(
+            self._h, C.c_void_p(obs['robot_node'].data_ptr()), C.c_void_p(obs['spatial_edges'].data_ptr()),
+            C.c_void_p(vm.data_ptr()), C.c_void_p(reward.data_ptr()) if reward is not None else None,
+            C.c_void_p(self._pen.data_ptr()), C.c_void_p(sp.data_ptr()), self._stream()), "cn_gst_step")
         out = dict(obs)
         out['spatial_edges'] = sp
         out['visible_masks'] = vm.bool() if vm.dtype != torch.bool else vm
@@ -478,13 +494,7 @@ class CudaPretextVecEnv(object):
     def step(self, actions):
         obs, reward, done, info = self.step_device(actions)
         e = self.env
-        e._host_packed.copy_(e._out_packed, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        h = e._host
-        done_np = h["done"].numpy().astype(np.bool_)
-        infos = LazyInfos(h["info"].numpy().copy(), h["info_aux"].numpy().copy(), done_np, h["ep_ret"].numpy().copy(),
-                          h["ep_len"].numpy().copy(), e._t_start)
-        return obs, h["reward"].clone().unsqueeze(1), done_np, infos
+        return (obs,) + e._host_results()
 
     def talk2Env(self, data):
         return np.ones(self.num_envs, dtype=bool)

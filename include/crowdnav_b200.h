@@ -96,6 +96,12 @@ typedef struct cn_copy_seg {
   size_t bytes;
 } cn_copy_seg;
 int cn_copy_segments(const cn_copy_seg *segs, int n, int device, void *stream);
+/* cn_copy_segments sources may also be PINNED host memory (the reward / mask tensors train.py builds on the host,
+ * rl/networks/storage.py:70-86 `insert`): the kernel reads them over the bus, no separate cudaMemcpyAsync per tensor.
+ *
+ * replaces: the result read-back of ShmemVecEnv.step_wait (rl/networks/shmem_vec_env.py:75-80: pipe recv + shared-memory
+ * read of every worker) -- ONE device->pinned-host copy of the packed step outputs on `stream`, then a wait for the stream. */
+int cn_fetch_sync(void *h_dst, const void *d_src, size_t bytes, int device, void *stream);
 
 /* BASELINE config 3: GST trajectory predictor + VecPretextNormalize processing (one fused launch per step).
  * replaces: VecPretextNormalize.reset / process_obs_rew (rl/vec_env/vec_pretext_normalize.py:85-191) and
