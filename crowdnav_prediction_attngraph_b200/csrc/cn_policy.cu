@@ -40,12 +40,17 @@ struct cn_policy {
   long dbg_launch_idx = 0;   // launch index within the current step (CN_PDL_WINDOW debugging)
   bool launch_error;  // a launch or a GEMM output map failed (cn_last_error has the stage and the reason)
   const char* cur_stage = nullptr;   // stage name of the launches being enqueued (error reports)
-  bool fuse_qkv;      // QKV projection + human-human attention in ONE kernel (cn_qkv_attn.cuh; CN_FUSE_QKV=0 disables)
+  bool fuse_qkv;      // QKV projection + human-human attention in ONE kernel (cn_qkv_attn.cuh; opt-in, CN_FUSE_QKV=1)
   TcMat tWqkvH;       // folded QKV weight, rows head-major: [8][Q 64 | K 64 | V 64][512]
   CUtensorMap qa_ah, qa_al, qa_bh, qa_bl;   // 32-wide (SWIZZLE_64B) boxes of tE2 and tWqkvH for the fused kernel
   float* bqkvH = nullptr;
   int* tile_tab = nullptr;   // row tiles of the fused kernel (cn_qkv_tiles_kernel)
   cudaEvent_t ev_tiles;
+  // human-human attention instance: R queries of an environment per warp (CN_ATTN_R = 1 (default), 2 or 4; measured on
+  // B200 at 4096 envs: 0.065 / 0.070 / 0.085 ms -- sharing K / V rows between queries does not pay, the kernel is bound by
+  // load latency at ~4 keys per query, not by L1 delivery)
+  void (*attn_kernel)(const float*, const int*, const int*, const int*, const int*, float*, __half*, __half*);
+  int attn_warps;
   int qkv_chunks;     // 1 (default): single pass; 2 (CN_QKV_CHUNKS=2): QKV + attention in two row chunks with overlap
   bool finalized;
   std::map<std::string, std::vector<float>> host;
@@ -334,8 +339,15 @@ int cn_policy_create(const cn_policy_config* cfg, cn_policy** out) {
     p->pdl = !(pd && pd[0] == '0');
     const char* qc = getenv("CN_QKV_CHUNKS");
     p->qkv_chunks = (qc && qc[0] == '2') ? 2 : 1;
+    const char* ar = getenv("CN_ATTN_R");
+    const int attn_r = ar ? atoi(ar) : 1;
+    p->attn_kernel = attn_r == 1 ? cn_hh_attention_kernel<1, 4, 4> : (attn_r == 4 ? cn_hh_attention_kernel<4, 2, 2> : cn_hh_attention_kernel<2, 4, 4>);
+    p->attn_warps = attn_r == 4 ? 2 : 4;
     const char* fq = getenv("CN_FUSE_QKV");
-    p->fuse_qkv = cfg->gemm_mode == 1 && p->qkv_chunks == 1 && !(fq && fq[0] == '0') && p->N <= QA_MAX_ENVS && p->H <= 128;
+    // opt-in (CN_FUSE_QKV=1): parity green, but the in-epilogue attention is bound by the SM's shared-memory bandwidth,
+    // which it shares with the operand fetch of the MMAs -- 0.109-0.129 ms against 0.073 + 0.064 ms of the two-kernel path
+    // in stage terms and no gain per rollout step (profiles/r2_qkv_attn_fused.md)
+    p->fuse_qkv = cfg->gemm_mode == 1 && p->qkv_chunks == 1 && (fq && fq[0] == '1') && p->N <= QA_MAX_ENVS && p->H <= 128;
   }
   cudaEventCreateWithFlags(&p->ev_tiles, cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
@@ -627,25 +639,25 @@ int cn_policy_act(cn_policy* p, const cn_act_ptrs* d, void* stream) {
     } else if (p->qkv_chunks == 1) {
       gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc);
       mark(p, st, 4);
-      launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, nullptr,
+      launch_k(p, p->attn_kernel, dim3(p->num_sms * 64 / p->attn_warps), dim3(p->attn_warps * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, nullptr,
                                                                              nullptr, ah, al);
     } else {
     gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mid);
     cudaEventRecord(p->ev_fork3, st);
     cudaStreamWaitEvent(p->st3, p->ev_fork3, 0);
-    launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 8), dim3(CN_ATTN_WARPS * 32), 0, p->st3, p->qkv, p->row_start, p->row_env, mid, nullptr,
+    launch_k(p, p->attn_kernel, dim3(p->num_sms * 32 / p->attn_warps), dim3(p->attn_warps * 32), 0, p->st3, p->qkv, p->row_start, p->row_env, mid, nullptr,
                                                                               nullptr, ah, al);
     cudaEventRecord(p->ev_join3, p->st3);
     gemm_tc(p, st, p->tE2, p->tWqkv, M, 1536, 512, 256, p->bqkv, CN_ACT_NONE, out32(p->qkv, 1536), mc, 0, 1 << 30, mid);
     mark(p, st, 4);
-    launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, mid, nullptr,
+    launch_k(p, p->attn_kernel, dim3(p->num_sms * 64 / p->attn_warps), dim3(p->attn_warps * 32), 0, st, p->qkv, p->row_start, p->row_env, mc, mid, nullptr,
                                                                            ah, al);
     cudaStreamWaitEvent(st, p->ev_join3, 0);
     }
   } else {
     gemm(p, st, p->e2, 512, p->Wqkv, 512, p->bqkv, p->qkv, 1536, M, 1536, 512, CN_ACT_NONE, 0, ALL, mc);
     mark(p, st, 4);
-    launch_k(p, cn_hh_attention_kernel, dim3(p->num_sms * 16), dim3(CN_ATTN_WARPS * 32), 0, st, p->qkv, p->row_start, p->row_env, p->mc, nullptr,
+    launch_k(p, p->attn_kernel, dim3(p->num_sms * 64 / p->attn_warps), dim3(p->attn_warps * 32), 0, st, p->qkv, p->row_start, p->row_env, p->mc, nullptr,
                                                                            p->ao, nullptr, nullptr);
   }
   mark(p, st, 5);

@@ -335,10 +335,14 @@ __global__ void __launch_bounds__(256) cn_embed1_kernel(const float* __restrict_
 //  * soft-max is two-pass (pass 1: scores -> shared memory + running max; pass 2: p = exp(s - max),
 //    P V): one exp per (key, head) and no rescaling of the accumulators;
 //  * the p of the other three chunks come from the neighbouring lanes of the aligned 4-lane group.
+//  * template parameter R: R query rows of the SAME environment share every K / V row a warp loads (each loaded
+//    element then feeds R FMAs).  Measured (B200, 4096 envs): R = 1 0.065 ms, R = 2 0.070 ms, R = 4 0.085 ms -- the
+//    L1 delivery rate (one FMA per 4 bytes) is not what limits the kernel, the extra registers cost occupancy; R = 1
+//    is the default, the others stay selectable with CN_ATTN_R for other crowd sizes.
 #define CN_ATTN_WARPS 4
 #define CN_ATTN_MAXKEYS 128
-#define CN_ATTN_KB 4          // keys whose rows are in flight together
-__global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(const float* __restrict__ qkv,
+template <int R, int KB /* keys whose rows are in flight together */, int W /* warps per CTA */>
+__global__ void __launch_bounds__(W * 32) cn_hh_attention_kernel(const float* __restrict__ qkv,
                                                                              const int* __restrict__ row_start,
                                                                              const int* __restrict__ row_env,
                                                                              const int* __restrict__ mc_ptr,
@@ -347,126 +351,147 @@ __global__ void __launch_bounds__(CN_ATTN_WARPS * 32) cn_hh_attention_kernel(con
                                                                              __half* __restrict__ out_hi,
                                                                              __half* __restrict__ out_lo) {
   cn_pdl_prologue();
-  __shared__ float sc[CN_ATTN_WARPS][CN_ATTN_MAXKEYS][8];       // scores [key][half * 4 + chunk]
+  __shared__ float sc[W][R][CN_ATTN_MAXKEYS][8];                // scores [query][key][half * 4 + chunk]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mc = *mc_ptr;
-  const int nwarps = gridDim.x * CN_ATTN_WARPS;
+  const int mc = cn_ld_after_wait(mc_ptr);
+  const int nwarps = gridDim.x * W;
   const float scale = 0.125f;   // 1/sqrt(head_dim = 64); torch scales q before q k^T
   const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
   const int own = (b0 ? 2 : 0) + (b1 ? 1 : 0);                  // head chunk this lane finishes
-  const int col = ((lane >> 4) << 2) + own;                     // its column in sc[][][8]
+  const int col = ((lane >> 4) << 2) + own;                     // its column in sc[][][][8]
   const int grp = lane & ~3;
-  float (*myc)[8] = sc[warp];
-  // grid-stride over the compacted rows: the launch is sized to the machine, not to the worst case
-  const int r_first = r0_ptr ? *r0_ptr : 0;                    // row chunk [r_first, mc) of this launch
-  for (int r = r_first + blockIdx.x * CN_ATTN_WARPS + warp; r < mc; r += nwarps) {
+  // grid-stride over the compacted rows: the launch is sized to the machine, not to the worst case.  The warp that
+  // meets the first row of a group of R consecutive queries of an environment does the whole group.
+  const int r_first = r0_ptr ? cn_ld_after_wait(r0_ptr) : 0;   // row chunk [r_first, mc) of this launch
+  for (int r = r_first + blockIdx.x * W + warp; r < mc; r += nwarps) {
     const int e = row_env[r];
     const int row0 = row_start[e];
     const int n = row_start[e + 1] - row0;
-    float4 q[4];
-    {
-      const float4* qv = reinterpret_cast<const float4*>(qkv + (size_t)r * 1536) + lane;
+    if ((r - row0) % R != 0) continue;
+    const int nq = (row0 + n - r) < R ? (row0 + n - r) : R;     // queries r .. r + nq - 1 (warp-uniform)
+    float4 q[R][4];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int ru = u < nq ? r + u : r;                        // a missing query repeats the first (results dropped)
+      const float4* qv = reinterpret_cast<const float4*>(qkv + (size_t)ru * 1536) + lane;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float4 a = __ldg(qv + 32 * c);
-        q[c] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+        q[u][c] = make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
       }
     }
-    // ---- pass 1: scores.  Keys are processed in blocks of CN_ATTN_KB with all of a block's K rows requested
-    // before the first is used: the kernel is load-latency bound (ncu: long-scoreboard stalls = 70 % of the
-    // issue latency at ~4 keys per query), so memory-level parallelism matters more than instruction count.
-    float m = -INFINITY;
-    for (int jb = 0; jb < n; jb += CN_ATTN_KB) {
-      float4 kr[CN_ATTN_KB][4];
+    // ---- pass 1: scores.  Keys are processed in blocks of KB with all of a block's K rows requested before the
+    // first is used (memory-level parallelism).
+    float m[R];
 #pragma unroll
-      for (int t = 0; t < CN_ATTN_KB; ++t) {
+    for (int u = 0; u < R; ++u) m[u] = -INFINITY;
+    for (int jb = 0; jb < n; jb += KB) {
+      float4 kr[KB][4];
+#pragma unroll
+      for (int t = 0; t < KB; ++t) {
         const int j = (jb + t < n) ? jb + t : n - 1;             // clamped: the duplicate load hits L1
         const float4* kv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j) * 1536 + 512) + lane;
 #pragma unroll
         for (int c = 0; c < 4; ++c) kr[t][c] = __ldg(kv + 32 * c);
       }
 #pragma unroll
-      for (int t = 0; t < CN_ATTN_KB; ++t) {
+      for (int t = 0; t < KB; ++t) {
         if (jb + t < n) {                                        // warp-uniform
-          float s[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float x = q[c].x * kr[t][c].x;
-            x = fmaf(q[c].y, kr[t][c].y, x); x = fmaf(q[c].z, kr[t][c].z, x); x = fmaf(q[c].w, kr[t][c].w, x);
-            s[c] = x;
+          for (int u = 0; u < R; ++u) {
+            float s[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float x = q[u][c].x * kr[t][c].x;
+              x = fmaf(q[u][c].y, kr[t][c].y, x); x = fmaf(q[u][c].z, kr[t][c].z, x); x = fmaf(q[u][c].w, kr[t][c].w, x);
+              s[c] = x;
+            }
+            // packed butterfly over the 16 lanes of the half: 4 values -> 1 per lane
+            const float x0 = b0 ? s[0] : s[2], x1 = b0 ? s[1] : s[3];               // what the xor-1 partner keeps
+            const float r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
+            const float u0 = (b0 ? s[2] : s[0]) + r0, u1 = (b0 ? s[3] : s[1]) + r1; // chunks (2 b0, 2 b0 + 1) over 2 lanes
+            const float y = b1 ? u0 : u1;
+            float v = (b1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, y, 2);          // chunk `own` over 4 lanes
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);                                // ... over the 16 lanes of the half
+            m[u] = fmaxf(m[u], v);
+            if ((lane & 12) == 0) sc[warp][u][jb + t][col] = v;                     // lanes 0-3 and 16-19
           }
-          // packed butterfly over the 16 lanes of the half: 4 values -> 1 per lane
-          const float x0 = b0 ? s[0] : s[2], x1 = b0 ? s[1] : s[3];               // what the xor-1 partner keeps
-          const float r0 = __shfl_xor_sync(0xffffffffu, x0, 1), r1 = __shfl_xor_sync(0xffffffffu, x1, 1);
-          const float u0 = (b0 ? s[2] : s[0]) + r0, u1 = (b0 ? s[3] : s[1]) + r1; // chunks (2 b0, 2 b0 + 1) over 2 lanes
-          const float y = b1 ? u0 : u1;
-          float v = (b1 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, y, 2);          // chunk `own` over 4 lanes
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);                                // ... over the 16 lanes of the half
-          m = fmaxf(m, v);
-          if ((lane & 12) == 0) myc[jb + t][col] = v;                             // lanes 0-3 and 16-19
         }
       }
     }
     __syncwarp();
     // ---- pass 2: p = exp(s - max), accumulate P V
-    float4 acc[4];
+    float4 acc[R][4];
+    float l[R];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float l = 0.0f;
-    for (int jb = 0; jb < n; jb += CN_ATTN_KB) {
-      float4 vr[CN_ATTN_KB][4];
+    for (int u = 0; u < R; ++u) {
+      l[u] = 0.0f;
 #pragma unroll
-      for (int t = 0; t < CN_ATTN_KB; ++t) {
+      for (int c = 0; c < 4; ++c) acc[u][c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    for (int jb = 0; jb < n; jb += KB) {
+      float4 vr[KB][4];
+#pragma unroll
+      for (int t = 0; t < KB; ++t) {
         const int j = (jb + t < n) ? jb + t : n - 1;
         const float4* vv = reinterpret_cast<const float4*>(qkv + (size_t)(row0 + j) * 1536 + 1024) + lane;
 #pragma unroll
         for (int c = 0; c < 4; ++c) vr[t][c] = __ldg(vv + 32 * c);
       }
 #pragma unroll
-      for (int t = 0; t < CN_ATTN_KB; ++t) {
+      for (int t = 0; t < KB; ++t) {
         if (jb + t < n) {
-          const float p = expf(myc[jb + t][col] - m);
-          l += p;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            // chunk c was finished by the lane of this 4-lane group with (b0, b1) = (c >> 1, c & 1)
-            const float pc = __shfl_sync(0xffffffffu, p, grp | (c >> 1) | ((c & 1) << 1));
-            acc[c].x = fmaf(pc, vr[t][c].x, acc[c].x); acc[c].y = fmaf(pc, vr[t][c].y, acc[c].y);
-            acc[c].z = fmaf(pc, vr[t][c].z, acc[c].z); acc[c].w = fmaf(pc, vr[t][c].w, acc[c].w);
+          for (int u = 0; u < R; ++u) {
+            const float p = expf(sc[warp][u][jb + t][col] - m[u]);
+            l[u] += p;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // chunk c was finished by the lane of this 4-lane group with (b0, b1) = (c >> 1, c & 1)
+              const float pc = __shfl_sync(0xffffffffu, p, grp | (c >> 1) | ((c & 1) << 1));
+              acc[u][c].x = fmaf(pc, vr[t][c].x, acc[u][c].x); acc[u][c].y = fmaf(pc, vr[t][c].y, acc[u][c].y);
+              acc[u][c].z = fmaf(pc, vr[t][c].z, acc[u][c].z); acc[u][c].w = fmaf(pc, vr[t][c].w, acc[u][c].w);
+            }
           }
         }
       }
     }
-    __syncwarp();                                      // sc is reused by this warp's next row
-    const float linv = 1.0f / l;
+    __syncwarp();                                      // sc is reused by this warp's next group
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float inv = __shfl_sync(0xffffffffu, linv, grp | (c >> 1) | ((c & 1) << 1));
-      acc[c].x *= inv; acc[c].y *= inv; acc[c].z *= inv; acc[c].w *= inv;
-    }
-    if (out) {
-      float4* dst = reinterpret_cast<float4*>(out + (size_t)r * 512) + lane;
+    for (int u = 0; u < R; ++u) {
+      if (u < nq) {                                    // warp-uniform
+        const float linv = 1.0f / l[u];
+        float4 a[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) dst[32 * c] = acc[c];
-    }
-    if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
-      uint2* dh = reinterpret_cast<uint2*>(out_hi + (size_t)r * 512) + lane;
-      uint2* dl = reinterpret_cast<uint2*>(out_lo + (size_t)r * 512) + lane;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float cv[4] = {fminf(fmaxf(acc[c].x, -65504.0f), 65504.0f), fminf(fmaxf(acc[c].y, -65504.0f), 65504.0f),
-                             fminf(fmaxf(acc[c].z, -65504.0f), 65504.0f), fminf(fmaxf(acc[c].w, -65504.0f), 65504.0f)};
-        uint32_t ph[2], pl[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const __half h0 = __float2half_rn(cv[2 * u]), h1 = __float2half_rn(cv[2 * u + 1]);
-          const __half l0 = __float2half_rn(cv[2 * u] - __half2float(h0)), l1 = __float2half_rn(cv[2 * u + 1] - __half2float(h1));
-          ph[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          pl[u] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int c = 0; c < 4; ++c) {
+          const float inv = __shfl_sync(0xffffffffu, linv, grp | (c >> 1) | ((c & 1) << 1));
+          a[c] = make_float4(acc[u][c].x * inv, acc[u][c].y * inv, acc[u][c].z * inv, acc[u][c].w * inv);
         }
-        dh[32 * c] = make_uint2(ph[0], ph[1]);
-        dl[32 * c] = make_uint2(pl[0], pl[1]);
+        if (out) {
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)(r + u) * 512) + lane;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[32 * c] = a[c];
+        }
+        if (out_hi) {     // (hi, lo) fp16 split = A operand of the tensor-core out-projection
+          uint2* dh = reinterpret_cast<uint2*>(out_hi + (size_t)(r + u) * 512) + lane;
+          uint2* dl = reinterpret_cast<uint2*>(out_lo + (size_t)(r + u) * 512) + lane;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float cv[4] = {fminf(fmaxf(a[c].x, -65504.0f), 65504.0f), fminf(fmaxf(a[c].y, -65504.0f), 65504.0f),
+                                 fminf(fmaxf(a[c].z, -65504.0f), 65504.0f), fminf(fmaxf(a[c].w, -65504.0f), 65504.0f)};
+            uint32_t ph[2], pl[2];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const __half h0 = __float2half_rn(cv[2 * w]), h1 = __float2half_rn(cv[2 * w + 1]);
+              const __half l0 = __float2half_rn(cv[2 * w] - __half2float(h0)), l1 = __float2half_rn(cv[2 * w + 1] - __half2float(h1));
+              ph[w] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+              pl[w] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            }
+            dh[32 * c] = make_uint2(ph[0], ph[1]);
+            dl[32 * c] = make_uint2(pl[0], pl[1]);
+          }
+        }
       }
     }
   }   // row loop

@@ -46,6 +46,12 @@ __device__ __forceinline__ uint64_t qa_desc64(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
+__device__ __forceinline__ float4 qa_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // head-major copy of the folded QKV weight / bias: dst row h * 192 + s * 64 + d <- src row s * 512 + h * 64 + d
 __global__ void cn_head_major_kernel(const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ wh,
                                      float* __restrict__ bh) {
@@ -92,7 +98,7 @@ cn_qkv_attn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                    const float* __restrict__ bias /* [8][192] head-major */, float inv_scale, const int* tile_tab,
                    const int* row_start, const int* row_env, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                   int dbg /* diagnostics: 1 = skip the attention, 2 = also skip the K / V staging */) {
+                   int dbg /* diagnostics: 1 = skip the attention, 2 = skip the K / V staging, 4 = skip the key loop, 8 = skip the stores */) {
   cn_pdl_trigger();
   constexpr int K = 512, NUM_KB = K / QA_BK;
   constexpr uint32_t TMEM_COLS = 512;                           // two 192-column accumulators at column 0 and 256
@@ -203,15 +209,14 @@ cn_qkv_attn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
       asm volatile("bar.sync 1, 256;" ::: "memory");            // the previous tile's attention has left K / V / bias
       if (et < QA_BN) bias_s[et] = __ldg(bias + head * QA_BN + et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      // both warps of a quadrant take Q_h of their row (scaled by 1/sqrt(64)): they split the keys of the attention
       float qv[64];
-      if (role == 0) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tc::tmem_ld32(tmem_acc + (uint32_t)(c * 32), v);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_acc + (uint32_t)(c * 32), v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) qv[c * 32 + j] = fmaf(__uint_as_float(v[j]), inv_scale, bias_s[c * 32 + j]) * 0.125f;
-        }
+        for (int j = 0; j < 32; ++j) qv[c * 32 + j] = fmaf(__uint_as_float(v[j]), inv_scale, bias_s[c * 32 + j]) * 0.125f;
       }
       {
         // role 0: columns 64..95 (K 0..31); role 1: columns 96..127 (K 32..63), 128..159 and 160..191 (V)
@@ -239,43 +244,56 @@ cn_qkv_attn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8 * ab) : "memory");
       asm volatile("bar.sync 1, 256;" ::: "memory");            // K, V of all 128 rows are in shared memory
-      if (role == 0 && r < cnt && !(dbg & 1)) {
+      // ---- attention of row r over the keys of its environment.  The two warps of a quadrant sit on the same
+      // scheduler (they hide each other's shared-memory latency): both compute the scores and the soft-max weights
+      // of their row, each accumulates and writes one half (32) of the head's 64 output columns.
+      if (r < cnt && !(dbg & 1)) {
         const int e = row_env[m0 + r];
         const int j0 = row_start[e] - m0, j1 = row_start[e + 1] - m0;      // keys: the rows of the same environment
-        float mx = -INFINITY, l = 0.0f, o[64];
+        float mx = -INFINITY, l = 0.0f, o[32];
 #pragma unroll
-        for (int d = 0; d < 64; ++d) o[d] = 0.0f;
-        for (int j = j0; j < j1; ++j) {
-          const float4* kr = reinterpret_cast<const float4*>(kv + (size_t)j * 128);
-          const int jx = j & 15;
+        for (int d = 0; d < 32; ++d) o[d] = 0.0f;
+        for (int j = j0; j < ((dbg & 4) ? j0 : j1); ++j) {
+          const uint32_t krow = kv_s + (uint32_t)j * 512u;
+          const uint32_t jx = (uint32_t)(j & 15);
           float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float4 k4 = kr[c ^ jx];
-            s0 = fmaf(qv[4 * c], k4.x, s0); s1 = fmaf(qv[4 * c + 1], k4.y, s1);
-            s2 = fmaf(qv[4 * c + 2], k4.z, s2); s3 = fmaf(qv[4 * c + 3], k4.w, s3);
+          for (int hb = 0; hb < 2; ++hb) {                       // 8 loads in flight, then their 32 FMAs
+            float4 kk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) kk[c] = qa_lds128(krow + ((((uint32_t)(hb * 8 + c)) ^ jx) << 4));
+            // consumed LAST-loaded first: the (ordered, volatile) loads must all be issued before the first FMA can
+            // go, so ptxas keeps the eight of them in flight instead of recycling four temporaries (seen in SASS)
+#pragma unroll
+            for (int c = 7; c >= 0; --c) {
+              const int d = 4 * (hb * 8 + c);
+              s0 = fmaf(qv[d], kk[c].x, s0); s1 = fmaf(qv[d + 1], kk[c].y, s1);
+              s2 = fmaf(qv[d + 2], kk[c].z, s2); s3 = fmaf(qv[d + 3], kk[c].w, s3);
+            }
           }
-          const float s = (s0 + s1) + (s2 + s3);
-          if (s > mx) {                                         // online soft-max: rescale only when the maximum moves
-            const float f = expf(mx - s);                       // exp(-inf) = 0 on the first key
+          float4 vv[8];                                         // this warp's half of V_j, requested before the exp
+#pragma unroll
+          for (int c = 0; c < 8; ++c) vv[c] = qa_lds128(krow + 256u + ((((uint32_t)(role * 8 + c)) ^ jx) << 4));
+          const float sc = (s0 + s1) + (s2 + s3);
+          if (sc > mx) {                                        // online soft-max: rescale only when the maximum moves
+            const float f = expf(mx - sc);                      // exp(-inf) = 0 on the first key
             l *= f;
 #pragma unroll
-            for (int d = 0; d < 64; ++d) o[d] *= f;
-            mx = s;
+            for (int d = 0; d < 32; ++d) o[d] *= f;
+            mx = sc;
           }
-          const float p = expf(s - mx);
-          l += p;
+          const float pw = expf(sc - mx);
+          l += pw;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float4 v4 = kr[16 + (c ^ jx)];
-            o[4 * c] = fmaf(p, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(p, v4.y, o[4 * c + 1]);
-            o[4 * c + 2] = fmaf(p, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(p, v4.w, o[4 * c + 3]);
+          for (int c = 7; c >= 0; --c) {
+            o[4 * c] = fmaf(pw, vv[c].x, o[4 * c]); o[4 * c + 1] = fmaf(pw, vv[c].y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(pw, vv[c].z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pw, vv[c].w, o[4 * c + 3]);
           }
         }
         const float inv = 1.0f / l;
-        const size_t ob = (size_t)(m0 + r) * 512 + head * 64;
+        const size_t ob = (size_t)(m0 + r) * 512 + head * 64 + role * 32;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t ph[4], pl[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -286,8 +304,10 @@ cn_qkv_attn_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             ph[t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
             pl[t] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
           }
-          *reinterpret_cast<uint4*>(out_hi + ob + 8 * c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(out_lo + ob + 8 * c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          if (!(dbg & 8)) {
+            *reinterpret_cast<uint4*>(out_hi + ob + 8 * c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(out_lo + ob + 8 * c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
         }
       }
     }

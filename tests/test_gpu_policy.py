@@ -120,13 +120,15 @@ def test_cuda_policy_varnum_input_size_2_both_gemm_modes():
         assert (value.cpu() - rv).abs().max() < TOL and (mean.cpu() - rm).abs().max() < TOL and (h1.cpu() - rh).abs().max() < TOL
 
 
-@pytest.mark.parametrize("H,seed", [(20, 11), (50, 12)])
-def test_benchmarked_tensor_core_path_at_full_size_matches_oracle(H, seed):
+@pytest.mark.parametrize("H,seed,fused", [(20, 11, "0"), (50, 12, "0"), (20, 13, "1"), (50, 14, "1")])
+def test_benchmarked_tensor_core_path_at_full_size_matches_oracle(H, seed, fused, monkeypatch):
     """The configuration bench.py times: gemm_mode = 1 (tcgen05 3xFP16), N = 4096 environments, device-side row
     compaction with random detected_human_num (ragged rows, many 128-row tiles per CTA: persistent tile loop, both TMEM
     accumulators in flight), 3 consecutive calls (the double-buffered outputs and the hidden-state feedback) -- against
-    the plain PyTorch fp32 oracle (oracle/policy_ref.py), action mean / hidden state 1e-4, value 1e-4 of its scale."""
+    the plain PyTorch fp32 oracle (oracle/policy_ref.py), action mean / hidden state 1e-4, value 1e-4 of its scale.
+    fused = "1": the opt-in single-kernel QKV projection + human-human attention (cn_qkv_attn.cuh, CN_FUSE_QKV=1)."""
     from oracle.policy_ref import PolicyRef
+    monkeypatch.setenv("CN_FUSE_QKV", fused)          # read by cn_policy_create
     from crowdnav_prediction_attngraph_b200.policy import make_reference_like_state_dict
     N = 4096
     sd = make_reference_like_state_dict(12, seed=seed)
