@@ -53,7 +53,7 @@ ABI_VERSION = 3          # include/crowdnav_b200.h CN_ABI_VERSION
 
 EXPORTS = [
     "cn_last_error", "cn_abi_version", "cn_env_create", "cn_env_destroy", "cn_env_reset", "cn_env_step",
-    "cn_env_step_host", "cn_env_state_bytes", "cn_env_state_copy", "cn_env_launch_count",
+    "cn_env_step_host", "cn_env_state_bytes", "cn_env_state_copy", "cn_env_launch_count", "cn_env_profile", "cn_env_stage_ms",
     "cn_policy_create", "cn_policy_destroy", "cn_policy_set_param", "cn_policy_finalize",
     "cn_policy_act", "cn_policy_launch_count", "cn_policy_last_rows", "cn_policy_profile", "cn_policy_stage_count",
     "cn_policy_stage_name", "cn_policy_stage_ms", "cn_copy_segments", "cn_fetch_sync",
@@ -134,6 +134,10 @@ def load_library(path=None):
     lib.cn_fetch_sync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.cn_env_launch_count.restype = C.c_int64
     lib.cn_env_launch_count.argtypes = [C.c_void_p]
+    lib.cn_env_profile.restype = C.c_int
+    lib.cn_env_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.cn_env_stage_ms.restype = C.c_int
+    lib.cn_env_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.cn_policy_create.argtypes = [C.POINTER(CnPolicyConfig), C.POINTER(C.c_void_p)]
     lib.cn_policy_destroy.argtypes = [C.c_void_p]
     lib.cn_policy_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]

@@ -97,6 +97,10 @@ struct CnState {
   // diagnostics of the last step (parity tests)
   float *last_hvx, *last_hvy;        // ORCA output velocities [N][H]
   int *orca_nlines, *orca_fail;      // [N][H]
+  // pre-solve (cn_env_kernels.cu, mode 3 -> mode 2): the humans' ORCA solve of the NEXT step, computed on the side stream
+  // while the policy runs, handed to that step's finishing pass
+  float *pre_vx, *pre_vy;            // [N][H]
+  int *pre_nlf;                      // [N][H] nl | (fail + 1) << 8
   // per-step event flags written by the step kernel, consumed by the event kernel:
   // 0 = nothing, 1 = goal dynamics (respawn / goal change) pending, 2 = episode finished (reset)
   uint8_t *evt;                      // [N]

@@ -129,9 +129,12 @@ CN_HD void cn_phase_load(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
 // ------------------------------------------------------------------------------------------
 // Phase ORCA, part 1 (per thread = one human's rvo2 simulator, crowd_sim.py:680-703, orca.py:64-117):
 // neighbour selection and ORCA half-plane construction into `lines` (sorted by distance).
+// `mark`: value written to sim_exists for a simulator this call creates: 1, or 2 = PROVISIONAL when the solve runs ahead of
+// the step it belongs to (pre-solve on the side stream, cn_env_kernels.cu): the finishing pass of that step promotes 2 / 3 -> 1;
+// a full solve treats anything but 1 as missing, so an abandoned pre-solve (state uploaded in between) leaves no trace.
 template <int MAXH>
 CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e, int h, CnLineStore lines, int& nl_out,
-                         float& vmax_out, CnF2& pref_out, bool use_fov = true) {
+                         float& vmax_out, CnF2& pref_out, bool use_fov = true, uint8_t mark = 1) {
   const int H = p.H;            // slots (row pitch of the [N][H] arrays)
   const int hn = s.hn;          // live humans: the simulator of human h holds the other hn - 1 (orca.py:80-95)
   const size_t i = cn_idx(p, e, h);
@@ -141,7 +144,8 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
   // --- cached simulator parameters (frozen at creation; orca.py:80-95 only updates pos/vel)
   if (p.randomize) {
     // (re)created when missing or when humans joined / left since its creation (orca.py:80-82: agent count mismatch)
-    if (!g.sim_exists[i] || (p.hrange > 0 && g.sim_n[i] != (uint8_t)hn)) {
+    const uint8_t ex = g.sim_exists[i];
+    if (ex != 1 || (p.hrange > 0 && g.sim_n[i] != (uint8_t)hn)) {
       g.sim_n[i] = (uint8_t)hn;
       g.sim_nd[i] = (float)g.nd_global[e];
       g.sim_rself[i] = (float)(s.rad[h] + pad + p.orca_safety_space);
@@ -151,7 +155,8 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
         const bool v = cn_in_fov(s.px[h], s.py[h], s.vx[h], s.vy[h], s.px[j], s.py[j], fov);
         g.sim_rother[i * H + j] = (float)((v ? s.rad[j] : 0.3) + pad + p.orca_safety_space);
       }
-      g.sim_exists[i] = 1;
+      // a pre-solve that RE-creates an official simulator (human count changed) marks it 3: still "exists" to a reader
+      g.sim_exists[i] = mark == 2 ? ((ex == 1 || ex == 3) ? (uint8_t)3 : (uint8_t)2) : (uint8_t)1;
     }
     nd = g.sim_nd[i]; rself = g.sim_rself[i]; vmax = g.sim_vmax[i];
   } else {
@@ -159,7 +164,7 @@ CN_HD void cn_orca_build(const CnParams& p, const CnState& g, CnEnvSh& s, int e,
     nd = (float)p.orca_neighbor_dist;
     rself = (float)(s.rad[h] + pad + p.orca_safety_space);
     vmax = (float)s.vpref[h];
-    g.sim_exists[i] = 1;
+    if (g.sim_exists[i] != 1) g.sim_exists[i] = mark;
   }
   // --- preferred velocity (orca.py:98-100), fp64 then narrowed
   const double dvx = s.gx[h] - s.px[h], dvy = s.gy[h] - s.py[h];

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
   if (mode == 1) {
     if (active && h == 0) { s->done = 1; s->info = 0; s->reward = 0.0; s->reset_flag = 0; s->nvis = 0; s->goal_flag = 0; s->lp3_cost = 0; s->hn = 0; }
   } else if (active) {
-    cn_phase_load(p, g, *s, e, h, action);
+    cn_phase_load(p, g, *s, e, h, mode == 3 ? nullptr : action);
   }
   __syncthreads();
   // live = this thread's slot holds a human (slots [hn, H) are empty when sim.human_num_range > 0)
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
     float vmax = 0.0f;
     CnF2 pref = f2(0.0f, 0.0f);
     result = f2(0.0f, 0.0f);
-    if (live) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref, use_fov);
+    if (live) cn_orca_build<MAXH>(p, g, *s, e, h, W.of(lane), nl, vmax, pref, use_fov, mode == 3 ? (uint8_t)2 : (uint8_t)1);
     __syncwarp();
     cn_orca_lp2_warp(hco, W, nl, vmax, pref, result, fail);           // per half-warp; idle lanes with nl = 0
     if (fail >= 0) {
@@ -166,10 +166,28 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
   };
   if (mode != 1 && p.social_force) {
     if (live) cn_sf_action(p, g, *s, e, h);                           // social-force humans: no linear programs
+  } else if (mode == 2) {
+    // finishing pass of a step whose ORCA solve already ran on the side stream (mode 3, same state: the humans do not
+    // see the robot, so their solve does not depend on this step's action)
+    if (live) {
+      const size_t i = cn_idx(p, e, h);
+      const int nlf = g.pre_nlf[i];
+      cn_orca_finish(p, g, *s, e, h, f2(g.pre_vx[i], g.pre_vy[i]), nlf & 0xff, (nlf >> 8) - 1);
+      if (g.sim_exists[i] >= 2) g.sim_exists[i] = 1;                  // simulators the pre-solve created become official
+    }
   } else if (mode != 1) {
     CnF2 result; int nl, fail;
     orca_solve(true, result, nl, fail);                               // get_human_actions (crowd_sim.py:680-703)
     if (live && fail >= 0) atomicAdd(&s->lp3_cost, 1);              // cost estimate for the next step's balancing
+    if (mode == 3) {                                                  // pre-solve: publish the result and stop
+      if (live) {
+        const size_t i = cn_idx(p, e, h);
+        g.pre_vx[i] = result.x; g.pre_vy[i] = result.y; g.pre_nlf[i] = nl | ((fail + 1) << 8);
+      }
+      __syncthreads();
+      if (active && h == 0) g.lp_cost[e] = s->lp3_cost;
+      return;
+    }
     if (p.test_phase) {
       // phase 'test': ground-truth look-ahead (crowd_sim_pred.py:136-138 -> crowd_sim_var_num.py:180-206):
       // lookahead_steps nested solves on a scratch copy of the joint state kept in the same shared arrays
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(288, 2) cn_env_step_kernel(CnParams p, CnState
   }
   if (active && h == 0) {
     g.evt[e] = (uint8_t)cn_event_flag(p, g, *s, e);
-    g.lp_cost[e] = s->lp3_cost;
+    if (mode != 2) g.lp_cost[e] = s->lp3_cost;                        // mode 2: the pre-solve already stored it
   }
 }
 
@@ -410,8 +428,14 @@ struct cn_env {
   // side stream of the event kernel (overlaps the caller's policy work between two steps)
   cudaStream_t side;
   cudaEvent_t ev_step, ev_side;
+  // optional timing of the env launches (cn_env_profile): [0..1] step / finishing kernel on the caller's stream,
+  // [2..3] event kernel(s) + balancing, [3..4] pre-solve kernel on the side stream
+  bool profile = false;
+  cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool side_pending;      // an event kernel is in flight: the next launch on the caller's stream waits for it
   bool use_side;
+  bool presolve;          // run the humans' ORCA solve of the next step on the side stream behind the event kernel
+  bool presolved;         // ... and one is in flight / done for the current state
   bool balance;           // re-deal environments to CTAs by their linearProgram3 load after every step (side stream)
   bool prep_dirty;        // a state upload may have invalidated the prepared episodes
   // staging for the host-buffer entry point
@@ -495,8 +519,13 @@ int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const 
   }
   const int grid = (env->p.N + env->epb - 1) / env->epb;
   KernelFn fn = pick_kernel(env->maxh);
+  // mode 0 with a pre-solve of this state done on the side stream (joined above) -> finishing pass only (mode 2)
+  const int kmode = (mode == 0 && env->presolved) ? 2 : mode;
+  env->presolved = false;
+  if (env->profile) cudaEventRecord(env->pev[0], stream);
   fn<<<grid, env->threads, env->smem_bytes, stream>>>(env->p, env->g, d_action, to_obs(o), out, env->epb, env->line_cap,
-                                                      mode);
+                                                      kmode);
+  if (env->profile) cudaEventRecord(env->pev[1], stream);
   env->launches += 1;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel launch: %s", cudaGetErrorString(err));
@@ -504,12 +533,26 @@ int launch_step(cn_env* env, const float* d_action, const cn_obs_ptrs* o, const 
   err = cudaEventRecord(env->ev_step, stream);
   if (err == cudaSuccess) err = cudaStreamWaitEvent(env->side, env->ev_step, 0);
   if (err != cudaSuccess) return cn_set_error("fork to side stream: %s", cudaGetErrorString(err));
+  if (env->profile) cudaEventRecord(env->pev[2], env->side);
   rc = event_kernel(env, 0, env->side);
   if (rc) return rc;
   if (env->balance && mode == 0) {
     cn_env_balance_kernel<<<1, 1024, 0, env->side>>>(env->p, env->g, grid, env->epb);
     env->launches += 1;
   }
+  if (env->profile) cudaEventRecord(env->pev[3], env->side);
+  if (env->presolve) {
+    // PRE-SOLVE: the humans never see the robot (robot.visible = False is the only supported setting), so their ORCA
+    // solve of the NEXT step depends on the state this step leaves behind (after the event kernel's goal changes and
+    // the installed episodes) and on nothing the policy is about to compute.  It runs here, on the side stream, while
+    // the caller's stream runs the policy; the next step only finishes (robot move, reward, integration, observation).
+    fn<<<grid, env->threads, env->smem_bytes, env->side>>>(env->p, env->g, nullptr, to_obs(o), out, env->epb, env->line_cap, 3);
+    env->launches += 1;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return cn_set_error("cn_env_step_kernel (pre-solve) launch: %s", cudaGetErrorString(err));
+    env->presolved = true;
+  }
+  if (env->profile) cudaEventRecord(env->pev[4], env->side);
   err = cudaEventRecord(env->ev_side, env->side);
   if (err != cudaSuccess) return cn_set_error("cudaEventRecord(side): %s", cudaGetErrorString(err));
   env->side_pending = true;
@@ -559,6 +602,11 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   {
     const char* ns = getenv("CN_NO_SIDE_STREAM");       // debugging / profiling aid
     env->use_side = !(ns && ns[0] == '1');
+    // pre-solve of the next step's ORCA on the side stream (launch_step); CN_PRESOLVE=0 disables.  Not with social-force
+    // humans (no linear programs to move) nor in the test phase (its look-ahead solves stay with the step).
+    const char* ps = getenv("CN_PRESOLVE");
+    env->presolve = env->use_side && !(ps && ps[0] == '0') && cfg->human_policy == 0 && cfg->phase != 2;
+    env->presolved = false;
   }
   err = cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaEventCreateWithFlags(&env->ev_step, cudaEventDisableTiming);
@@ -628,6 +676,7 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   A(prep_mt, N * 624); A(prep_mt_pos, N);
   A(last_hvx, NH); A(last_hvy, NH); A(orca_nlines, NH); A(orca_fail, NH); A(evt, N); A(spawn_overflow, N);
   A(lp_cost, N); A(defer_list, N); A(defer_ctl, 8); A(hn, N); A(prep_hn, N); A(sim_n, NH);
+  A(pre_vx, NH); A(pre_vy, NH); A(pre_nlf, NH);
   A(hwx, cfg->human_policy ? NH : (size_t)4); A(hwy, cfg->human_policy ? NH : (size_t)4);
 #undef A
   if (!rc) {
@@ -747,6 +796,7 @@ int cn_env_destroy(cn_env* env) {
   if (env->side) cudaStreamDestroy(env->side);
   if (env->ev_step) cudaEventDestroy(env->ev_step);
   if (env->ev_side) cudaEventDestroy(env->ev_side);
+  for (int i = 0; i < 5; ++i) if (env->pev[i]) cudaEventDestroy(env->pev[i]);
   for (void* q : env->allocs) cudaFree(q);
   delete env;
   return 0;
@@ -814,7 +864,12 @@ int cn_env_state_copy(cn_env* env, const char* name, void* h_buf, size_t bytes, 
     err = dir ? cudaMemcpy(it->second.ptr, h_buf, bytes, cudaMemcpyHostToDevice)
               : cudaMemcpy(h_buf, it->second.ptr, bytes, cudaMemcpyDeviceToHost);
   if (err != cudaSuccess) return cn_set_error("cn_env_state_copy(%s): %s", name, cudaGetErrorString(err));
-  if (dir) env->prep_dirty = true;
+  if (dir) { env->prep_dirty = true; env->presolved = false; }     // an uploaded state invalidates the pre-solve in flight
+  if (!dir && strcmp(name, "sim_exists") == 0) {
+    // 2 = created, 3 = re-created by a pre-solve that belongs to the NEXT step: report the state as of the last step
+    unsigned char* b = static_cast<unsigned char*>(h_buf);
+    for (size_t i = 0; i < bytes; ++i) if (b[i] >= 2) b[i] = (unsigned char)(b[i] == 3);
+  }
   return 0;
 }
 
@@ -844,6 +899,32 @@ int cn_fetch_sync(void* h_dst, const void* d_src, size_t bytes, int device, void
   cudaError_t err = cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize((cudaStream_t)stream);
   if (err != cudaSuccess) return cn_set_error("cn_fetch_sync: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+int cn_env_profile(cn_env* env, int enable) {
+  if (!env) return cn_set_error("cn_env_profile: null argument");
+  CnDeviceGuard guard(env->device);
+  if (enable && !env->pev[0]) {
+    for (int i = 0; i < 5; ++i)
+      if (cudaEventCreate(&env->pev[i]) != cudaSuccess) return cn_set_error("cn_env_profile: cudaEventCreate failed");
+  }
+  env->profile = enable != 0;
+  return 0;
+}
+
+int cn_env_stage_ms(cn_env* env, float* out3) {
+  if (!env || !out3) return cn_set_error("cn_env_stage_ms: null argument");
+  if (!env->pev[0]) return cn_set_error("cn_env_stage_ms: call cn_env_profile(env, 1) before the step");
+  CnDeviceGuard guard(env->device);
+  cudaError_t err = cudaDeviceSynchronize();
+  out3[0] = out3[1] = out3[2] = 0.0f;
+  if (err == cudaSuccess) err = cudaEventElapsedTime(&out3[0], env->pev[0], env->pev[1]);
+  if (err == cudaSuccess && env->use_side) {
+    err = cudaEventElapsedTime(&out3[1], env->pev[2], env->pev[3]);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&out3[2], env->pev[3], env->pev[4]);
+  }
+  if (err != cudaSuccess) return cn_set_error("cn_env_stage_ms: %s", cudaGetErrorString(err));
   return 0;
 }
 

@@ -152,6 +152,12 @@ int cn_env_state_copy(cn_env *env, const char *name, void *h_buf, size_t bytes, 
 
 /* Number of kernels this library launched since the handle was created (bench gpu_launches).  */
 int64_t cn_env_launch_count(cn_env *env);
+/* measurement hooks (no reference equivalent): with profiling enabled every step records CUDA events around its launches;
+ * cn_env_stage_ms synchronises and returns, for the LAST step, out3[0] = step kernel on the caller's stream (the whole
+ * step, or only its finishing pass when the ORCA solve ran ahead on the side stream), out3[1] = event kernel(s) +
+ * balancing pass and out3[2] = pre-solve of the next step, both on the engine's side stream (ms).                      */
+int cn_env_profile(cn_env *env, int enable);
+int cn_env_stage_ms(cn_env *env, float *out3);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Attention-graph policy (rl/networks/model.py:56-80, selfAttn_srnn_temp_node.py:360-449).    */

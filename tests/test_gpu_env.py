@@ -193,3 +193,35 @@ def test_heavy_event_path_equals_warp_path_at_config4_shape(monkeypatch):
         assert np.array_equal(finals[0][k], finals[2][k]), k
     d = [f["deferrals"] for f in finals]
     assert d[1] > 0 and d[1] >= d[0] >= 0 and d[2] == 0, d
+
+
+@pytest.mark.parametrize("over", [dict(human_num=20), dict(human_num=30, randomize_attributes=1, random_goal_changing=1,
+                                                           goal_change_chance=0.5)])
+def test_presolve_on_side_stream_equals_in_step_solve(over, monkeypatch):
+    """The default engine solves the humans' ORCA of step t+1 on the side stream right after step t (they never see the
+    robot, so nothing the policy computes enters it) and step t+1 only finishes; CN_PRESOLVE=0 keeps the solve inside the
+    step.  Same seeds and actions => bit-identical observations, rewards, dones, infos and final state, through episode
+    ends, goal changes and an uploaded state in the middle (which must discard the pre-solve in flight)."""
+    N, T = 256, 260
+    monkeypatch.setenv("CN_PRESOLVE", "1")
+    a = _engine(num_envs=N, seed=77, **over)
+    monkeypatch.setenv("CN_PRESOLVE", "0")
+    b = _engine(num_envs=N, seed=77, **over)
+    oa, obb = a.reset(), b.reset()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    for t in range(T):
+        for k in oa:
+            assert torch.equal(oa[k], obb[k]), (k, t)
+        act = torch.rand(N, 2, device="cuda", generator=gen) * 2.4 - 1.2
+        if t == 130:        # upload a state between two steps: positions of half of the humans jump by 0.25 m
+            for env in (a, b):
+                px = env.get_state("hpx")
+                px.reshape(N, -1)[:, ::2] += 0.25
+                env.set_state("hpx", px)
+        oa, ra, da, ia = a.step_device(act)
+        obb, rb, db, ib = b.step_device(act)
+        assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(ia, ib), t
+    for name in ("hpx", "hpy", "hvx", "hvy", "hgx", "hgy", "rpx", "rpy", "sim_exists", "last_hvx", "last_hvy", "orca_nlines",
+                 "orca_fail", "mt_pos", "case_counter"):
+        assert np.array_equal(a.get_state(name), b.get_state(name)), name
+    assert a.launch_count() > b.launch_count()        # the pre-solve is one more launch per step
