@@ -602,10 +602,14 @@ int cn_env_create(const cn_config* cfg, cn_env** out) {
   {
     const char* ns = getenv("CN_NO_SIDE_STREAM");       // debugging / profiling aid
     env->use_side = !(ns && ns[0] == '1');
-    // pre-solve of the next step's ORCA on the side stream (launch_step); CN_PRESOLVE=0 disables.  Not with social-force
-    // humans (no linear programs to move) nor in the test phase (its look-ahead solves stay with the step).
+    // pre-solve of the next step's ORCA on the side stream (launch_step).  Not with social-force humans (no linear
+    // programs to move) nor in the test phase (its look-ahead solves stay with the step).  Default: on for crowds of up
+    // to 32 human slots (measured: 20 humans 0.455 -> 0.442 ms/step, e2e 0.534 -> 0.501), off above (50 humans 2.15 ->
+    // 2.19, 100 humans 4.9 -> 5.1 ms/step: the many short CTAs of the large-H solve take SMs from the policy's GEMMs
+    // instead of filling gaps); CN_PRESOLVE=1 / 0 forces it.
     const char* ps = getenv("CN_PRESOLVE");
-    env->presolve = env->use_side && !(ps && ps[0] == '0') && cfg->human_policy == 0 && cfg->phase != 2;
+    const bool want = ps ? ps[0] != '0' : (cfg->human_num + cfg->human_num_range <= 32);
+    env->presolve = env->use_side && want && cfg->human_policy == 0 && cfg->phase != 2;
     env->presolved = false;
   }
   err = cudaStreamCreateWithFlags(&env->side, cudaStreamNonBlocking);

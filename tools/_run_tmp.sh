@@ -1,7 +1,6 @@
-timeout 500 python bench.py > gpurun_out/r2_bench_1gpu_final.json 2> gpurun_out/r2_bench_1gpu_final.err; python - <<'PY'
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 90 --warmup 10 --no-cpu-baseline > gpurun_out/r2_bench_2gpu_final.json 2> gpurun_out/r2_bench_2gpu_final.err; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2_bench_1gpu_final.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ['value','ms_per_step','gpu_launches']}, d['e2e'], d['update']['ms'], {k:(v['ms_per_step'], v.get('update',{}).get('ms')) for k,v in d['configs'].items()}, d['cpu_baseline']['value'])
-print(d['roofline']); print(d['breakdown_ms'])
+d=json.loads(open('gpurun_out/r2_bench_2gpu_final.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ['value','ms_per_step','n_gpus']}, d['e2e']['value'], d['update']['ms'], d['update']['ms_samples'], d['update']['allreduce_ms'], {k:(v['ms_per_step'], v.get('update',{}).get('ms')) for k,v in d['configs'].items()})
 PY
-tail -3 gpurun_out/r2_bench_1gpu_final.err
+tail -2 gpurun_out/r2_bench_2gpu_final.err
