@@ -225,3 +225,23 @@ def test_presolve_on_side_stream_equals_in_step_solve(over, monkeypatch):
                  "orca_fail", "mt_pos", "case_counter"):
         assert np.array_equal(a.get_state(name), b.get_state(name)), name
     assert a.launch_count() > b.launch_count()        # the pre-solve is one more launch per step
+
+
+def test_env_profile_hooks_time_the_step_launches():
+    """cn_env_profile / cn_env_stage_ms (measurement hooks behind bench.py's roofline): CUDA-event durations of the launch
+    on the caller's stream, of the event kernels and of the pre-solve on the side stream, for the last step."""
+    import ctypes as C
+    from crowdnav_prediction_attngraph_b200 import _capi
+    env = _engine(num_envs=512, human_num=20, seed=3)
+    env.reset()
+    buf = (C.c_float * 3)()
+    assert env.lib.cn_env_stage_ms(env._h, buf) != 0                    # not enabled yet: a loud error, not zeros
+    _capi.check(env.lib, env.lib.cn_env_profile(env._h, 1), "cn_env_profile")
+    act = torch.zeros(512, 2, device="cuda")
+    for _ in range(3):
+        env.step_device(act)
+    _capi.check(env.lib, env.lib.cn_env_stage_ms(env._h, buf), "cn_env_stage_ms")
+    step_ms, event_ms, presolve_ms = buf[0], buf[1], buf[2]
+    assert 0.0 < step_ms < 5.0 and 0.0 < event_ms < 5.0 and 0.0 < presolve_ms < 5.0
+    assert presolve_ms > step_ms            # 20 humans: the ORCA solve runs ahead, the step launch only finishes
+    _capi.check(env.lib, env.lib.cn_env_profile(env._h, 0), "cn_env_profile")

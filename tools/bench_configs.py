@@ -67,8 +67,33 @@ def run(name, steps, warmup):
     f1.record()
     torch.cuda.synchronize()
     ms_env = f0.elapsed_time(f1) / steps
+    # per-stage timing (CUDA events inside the library; profile mode serialises the side streams' joins)
+    import ctypes as C
+    from crowdnav_prediction_attngraph_b200 import _capi
+    lib = eng.lib
+    lib.cn_policy_profile(eng._h, 1)
+    lib.cn_env_profile(env._h, 1)
+    ns = lib.cn_policy_stage_count()
+    names = [lib.cn_policy_stage_name(i).decode() for i in range(ns)]
+    acc, est, reps = [0.0] * ns, [0.0] * 3, 5
+    for _ in range(reps):
+        s = rollouts.step
+        o = {k: rollouts.obs[k][s] for k in rollouts.obs}
+        value, action, logp, h_new = eng.act(o, rollouts.recurrent_hidden_states['human_node_rnn'][s], rollouts.masks[s])
+        buf = (C.c_float * ns)()
+        _capi.check(lib, lib.cn_policy_stage_ms(eng._h, buf, ns), "stage_ms")
+        nobs, rew, done, info = env.step_device(action)
+        ebuf = (C.c_float * 3)()
+        _capi.check(lib, lib.cn_env_stage_ms(env._h, ebuf), "env_stage_ms")
+        for i in range(ns):
+            acc[i] += buf[i] / reps
+        for i in range(3):
+            est[i] += ebuf[i] / reps
+        rollouts.insert(nobs, {'human_node_rnn': h_new}, action, logp, value, rew, (1.0 - done.float()).unsqueeze(1))
+    stages = {"env_step_kernel": est[0], "env_event_kernels_side": est[1], "env_presolve_side": est[2]}
+    stages.update({n: round(v, 4) for n, v in zip(names, acc)})
     overflow = int(env.get_state("spawn_overflow").sum())
-    print(json.dumps({"config": name, "env_kwargs": kw, "envs": N, "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3,
+    print(json.dumps({"config": name, "stages_ms": stages, "env_kwargs": kw, "envs": N, "ms_per_step": ms, "env_steps_per_s": N / ms * 1e3,
                       "env_only_ms_per_step": ms_env, "valid_human_rows": int(eng.lib.cn_policy_last_rows(eng._h)),
                       "spawn_overflow_envs": overflow, "defer_ctl": [int(x) for x in env.get_state("defer_ctl")]}))
     del eng, policy, env
