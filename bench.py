@@ -702,14 +702,15 @@ def run_ours(a):
     # caller's stream only finishes the step.  Their CUDA-event durations are added.
     env_ms = env_stage[0] + env_stage[2]
     env_gbs = B_ENV * N / (env_ms / 1000.0) / 1e9 if env_ms > 0 else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch at N=4096, H=20 (ncu --set full,
-    # profiles/r1_env_step_kernel_summary.md, capture r1_env_step_v6): 11.24 MB + 0.45 MB
-    env_traffic = 11.69e6 * N / 4096.0 if HUMANS == 20 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of the two launches at N=4096, H=20 (ncu --set full of the final code,
+    # profiles/r2_env_step_presolve_ncu_raw.csv): pre-solve 8.26 MB + 0.33 MB, finishing pass 8.30 MB + 0.01 MB -- the
+    # state is read twice since the solve runs ahead, 1.4x the algorithmic bytes
+    env_traffic = 16.90e6 * N / 4096.0 if HUMANS == 20 else None
     roof_env = {"kernel": "cn_env_step_kernel, pre-solve launch (side stream, %.4f ms) + finishing launch (%.4f ms): one rollout "
                           "step of %d envs; cn_env_event_kernel runs on the side stream" % (env_stage[2], env_stage[0], N),
                 "bound": "hbm",
                 "achieved": env_gbs, "peak": hbm, "unit": "GB/s", "frac": env_gbs / hbm, "traffic": env_traffic,
-                "traffic_source": "ncu capture profiles/r1_env_step_kernel_summary.md (v6), scaled by N/4096",
+                "traffic_source": "ncu --set full capture profiles/r2_env_step_presolve_ncu_raw.csv (both launches), scaled by N/4096",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", "launch_ms": env_ms,
                 "algorithmic_bytes_per_launch": B_ENV * N,
                 "note": "latency/divergence bound by construction (per-human ORCA LP), see DESIGN.md"}
