@@ -15,6 +15,10 @@
  *   - return value: 0 = ok, non-zero = error; cn_last_error() gives the message of the last
  *     failure on the calling thread.  A missing CUDA device is an error, never a CPU fallback.
  *   - one host thread per handle; handles on different GPUs are independent.
+ *   - current device: the per-step entry points (cn_env_reset / cn_env_step, cn_policy_act, cn_gst_step,
+ *     cn_copy_segments, cn_fetch_sync, cn_env_profile / cn_env_stage_ms) run on the handle's device and RESTORE the
+ *     caller's current device before returning; the set-up calls (create / destroy / set_param / finalize,
+ *     cn_env_state_copy, cn_env_step_host, cn_gst_reset) leave the handle's device current, like cudaSetDevice.
  */
 #ifndef CROWDNAV_B200_H
 #define CROWDNAV_B200_H
