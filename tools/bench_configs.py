@@ -16,6 +16,8 @@ CONFIGS = {
     "c2": (dict(human_num=20), 4096),
     "c4": (dict(human_num=50, randomize_attributes=1, random_goal_changing=1, goal_change_chance=0.5), 2048),
     "c2_h50": (dict(human_num=50), 4096),
+    # BASELINE config 5 as bench.py runs it (circle and arena x2, see bench.py EXTRA_CONFIGS)
+    "c5": (dict(human_num=100, circle_radius=2 * 6 * 2 ** 0.5, arena_size=12.0), 4096),
     "c1_varnum": (dict(human_num=5, const_vel=0), 4096),
     # BASELINE config 3: CrowdSimPredRealGST-v0 + VecPretextNormalize (GST predictor), H = 20, N = 4096
     "c3": (dict(human_num=20), 4096),
