@@ -13,7 +13,6 @@ import ctypes as C
 import math
 import os
 
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

@@ -6,7 +6,6 @@ Differences that do not change results: tensors are created directly on `device`
 `human_human_edge_rnn` hidden state (2.7 GB at N=4096, H=20 in the reference, storage.py:34) is a
 stride-0 expanded zero; `recurrent_generator` gathers minibatches with one index_select per
 tensor instead of a Python loop over environments (storage.py:208-223)."""
-import ctypes as C
 
 import torch
 
